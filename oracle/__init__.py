@@ -1,0 +1,1 @@
+"""CPU oracle (test infrastructure). Only tests/, __graft_entry__.smoke() and bench.py's CPU legs import this."""

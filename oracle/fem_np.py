@@ -1,0 +1,496 @@
+"""ORACLE (test infrastructure, not product code) -- P1/P0 finite-element restatement in NumPy/SciPy.
+
+PARITY UNPINNED: none of the element formulas exist in /root/reference (the plugins FluidOptim /
+PLaplacian / ADMMOptim named at 3d_admm.lua:1-3 are un-vendored, SURVEY.md section 0 + App. B).
+Every function states the script evidence it rests on.  The model:
+
+    L(u,q,lam,Lam) = J'(u) + (lam, grad u - q) + tau/2 |grad u - q|^2 + sum_i Lam_i g_i(u),  |q_T|_F <= sigma
+    g_vol(u)  = int det(I + grad u) dx - V_ref            (VolumeDefect,     3d_admm.lua:780,1167)
+    g_k(u)    = int (x_k + u_k) det(I + grad u) dx         (BarycenterDefect, 3d_admm.lua:1168)
+
+DoF layout: P1 index = vertex*dim + comp; P0 index = element*dim*dim + (row*dim + col)
+(l1..l9 = lambda00,01,02,10,..,22 -- 3d_admm.lua:343-351).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from .mesh_np import Mesh, p1_pattern
+
+# ------------------------------------------------------------------------------------------
+# element geometry
+# ------------------------------------------------------------------------------------------
+
+
+def geometry(mesh: Mesh):
+    """P1 gradients G (ne,d+1,d), element measure vol (ne,) (|det J|/d!  -- refined.ugx has 134
+    clockwise triangles), centroid xbar (ne,d)."""
+    d = mesh.dim
+    X = mesh.xyz[mesh.elems]                         # (ne,d+1,d)
+    J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))   # columns = edge vectors
+    Jinv = np.linalg.inv(J)
+    G = np.empty((mesh.ne, d + 1, d))
+    G[:, 1:, :] = Jinv                               # rows of J^-1
+    G[:, 0, :] = -Jinv.sum(axis=1)
+    vol = np.abs(np.linalg.det(J)) / math.factorial(d)
+    return G, vol, X.mean(axis=1)
+
+
+def grad_u(mesh: Mesh, G, u):
+    """(grad u)_{ij} = sum_a u_{a,i} G_{a,j}, constant per element. u is (nv*d,) or None (=0)."""
+    d = mesh.dim
+    if u is None:
+        return np.zeros((mesh.ne, d, d))
+    U = u.reshape(-1, d)[mesh.elems]                 # (ne,d+1,d)
+    return np.einsum("eai,eaj->eij", U, G)
+
+
+def cofactor(F):
+    """cof(F) = det(F) F^-T, written polynomially so that singular F is fine."""
+    d = F.shape[-1]
+    C = np.empty_like(F)
+    if d == 2:
+        C[:, 0, 0], C[:, 0, 1] = F[:, 1, 1], -F[:, 1, 0]
+        C[:, 1, 0], C[:, 1, 1] = -F[:, 0, 1], F[:, 0, 0]
+    else:
+        for i in range(3):
+            C[:, i, :] = np.cross(F[:, (i + 1) % 3, :], F[:, (i + 2) % 3, :])
+    return C
+
+
+def det(F):
+    d = F.shape[-1]
+    if d == 2:
+        return F[:, 0, 0] * F[:, 1, 1] - F[:, 0, 1] * F[:, 1, 0]
+    return np.einsum("ei,ei->e", F[:, 0, :], np.cross(F[:, 1, :], F[:, 2, :]))
+
+
+def _eps_det(mesh, G, F):
+    """T[e,a,i,b,j] = sum_k eps_{ijk} det[G_a, G_b, F_k]   (3D)   /   eps_{ij} det[G_a, G_b]  (2D)
+    = d cof(F)[e_j (x) G_b] : (e_i (x) G_a), the second derivative kernel of det(I+grad u)."""
+    d = mesh.dim
+    ne = mesh.ne
+    T = np.zeros((ne, d + 1, d, d + 1, d))
+    if d == 2:
+        D = G[:, :, None, 0] * G[:, None, :, 1] - G[:, :, None, 1] * G[:, None, :, 0]   # (ne,a,b)
+        T[:, :, 0, :, 1] = D
+        T[:, :, 1, :, 0] = -D
+    else:
+        for i in range(3):
+            j, k = (i + 1) % 3, (i + 2) % 3
+            # det[G_a, G_b, F_k] = G_a . (G_b x F_k)
+            GbxFk = np.cross(G[:, :, :], F[:, None, k, :])            # (ne,b,3)
+            T[:, :, i, :, j] = np.einsum("eax,ebx->eab", G, GbxFk)
+            GbxFj = np.cross(G[:, :, :], F[:, None, j, :])
+            T[:, :, i, :, k] = -np.einsum("eax,ebx->eab", G, GbxFj)
+    return T
+
+
+# ------------------------------------------------------------------------------------------
+# P1 assembly
+# ------------------------------------------------------------------------------------------
+
+
+def dirichlet_dofs(mesh: Mesh, subsets=("inlet", "wall", "outlet")):
+    """u = 0 on inlet, wall, outlet for every component; obstacle_surface free (3d_admm.lua:445-457)."""
+    m = mesh.vertex_mask(list(subsets))
+    return np.repeat(m, mesh.dim)
+
+
+def hessian_matrix(mesh: Mesh, u, c=1.0, lam_vol=0.0, lam_bary=None, dmask=None):
+    """DeformationEquation jacobian (3d_admm.lua:393-405, assembled at :972,:1008,... ):
+        K[(a,i),(b,j)] = vol*( c*delta_ij G_a.G_b
+                               + (Lam_vol + sum_k Lam_k (xbar_k+ubar_k)) * T[a,i,b,j]
+                               + sum_k Lam_k (delta_ik (C G_b)_j + delta_jk (C G_a)_i)/(d+1) )
+    followed by symmetric Dirichlet elimination (rows AND columns -> identity)."""
+    d = mesh.dim
+    ne = mesh.ne
+    G, vol, xbar = geometry(mesh)
+    lam_bary = np.zeros(d) if lam_bary is None else np.asarray(lam_bary, float)
+    K = np.zeros((ne, d + 1, d, d + 1, d))
+    GG = np.einsum("eax,ebx->eab", G, G)
+    for i in range(d):
+        K[:, :, i, :, i] += c * GG
+    if lam_vol != 0.0 or np.any(lam_bary != 0.0):
+        F = np.eye(d)[None] + grad_u(mesh, G, u)
+        C = cofactor(F)
+        ubar = np.zeros((ne, d)) if u is None else u.reshape(-1, d)[mesh.elems].mean(axis=1)
+        w = lam_vol + (xbar + ubar) @ lam_bary
+        K += w[:, None, None, None, None] * _eps_det(mesh, G, F)
+        CG = np.einsum("eij,eaj->eai", C, G)          # (C G_a)_i
+        for k in range(d):
+            if lam_bary[k] != 0.0:
+                K[:, :, k, :, :] += lam_bary[k] / (d + 1) * CG[:, None, :, :]
+                K[:, :, :, :, k] += lam_bary[k] / (d + 1) * CG[:, :, :, None]
+    K *= vol[:, None, None, None, None]
+    dof = (mesh.elems[:, :, None].astype(np.int64) * d + np.arange(d)[None, None, :])   # (ne,a,i)
+    rows = np.broadcast_to(dof[:, :, :, None, None], K.shape).ravel()
+    cols = np.broadcast_to(dof[:, None, None, :, :], K.shape).ravel()
+    n = mesh.nv * d
+    A = sp.csr_matrix((K.ravel(), (rows, cols)), shape=(n, n))
+    A.sum_duplicates()
+    if dmask is not None:
+        A = apply_dirichlet_sym(A, dmask)
+    return A
+
+
+def apply_dirichlet_sym(A, dmask):
+    keep = sp.diags((~dmask).astype(float))
+    A = keep @ A @ keep + sp.diags(dmask.astype(float))
+    A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def load_vector(mesh: Mesh, u, S=None, w=None, sign=1.0):
+    """Generic P1 element load vector (one kernel serves all RHS-type ElemDiscs):
+        f[(a,i)] = sign * vol * ( ((S + wc*C) G_a)_i + w_i det(F)/(d+1) ),   wc = w_vol + sum_k w_k (xbar_k+ubar_k)
+    with w = (w_vol, w_1..w_d), C = cof(F), F = I + grad u.
+      DeformationEquationRHS            S = lam + tau(grad u - q), w = Lam        sign +1  (3d_admm.lua:407-442,973)
+      DeformationEquationLargeProblemRHS S as above,               w = Lam + mult  sign +1  (3d_admm.lua:472-507,1081-1091)
+      VolumeConstraintSecondDerivative   S = 0,                     w = (1,0,0,0)   sign -1  (3d_admm.lua:559,954-959)
+      SecondDerivativeBarycenter(k)      S = 0,                     w = e_k         sign -1  (3d_admm.lua:577-617)
+    """
+    d = mesh.dim
+    G, vol, xbar = geometry(mesh)
+    gu = grad_u(mesh, G, u)
+    M = np.zeros((mesh.ne, d, d)) if S is None else S.copy()
+    f = np.zeros((mesh.ne, d + 1, d))
+    if w is not None and np.any(np.asarray(w) != 0.0):
+        w = np.asarray(w, float)
+        F = np.eye(d)[None] + gu
+        C = cofactor(F)
+        ubar = np.zeros((mesh.ne, d)) if u is None else u.reshape(-1, d)[mesh.elems].mean(axis=1)
+        wc = w[0] + (xbar + ubar) @ w[1:]
+        M = M + wc[:, None, None] * C
+        f += (det(F)[:, None, None] / (d + 1)) * w[None, None, 1:]
+    f += np.einsum("eij,eaj->eai", M, G)
+    f *= sign * vol[:, None, None]
+    out = np.zeros(mesh.nv * d)
+    dof = (mesh.elems[:, :, None].astype(np.int64) * d + np.arange(d)[None, None, :])
+    np.add.at(out, dof.ravel(), f.ravel())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# P0 (tensor) operations
+# ------------------------------------------------------------------------------------------
+
+
+def p0_grad(mesh, u):
+    G, _, _ = geometry(mesh)
+    return grad_u(mesh, G, u).reshape(-1)
+
+
+def mass_model(mesh, u, lam):
+    """MassModel (3d_admm.lua:650-674, assembled :899-900): diagonal P0 mass matrix diag = |T| and
+    defect = -|T| (grad u + lam); the script solves DiagQ q = defect and negates (:903-905)."""
+    d2 = mesh.dim ** 2
+    _, vol, _ = geometry(mesh)
+    diag = np.repeat(vol, d2)
+    rhs = -diag * (p0_grad(mesh, u) + lam)
+    return diag, rhs
+
+
+def project_frobenius(q, sigma, d):
+    """Testing(q_projected,q_piecewise,cmps,sigma) (3d_admm.lua:910): q * min(1, sigma/|q|_F) per element."""
+    Q = q.reshape(-1, d * d)
+    nrm = np.sqrt((Q * Q).sum(axis=1))
+    s = np.where(nrm > sigma, sigma / np.where(nrm > 0, nrm, 1.0), 1.0)
+    return (Q * s[:, None]).reshape(-1)
+
+
+def _svd2(Q):
+    """Closed-form SVD pieces of 2x2 matrices: returns s1>=s2>=0 and rotation angles."""
+    a, b, c, dd = Q[:, 0], Q[:, 1], Q[:, 2], Q[:, 3]
+    E, Fh, Gh, H = (a + dd) / 2, (a - dd) / 2, (c + b) / 2, (c - b) / 2
+    q_, r_ = np.hypot(E, H), np.hypot(Fh, Gh)
+    s1, s2 = q_ + r_, q_ - r_           # s2 may be negative (signed), |s2| is the singular value
+    a1, a2 = np.arctan2(Gh, Fh), np.arctan2(H, E)
+    theta, phi = (a2 - a1) / 2, (a2 + a1) / 2
+    return s1, s2, theta, phi
+
+
+def project_spectral(q, sigma):
+    """ProjectWithSpectralNorm (2d_admm.lua:902): clip the singular values of the 2x2 at sigma."""
+    Q = q.reshape(-1, 4)
+    s1, s2, theta, phi = _svd2(Q)
+    t1 = np.minimum(s1, sigma)
+    t2 = np.clip(s2, -sigma, sigma)
+    cp, sp_, ct, st = np.cos(phi), np.sin(phi), np.cos(theta), np.sin(theta)
+    # Q = R(phi) diag(s1,s2) R(theta)   with R(x) = [[cos,-sin],[sin,cos]]
+    out = np.empty_like(Q)
+    out[:, 0] = cp * t1 * ct - sp_ * t2 * st
+    out[:, 1] = -cp * t1 * st - sp_ * t2 * ct
+    out[:, 2] = sp_ * t1 * ct + cp * t2 * st
+    out[:, 3] = -sp_ * t1 * st + cp * t2 * ct
+    return out.reshape(-1)
+
+
+def max_frobenius_norm(mesh, u):
+    """MaximumFrobeniusNorm(u_old,cmps,"outer",4) (3d_admm.lua:916)."""
+    g = p0_grad(mesh, u).reshape(-1, mesh.dim ** 2)
+    return float(np.sqrt((g * g).sum(axis=1)).max())
+
+
+def max_spectral_norm(mesh, u):
+    """MaxSpectralNorm (2d_admm.lua:901): max over elements of the largest singular value."""
+    g = p0_grad(mesh, u).reshape(-1, 4)
+    s1, _, _, _ = _svd2(g)
+    return float(s1.max())
+
+
+def lambda_update_defect(mesh, u, qproj, tau=1.0):
+    """LambdaUpdate (3d_admm.lua:677-694, :1221): defect = -tau (grad u - q_proj) pointwise per P0 dof
+    (the script negates it and adds it to lambda: "lambda += tau(Grad_u-q_proj)", :1220-1223)."""
+    return -tau * (p0_grad(mesh, u) - qproj)
+
+
+# ------------------------------------------------------------------------------------------
+# integrals / norms
+# ------------------------------------------------------------------------------------------
+
+
+def l2norm_p1(mesh, v, comp):
+    """L2Norm(gf,"u1",4,"outer") (3d_admm.lua:1137-1146): exact P1 mass-matrix norm of one component."""
+    d = mesh.dim
+    _, vol, _ = geometry(mesh)
+    f = v.reshape(-1, d)[:, comp][mesh.elems]
+    val = (vol / ((d + 1) * (d + 2)) * ((f * f).sum(axis=1) + f.sum(axis=1) ** 2)).sum()
+    return math.sqrt(val)
+
+
+def l2norm_p0(mesh, v, comp):
+    """L2Norm(temp1_piecewise,"l1",4,"outer") (3d_admm.lua:1243-1251)."""
+    _, vol, _ = geometry(mesh)
+    f = v.reshape(-1, mesh.dim ** 2)[:, comp]
+    return math.sqrt((vol * f * f).sum())
+
+
+def volume_defect(mesh, u, vref):
+    """VolumeDefect(u,Vref,"outer",cmps,4,false,1,false) (3d_admm.lua:780,1167)."""
+    G, vol, _ = geometry(mesh)
+    F = np.eye(mesh.dim)[None] + grad_u(mesh, G, u)
+    return float((vol * det(F)).sum() - vref)
+
+
+def barycenter_defect(mesh, u):
+    """BarycenterDefect(u,cmps,"outer",4) (3d_admm.lua:1168): int (x_k+u_k) det(I+grad u) dx, k=1..d."""
+    d = mesh.dim
+    G, vol, xbar = geometry(mesh)
+    F = np.eye(d)[None] + grad_u(mesh, G, u)
+    ubar = u.reshape(-1, d)[mesh.elems].mean(axis=1)
+    return ((vol * det(F))[:, None] * (xbar + ubar)).sum(axis=0)
+
+
+# ------------------------------------------------------------------------------------------
+# multigrid + Krylov (obstacle_optim_3d_util.lua:9-43)
+# ------------------------------------------------------------------------------------------
+
+
+def prolongation(fine: Mesh, d: int):
+    """StdTransfer for nested P1: copies weight 1, edge midpoints 1/2,1/2; same for all comps."""
+    nvc, nvf = fine.nv_coarse, fine.nv
+    k = nvf - nvc
+    rows = np.concatenate([np.arange(nvc), nvc + np.arange(k), nvc + np.arange(k)])
+    cols = np.concatenate([np.arange(nvc), fine.parent_a, fine.parent_b])
+    vals = np.concatenate([np.ones(nvc), 0.5 * np.ones(2 * k)])
+    Ps = sp.csr_matrix((vals, (rows, cols)), shape=(nvf, nvc))
+    return sp.kron(Ps, sp.identity(d), format="csr")
+
+
+def gershgorin_lmax(A):
+    """Upper bound of lambda_max(D^-1 A): max_i sum_j |a_ij| / a_ii (used by the Chebyshev smoother)."""
+    rs = np.asarray(abs(A).sum(axis=1)).ravel()
+    return float((rs / A.diagonal()).max())
+
+
+class GMG:
+    """V(nu1,nu2) geometric multigrid, Galerkin RAP coarse operators, dense/LU base solve on level 0.
+    smoother: 'gs'   forward lexicographic Gauss-Seidel (what the reference asks for, u3:16 -- [UPSTREAM-UNVERIFIED] C5)
+              'cheb' Chebyshev(point-Jacobi) of degree nu on [lmax/4, lmax], lmax = 1.1*Gershgorin bound? no: = Gershgorin
+              'jac'  damped point Jacobi, omega = 0.66
+    The product (CUDA) path implements 'cheb' and 'jac'; 'gs' is kept for side-by-side iteration counts."""
+
+    def __init__(self, levels, A_top, dmasks, smoother="cheb", nu1=3, nu2=3, cheb_ratio=4.0, omega=0.66):
+        d = levels[0].dim
+        self.smoother, self.nu1, self.nu2, self.omega = smoother, nu1, nu2, omega
+        self.A = [None] * len(levels)
+        self.P = [None] * len(levels)
+        self.keep = [(~m).astype(float) for m in dmasks]
+        self.A[-1] = A_top.tocsr()
+        for l in range(len(levels) - 1, 0, -1):
+            P = prolongation(levels[l], d)
+            self.P[l] = P
+            Ac = (P.T @ self.A[l] @ P).tocsr()
+            self.A[l - 1] = apply_dirichlet_sym(Ac, dmasks[l - 1])
+        self.lu = spla.splu(self.A[0].tocsc())
+        self.dinv = [1.0 / A.diagonal() for A in self.A]
+        self.lmax = [gershgorin_lmax(A) for A in self.A]
+        self.cheb_ratio = cheb_ratio
+        if smoother == "gs":
+            self.LD = [sp.tril(A, 0, format="csr") for A in self.A]
+
+    # -- smoothers -------------------------------------------------------------------------
+    def _smooth(self, l, x, b, nu, zero_guess):
+        A = self.A[l]
+        if self.smoother == "gs":
+            for _ in range(nu):
+                r = b - A @ x
+                x = x + spla.spsolve_triangular(self.LD[l], r, lower=True)
+            return x
+        if self.smoother == "jac":
+            for it in range(nu):
+                r = b if (zero_guess and it == 0) else b - A @ x
+                x = x + self.omega * self.dinv[l] * r
+            return x
+        # Chebyshev (Saad, Alg. 12.1) preconditioned by point Jacobi
+        lmax = self.lmax[l]
+        lmin = lmax / self.cheb_ratio
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        sigma1 = theta / delta
+        rho = 1.0 / sigma1
+        r = b if zero_guess else b - A @ x
+        dvec = self.dinv[l] * r / theta
+        x = x + dvec
+        for _ in range(nu - 1):
+            rho_new = 1.0 / (2.0 * sigma1 - rho)
+            r = b - A @ x
+            dvec = rho_new * rho * dvec + (2.0 * rho_new / delta) * (self.dinv[l] * r)
+            x = x + dvec
+            rho = rho_new
+        return x
+
+    def vcycle(self, l, b):
+        if l == 0:
+            return self.lu.solve(b)
+        x = self._smooth(l, np.zeros_like(b), b, self.nu1, True)
+        r = b - self.A[l] @ x
+        bc = self.keep[l - 1] * (self.P[l].T @ r)
+        x = x + self.P[l] @ self.vcycle(l - 1, bc)
+        return self._smooth(l, x, b, self.nu2, False)
+
+    def apply(self, b):
+        return self.vcycle(len(self.A) - 1, b)
+
+
+def bicgstab(A, b, x0, precond, abs_tol=1e-10, max_it=3000, red_tol=0.0, check_half=False):
+    """Right-preconditioned BiCGStab with the reference's ConvCheck semantics (u3:32-38):
+    stop when |r|_2 < abs_tol (or |r|/|r0| < red_tol), fail after max_it. Returns (x, ok, its, r)."""
+    x = x0.copy()
+    r = b - A @ x
+    nr0 = nr = np.linalg.norm(r)
+    if nr < abs_tol:
+        return x, True, 0, r
+    rh = r.copy()
+    rho_old = alpha = omega = 1.0
+    v = np.zeros_like(b)
+    p = np.zeros_like(b)
+    for it in range(1, max_it + 1):
+        rho = rh @ r
+        if rho == 0.0 or not np.isfinite(rho):
+            return x, False, it, r
+        beta = (rho / rho_old) * (alpha / omega)
+        p = r + beta * (p - omega * v)
+        ph = precond(p)
+        v = A @ ph
+        alpha = rho / (rh @ v)
+        s = r - alpha * v
+        if check_half and np.linalg.norm(s) < abs_tol:
+            return x + alpha * ph, True, it, s
+        sh = precond(s)
+        t = A @ sh
+        tt = t @ t
+        omega = (t @ s) / tt if tt > 0 else 0.0
+        x = x + alpha * ph + omega * sh
+        r = s - omega * t
+        rho_old = rho
+        nr = np.linalg.norm(r)
+        if nr < abs_tol or nr < red_tol * nr0:
+            return x, True, it, r
+        if omega == 0.0 or not np.isfinite(nr):
+            return x, False, it, r
+    return x, False, max_it, r
+
+
+def cg_jacobi(diag, b, x0, damp=0.66, abs_tol=1e-9, max_it=2000):
+    """CG + Jacobi(0.66) + ConvCheck(2000,1e-9,0,true) on the diagonal P0 mass matrix (3d_admm.lua:701-703)."""
+    x = x0.copy()
+    r = b - diag * x
+    if np.linalg.norm(r) < abs_tol:
+        return x, True, 0
+    z = damp * r / diag
+    p = z.copy()
+    rz = r @ z
+    for it in range(1, max_it + 1):
+        q = diag * p
+        a = rz / (p @ q)
+        x += a * p
+        r -= a * q
+        if np.linalg.norm(r) < abs_tol:
+            return x, True, it
+        z = damp * r / diag
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, False, max_it
+
+
+# ------------------------------------------------------------------------------------------
+# lua-matrix restatement (host Schur algebra, 3d_admm.lua:1063-1078)
+# ------------------------------------------------------------------------------------------
+
+
+def lua_matrix_invert(S):
+    """matrix.invert (lua-matrix/matrix.lua:513-534) = Gauss-Jordan on [S | I] via dogauss (:450-507)
+    whose pivot rule picks the SMALLEST non-zero |entry| of the column (pivotOk, :422-442)."""
+    n = len(S)
+    m = [list(map(float, S[i])) + [1.0 if i == j else 0.0 for j in range(n)] for i in range(n)]
+    cols = 2 * n
+    for j in range(n):
+        imin, nmin = None, math.inf
+        for i in range(j, n):
+            a = abs(m[i][j])
+            if 0 < a < nmin:
+                imin, nmin = i, a
+        if imin is None:
+            return None
+        if imin != j:
+            m[j], m[imin] = m[imin], m[j]
+        for i in range(j + 1, n):
+            if m[i][j] != 0:
+                fac = m[i][j] / m[j][j]
+                m[i][j] = 0.0
+                for jj in range(j + 1, cols):
+                    m[i][jj] = m[i][jj] - fac * m[j][jj]
+    for j in range(n - 1, -1, -1):
+        div = m[j][j]
+        for jj in range(j + 1, cols):
+            m[j][jj] = m[j][jj] / div
+        for i in range(j - 1, -1, -1):
+            if m[i][j] != 0:
+                fac = m[i][j]
+                for jj in range(j + 1, cols):
+                    m[i][jj] = m[i][jj] - fac * m[j][jj]
+                m[i][j] = 0.0
+        m[j][j] = 1.0
+    return [row[n:] for row in m]
+
+
+def lua_matrix_mul(A, B):
+    """matrix.mul (lua-matrix/matrix.lua:223-237): plain triple loop, left-to-right accumulation."""
+    n, k, mcols = len(A), len(B), len(B[0])
+    out = [[0.0] * mcols for _ in range(n)]
+    for i in range(n):
+        for j in range(mcols):
+            num = A[i][0] * B[0][j]
+            for t in range(1, k):
+                num = num + A[i][t] * B[t][j]
+            out[i][j] = num
+    return out
