@@ -1,0 +1,150 @@
+// Shared infrastructure of libadmm_b200: error handling, device buffers, context, reductions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace ab {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define AB_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            throw ab::Error(-2, std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+#define AB_REQUIRE(cond, code, msg)                 \
+    do {                                            \
+        if (!(cond)) throw ab::Error((code), (msg)); \
+    } while (0)
+
+struct Comm;  // multi-GPU communicator (comm.cuh)
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // small device scratch for reductions: partial sums + ticket counters + result slots
+    double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
+    unsigned int* d_tickets = nullptr;
+    double* d_results = nullptr;    // kResultSlots doubles (device)
+    double* h_results = nullptr;    // pinned mirror
+    std::shared_ptr<Comm> comm;
+    static constexpr int kMaxBlocks = 1184;   // 148 SMs x 8
+    static constexpr int kMaxVals = 16;
+    static constexpr int kResultSlots = 64;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) AB_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T* h, size_t cnt, cudaStream_t s) { AB_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, s)); }
+    void upload(const std::vector<T>& h, cudaStream_t s) {
+        if (n < h.size()) alloc(h.size());
+        if (!h.empty()) { AB_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s)); AB_CUDA(cudaStreamSynchronize(s)); }
+    }
+    void zero(cudaStream_t s) { if (n) AB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+#define AB_LAUNCH(ctx, kernel, grid, block, smem, ...)                  \
+    do {                                                                \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        (ctx)->launches++;                                              \
+    } while (0)
+
+inline int grid_for(int64_t n, int block, int max_blocks) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side deterministic reduction: per-block partials + "last block" finalisation
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Reduce NV per-thread values over the whole grid. Block size must be 256. OP: 0 = sum, 1 = max.
+// Results are written to out[0..NV) by the last block to finish, summing the per-block partials in block
+// order (bitwise reproducible for a fixed launch configuration).
+template <int NV, int OP>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                            double* __restrict__ out) {
+    __shared__ double sm[NV][8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double w = OP == 0 ? warp_sum(v[k]) : warp_max(v[k]);
+        if (lane == 0) sm[k][warp] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double acc = sm[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) acc = OP == 0 ? acc + sm[threadIdx.x][w] : fmax(acc, sm[threadIdx.x][w]);
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = acc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        // NV values, gridDim.x partials each: warp k reduces value k (NV <= 8 warps) -- fixed order
+        for (int k = warp; k < NV; k += 8) {
+            double acc = OP == 0 ? 0.0 : -1.0e300;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) {
+                double p = partials[(size_t)b * NV + k];
+                acc = OP == 0 ? acc + p : fmax(acc, p);
+            }
+            acc = OP == 0 ? warp_sum(acc) : warp_max(acc);
+            if (lane == 0) out[k] = acc;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+}  // namespace ab

@@ -1,0 +1,485 @@
+// Linear-algebra kernels (fp64, sm_100a): BLAS-1 with fused reductions, BSR SpMV / residual /
+// Chebyshev-Jacobi smoother step, P1 transfers, Galerkin RAP, dense coarse inverse.
+// All are HBM-bandwidth bound; no tensor cores by design.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace ab {
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------
+// BLAS-1
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fill(int64_t n, double c, double* __restrict__ x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = c;
+}
+
+// out = a*x + b*y  (y may be null -> out = a*x). In-place allowed (out == x or out == y).
+__global__ void k_axpby(int64_t n, double a, const double* x, double b, const double* y, double* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (y) {
+        for (; i < n; i += stride) out[i] = a * x[i] + b * y[i];
+    } else {
+        for (; i < n; i += stride) out[i] = a * x[i];
+    }
+}
+
+// NX dot products <x_k, y> in one pass over y (VecProd; S-column batches)
+template <int NX>
+__global__ void __launch_bounds__(256) k_dot_multi(int64_t n, const double* x0, const double* x1,
+                                                   const double* x2, const double* x3, const double* __restrict__ y,
+                                                   double* partials, unsigned int* ticket, double* out) {
+    const double* xs[4] = {x0, x1, x2, x3};
+    double v[NX];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) v[k] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double yi = y[i];
+#pragma unroll
+        for (int k = 0; k < NX; ++k) v[k] += xs[k][i] * yi;
+    }
+    grid_reduce<NX, 0>(v, partials, ticket, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device scalars of the Krylov recurrences (no host round trip inside an iteration)
+// ---------------------------------------------------------------------------------------------
+enum { SC_RHO = 0, SC_RHO_OLD, SC_ALPHA, SC_OMEGA, SC_RV, SC_TS, SC_TT, SC_RR, SC_SS, SC_BETA, SC_PQ, SC_RZ, SC_RZ_OLD, SC_COUNT };
+
+// p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega)   [BiCGStab]
+__global__ void k_bicg_update_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
+                                double* __restrict__ p) {
+    const double beta = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
+    const double omega = sc[SC_OMEGA];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = r[i] + beta * (p[i] - omega * v[i]);
+}
+// alpha = rho / <rh,v>;  s = r - alpha v;  reduce |s|^2
+__global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
+                                                double* __restrict__ s, double* partials, unsigned int* ticket) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double si = r[i] - alpha * v[i];
+        s[i] = si;
+        acc[0] += si * si;
+    }
+    grid_reduce<1, 0>(acc, partials, ticket, sc + SC_SS);
+}
+// omega = <t,s>/<t,t>; x += alpha ph + omega sh; r = s - omega t; reduce |r|^2 and <rh,r> (next rho)
+__global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* __restrict__ sc, const double* __restrict__ ph, const double* __restrict__ sh,
+                                                 const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ rh,
+                                                 double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    const double tt = sc[SC_TT];
+    const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * ph[i] + omega * sh[i];
+        double ri = s[i] - omega * t[i];
+        r[i] = ri;
+        acc[0] += ri * ri;
+        acc[1] += rh[i] * ri;
+    }
+    grid_reduce<2, 0>(acc, partials, ticket, out2);   // out2[0] = |r|^2, out2[1] = <rh,r>
+}
+// bookkeeping between iterations: rho_old = rho; alpha, omega stored; rho = <rh,r>
+__global__ void k_bicg_roll(double* sc, const double* out2) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    const double tt = sc[SC_TT];
+    const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
+    sc[SC_RHO_OLD] = sc[SC_RHO];
+    sc[SC_ALPHA] = alpha;
+    sc[SC_OMEGA] = omega;
+    sc[SC_RR] = out2[0];
+    sc[SC_RHO] = out2[1];
+}
+// x += alpha * ph (half-step exit of BiCGStab)
+__global__ void k_bicg_half_x(int64_t n, const double* __restrict__ sc, const double* __restrict__ ph, double* __restrict__ x) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += alpha * ph[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSR SpMV family.  One group of LPR lanes per block row; the row's value array (len*D*D doubles,
+// contiguous) is streamed with unit-stride loads across the lanes, block-column indices are loaded
+// once per row and broadcast with shuffles, x is gathered through the read-only path.
+//   MODE 0: y = A x
+//   MODE 1: y = b - A x
+//   MODE 2: Chebyshev/Jacobi step  r = b - A xin ; d = c1*d + c2*dinv*r ; xout = xin + d
+// DOTS (MODE 0 only): 0 none, 1: <w,y> -> red[0], 2: <w,y>, <y,y> -> red[0..1]   (w given)
+// ---------------------------------------------------------------------------------------------
+template <int D, int LPR, int MODE, int DOTS>
+__global__ void __launch_bounds__(256) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                  const double* __restrict__ vals, const double* __restrict__ x,
+                                                  const double* __restrict__ b, double* __restrict__ y,
+                                                  const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
+                                                  const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
+    constexpr int DD = D * D;
+    constexpr int GPW = 32 / LPR;                       // groups per warp
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LPR;                          // lane within group
+    const int gbase = lane - gl;                        // first lane of my group
+    const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
+    double dot[2] = {0.0, 0.0};
+    (void)GPW;
+    // every lane of a warp iterates the same number of times (rows padded with idle groups)
+    const int64_t nrounds = (nb + ngroups - 1) / ngroups;
+    for (int64_t round = 0; round < nrounds; ++round) {
+        const int64_t row = gid + round * ngroups;
+        const bool active = row < nb;
+        int s = 0, e = 0;
+        if (active) { s = rowptr[row]; e = rowptr[row + 1]; }
+        double acc[D];
+#pragma unroll
+        for (int r = 0; r < D; ++r) acc[r] = 0.0;
+        for (int cs = s; cs < e; cs += LPR) {           // chunks of LPR blocks
+            const int nblk = min(LPR, e - cs);
+            int mycol = 0;
+            if (gl < nblk) mycol = __ldg(colidx + cs + gl);
+            const int64_t base = (int64_t)cs * DD;
+            const int nent = nblk * DD;
+#pragma unroll 4
+            for (int k0 = 0; k0 < nent; k0 += LPR) {   // uniform trip count within the group (shuffles inside)
+                const int k = k0 + gl;
+                const bool valid = k < nent;
+                const int blk = valid ? k / DD : 0;
+                const int wq = k - blk * DD;
+                const int r = wq / D;
+                const int c = wq - r * D;
+                const double a = valid ? __ldg(vals + base + k) : 0.0;
+                const int col = __shfl_sync(gmask, mycol, gbase + blk);
+                const double xv = valid ? __ldg(x + (int64_t)col * D + c) : 0.0;
+                const double pr = a * xv;
+#pragma unroll
+                for (int rr = 0; rr < D; ++rr) acc[rr] += (rr == r) ? pr : 0.0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(gmask, acc[r], o);
+        }
+        if (active && gl < D) {
+            double a = acc[0];
+#pragma unroll
+            for (int r = 1; r < D; ++r) a = (gl == r) ? acc[r] : a;
+            const int64_t i = row * D + gl;
+            if (MODE == 0) {
+                y[i] = a;
+                if (DOTS >= 1) dot[0] += w[i] * a;
+                if (DOTS >= 2) dot[1] += a * a;
+            } else if (MODE == 1) {
+                y[i] = b[i] - a;
+            } else {
+                const double res = b[i] - a;
+                const double dn = (c1 != 0.0 ? c1 * dvec[i] : 0.0) + c2 * dinv[i] * res;   // c1 == 0: dvec may be uninitialised
+                dvec[i] = dn;
+                y[i] = x[i] + dn;
+            }
+        }
+    }
+    if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
+}
+
+// first Chebyshev/Jacobi step from a zero initial guess: d = c2*dinv*b ; x = d   (no matrix pass)
+__global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* __restrict__ b,
+                               double* __restrict__ d, double* __restrict__ x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double dn = c2 * dinv[i] * b[i];
+        d[i] = dn;
+        x[i] = dn;
+    }
+}
+
+// point-Jacobi data: dinv_i = 1/a_ii and the Gershgorin bound max_i sum_j |a_ij| / a_ii  (-> red[0])
+template <int D>
+__global__ void __launch_bounds__(256) k_diag_gershgorin(int nb, const int* __restrict__ rowptr, const int* __restrict__ diagpos,
+                                                         const double* __restrict__ vals, double* __restrict__ dinv, double* partials,
+                                                         unsigned int* ticket, double* red) {
+    constexpr int DD = D * D;
+    double mx[1] = {0.0};
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nb * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(t / D), r = (int)(t - (int64_t)row * D);
+        const int s = rowptr[row], e = rowptr[row + 1];
+        double sum = 0.0;
+        for (int k = s; k < e; ++k) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) sum += fabs(vals[(int64_t)k * DD + r * D + c]);
+        }
+        const double aii = vals[(int64_t)diagpos[row] * DD + r * D + r];
+        dinv[t] = 1.0 / aii;
+        mx[0] = fmax(mx[0], sum / aii);
+    }
+    grid_reduce<1, 1>(mx, partials, ticket, red);
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1 transfers (StdTransfer, obstacle_optim_3d_util.lua:28): copies weight 1, edge midpoints 1/2,1/2
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, const int* __restrict__ pb,
+                              const double* __restrict__ xc, double* __restrict__ xf) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvf * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
+        double add;
+        if (v < nvc) add = xc[t];
+        else {
+            const int k = v - nvc;
+            add = 0.5 * (xc[(int64_t)pa[k] * D + c] + xc[(int64_t)pb[k] * D + c]);
+        }
+        xf[t] += add;
+    }
+}
+
+// rc = mask * P^T rf : gather over the coarse vertex graph, `mid` gives the fine midpoint of every coarse edge
+template <int D>
+__global__ void k_restrict(int nvc, const int* __restrict__ rowptr, const int* __restrict__ mid, const int* __restrict__ diagpos,
+                           const unsigned char* __restrict__ dirmask, const double* __restrict__ rf, double* __restrict__ rc) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvc * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
+        const int s = rowptr[v], e = rowptr[v + 1], dp = diagpos[v];
+        double half = 0.0;
+        for (int k = s; k < e; ++k)
+            if (k != dp) half += rf[(int64_t)mid[k] * D + c];
+        double val = rf[t] + 0.5 * half;
+        if (dirmask && ((dirmask[v] >> c) & 1)) val = 0.0;
+        rc[t] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Galerkin coarse operator Ac = Dir(P^T Af P)  (rap = true, obstacle_optim_3d_util.lua:27).
+// Row-owner gather: one warp per coarse block row I accumulates its row in shared memory from the
+// fine rows of its children (copy of I: weight 1; midpoints of the coarse edges at I: weight 1/2).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __restrict__ crowptr, const int* __restrict__ ccol,
+                                             const int* __restrict__ cmid, const int* __restrict__ cdiag,
+                                             const int* __restrict__ frowptr, const int* __restrict__ fcol, const double* __restrict__ fvals,
+                                             const int* __restrict__ pa, const int* __restrict__ pb,
+                                             const unsigned char* __restrict__ dirmask, double* __restrict__ cvals) {
+    constexpr int DD = D * D;
+    extern __shared__ double sm_rap[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* acc = sm_rap + (size_t)wib * maxrow * DD;
+    int* cols = (int*)(sm_rap + (size_t)(blockDim.x >> 5) * maxrow * DD) + (size_t)wib * maxrow;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; I < nvc; I += nwarps) {
+        const int cs = crowptr[I], ce = crowptr[I + 1], len = ce - cs;
+        for (int k = lane; k < len * DD; k += 32) acc[k] = 0.0;
+        for (int k = lane; k < len; k += 32) cols[k] = ccol[cs + k];
+        __syncwarp();
+        for (int ck = 0; ck < len; ++ck) {                       // children of I
+            const int child = cmid[cs + ck];
+            const double wI = (cs + ck == cdiag[I]) ? 1.0 : 0.5;
+            const int fs = frowptr[child], fe = frowptr[child + 1];
+            for (int k = lane; k < (fe - fs) * DD; k += 32) {
+                const int blk = k / DD, rc = k - blk * DD;
+                const int j = fcol[fs + blk];
+                const double a = wI * fvals[(int64_t)fs * DD + k];
+                int J0, J1;
+                double wJ;
+                if (j < nvc) { J0 = j; J1 = -1; wJ = 1.0; }
+                else { J0 = pa[j - nvc]; J1 = pb[j - nvc]; wJ = 0.5; }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int J = q == 0 ? J0 : J1;
+                    if (J < 0) continue;
+                    int lo = 0, hi = len - 1;                    // binary search J in cols
+                    while (lo < hi) {
+                        int m = (lo + hi) >> 1;
+                        if (cols[m] < J) lo = m + 1; else hi = m;
+                    }
+                    atomicAdd(&acc[lo * DD + rc], wJ * a);
+                }
+            }
+        }
+        __syncwarp();
+        const unsigned char mI = dirmask ? dirmask[I] : 0;
+        for (int k = lane; k < len * DD; k += 32) {
+            const int blk = k / DD, rc = k - blk * DD, r = rc / D, c = rc - r * D;
+            double val = acc[k];
+            if (dirmask) {
+                const unsigned char mJ = dirmask[cols[blk]];
+                if (((mI >> r) & 1) || ((mJ >> c) & 1)) val = (cols[blk] == (int)I && r == c) ? 1.0 : 0.0;
+            }
+            cvals[(int64_t)cs * DD + k] = val;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse-level direct solve (replaces SuperLU(), obstacle_optim_3d_util.lua:21):
+// dense inverse of the free-DoF block by Gauss-Jordan with partial pivoting (cooperative kernel),
+// applied as one GEMV per V-cycle.
+// ---------------------------------------------------------------------------------------------
+// scatter the BSR level-0 matrix into the augmented dense system [A_ff | I]  (n x 2n, row-major)
+template <int D>
+__global__ void k_bsr_to_dense(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
+                               const int* __restrict__ dof2free, int n, double* __restrict__ M) {
+    constexpr int DD = D * D;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)rowptr[nb] * DD; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t blk = t / DD;
+        const int rc = (int)(t - blk * DD), r = rc / D, c = rc - r * D;
+        // find block row by binary search
+        int lo = 0, hi = nb - 1;
+        while (lo < hi) {
+            int m = (lo + hi + 1) >> 1;
+            if (rowptr[m] <= blk) lo = m; else hi = m - 1;
+        }
+        const int fi = dof2free[lo * D + r], fj = dof2free[colidx[blk] * D + c];
+        if (fi >= 0 && fj >= 0) M[(int64_t)fi * 2 * n + fj] = vals[t];
+    }
+}
+__global__ void k_dense_identity(int n, double* __restrict__ M) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) M[(int64_t)i * 2 * n + n + i] = 1.0;
+}
+
+// in-place Gauss-Jordan on M = [A | I] -> rows hold [e_k-ish | A^-1 rows] up to a row permutation and scaling.
+// used[] is kept redundantly in every block's shared memory; pivrow[k] (global) records the pivot row of step k.
+__global__ void __launch_bounds__(256) k_gauss_jordan(int n, double* __restrict__ M, int* __restrict__ pivrow, int* __restrict__ fail) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ unsigned char sm_used[];          // n bytes
+    __shared__ double s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ int s_piv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t ld = 2 * (int64_t)n;
+    for (int i = tid; i < n; i += blockDim.x) sm_used[i] = 0;
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        // pivot search (redundant per block): max |M[i][k]| over unused rows, ties -> smallest i
+        double best = -1.0;
+        int bi = -1;
+        for (int i = tid; i < n; i += blockDim.x) {
+            if (!sm_used[i]) {
+                double a = fabs(M[i * ld + k]);
+                if (a > best) { best = a; bi = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double b = s_val[0];
+            int ix = s_idx[0];
+            for (int w = 1; w < 8; ++w)
+                if (s_val[w] > b || (s_val[w] == b && s_idx[w] >= 0 && (ix < 0 || s_idx[w] < ix))) { b = s_val[w]; ix = s_idx[w]; }
+            s_piv = ix;
+            if (blockIdx.x == 0) {
+                pivrow[k] = ix;
+                if (!(b > 0.0)) *fail = 1;
+            }
+        }
+        __syncthreads();
+        const int p = s_piv;
+        if (p < 0) break;                                // singular: every block takes this branch together
+        sm_used[p] = 1;                                  // benign same-value race
+        const double piv = M[p * ld + k];
+        const double* prow = M + p * ld;
+        for (int i = blockIdx.x; i < n; i += gridDim.x) {
+            if (i == p) continue;
+            double* row = M + i * ld;
+            const double f = row[k] / piv;
+            __syncthreads();                             // everyone has read row[k] before it is overwritten
+            if (f != 0.0) {
+                for (int c = k + 1 + tid; c < 2 * n; c += blockDim.x) row[c] -= f * prow[c];
+                if (tid == 0) row[k] = 0.0;
+            }
+        }
+        grid.sync();
+    }
+}
+// Ainv[k][c] = M[pivrow[k]][n+c] / M[pivrow[k]][k]
+__global__ void k_extract_inverse(int n, const double* __restrict__ M, const int* __restrict__ pivrow, double* __restrict__ Ainv) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)n * n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t / n), c = (int)(t - (int64_t)k * n);
+        const int p = pivrow[k];
+        Ainv[t] = M[(int64_t)p * 2 * n + n + c] / M[(int64_t)p * 2 * n + k];
+    }
+}
+// x0 = scatter(Ainv * gather(b0)) ; Dirichlet dofs: x = b (identity rows).  One warp per free row.
+__global__ void __launch_bounds__(256) k_coarse_solve(int n, int ndof, const double* __restrict__ Ainv, const int* __restrict__ free2dof,
+                                                      const int* __restrict__ dof2free, const double* __restrict__ b, double* __restrict__ x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        double acc = 0.0;
+        for (int c = lane; c < n; c += 32) acc += Ainv[i * n + c] * b[free2dof[c]];
+        acc = warp_sum(acc);
+        if (lane == 0) x[free2dof[i]] = acc;
+    }
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ndof; t += (int64_t)gridDim.x * blockDim.x)
+        if (dof2free[t] < 0) x[t] = b[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagonal operator (P0 mass matrix) kernels for CG + Jacobi (3d_admm.lua:701-703)
+// ---------------------------------------------------------------------------------------------
+// q = diag .* p ; reduce <p,q>
+__global__ void __launch_bounds__(256) k_diag_apply_dot(int64_t n, const double* __restrict__ diag, const double* __restrict__ p,
+                                                        double* __restrict__ q, double* partials, unsigned int* ticket, double* out) {
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double qi = diag[i] * p[i];
+        q[i] = qi;
+        acc[0] += p[i] * qi;
+    }
+    grid_reduce<1, 0>(acc, partials, ticket, out);
+}
+// r = b - diag .* x ; z = damp * r / diag ; p = z ; reduce |r|^2, <r,z>
+__global__ void __launch_bounds__(256) k_cg_init(int64_t n, double damp, const double* __restrict__ diag, const double* __restrict__ b,
+                                                 const double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                 double* __restrict__ p, double* partials, unsigned int* ticket, double* out2) {
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ri = b[i] - diag[i] * x[i];
+        double zi = damp * ri / diag[i];
+        r[i] = ri; z[i] = zi; p[i] = zi;
+        acc[0] += ri * ri;
+        acc[1] += ri * zi;
+    }
+    grid_reduce<2, 0>(acc, partials, ticket, out2);
+}
+// a = rz/pq ; x += a p ; r -= a q ; z = damp r/diag ; reduce |r|^2, <r,z>
+__global__ void __launch_bounds__(256) k_cg_step(int64_t n, double damp, const double* __restrict__ sc, const double* __restrict__ diag,
+                                                 const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+                                                 double* __restrict__ r, double* __restrict__ z, double* partials, unsigned int* ticket,
+                                                 double* out2) {
+    const double a = sc[SC_RZ] / sc[SC_PQ];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += a * p[i];
+        double ri = r[i] - a * q[i];
+        double zi = damp * ri / diag[i];
+        r[i] = ri; z[i] = zi;
+        acc[0] += ri * ri;
+        acc[1] += ri * zi;
+    }
+    grid_reduce<2, 0>(acc, partials, ticket, out2);
+}
+// p = z + (rz_new/rz_old) p ; roll scalars
+__global__ void k_cg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ z, double* __restrict__ p) {
+    const double beta = sc[SC_RZ] / sc[SC_RZ_OLD];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
+}
+__global__ void k_cg_roll(double* sc, const double* out2) {
+    sc[SC_RZ_OLD] = sc[SC_RZ];
+    sc[SC_RR] = out2[0];
+    sc[SC_RZ] = out2[1];
+}
+
+}  // namespace ab

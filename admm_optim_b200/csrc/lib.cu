@@ -1,0 +1,1384 @@
+// libadmm_b200: objects behind the C ABI of include/admm_b200.h.
+//   Domain/levels -> Space -> Vector / ElemDisc / DomainDisc / Operator / Solver (BiCGStab+GMG, CG+Jacobi)
+// The call order served is the ADMM / Newton-Schur loop of 3d_admm.lua:875-1304 (2d_admm.lua:868-1253).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "../../include/admm_b200.h"
+#include "common.cuh"
+#include "kernels_fe.cuh"
+#include "kernels_la.cuh"
+#include "mesh.hpp"
+
+namespace ab {
+
+static thread_local std::string g_last_error;
+static uint64_t g_version_counter = 1;
+static bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && *v && strcmp(v, "0") != 0;
+}
+
+// =============================================================================================
+// Domain: host hierarchy + device-resident level structures
+// =============================================================================================
+struct LevelDev {
+    int nv = 0, ne = 0, nvc = 0, maxrow = 0;
+    int64_t nnzb = 0;
+    DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
+    DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
+    DevBuf<int> vsub;
+    DevBuf<double> xyz;                          // top level only
+    DevBuf<int> elems, elem_pos;                 // top level only
+};
+
+struct MatrixData;
+
+struct Domain {
+    Context* ctx = nullptr;
+    HostMesh mesh;
+    std::vector<LevelDev> dev;
+    bool finalized = false;
+    uint64_t coords_version = 1;
+    bool host_xyz_stale = false;
+    std::vector<std::weak_ptr<MatrixData>> live;   // assembled matrices, for signature sharing
+    int dim() const { return mesh.dim; }
+    int top() const { return (int)mesh.levels.size() - 1; }
+    void finalize();
+};
+
+template <int D>
+static void launch_elem_pos(Context* ctx, LevelDev& L) {
+    const int64_t n = (int64_t)L.ne * (D + 1) * (D + 1);
+    AB_LAUNCH(ctx, (k_elem_pos<D>), grid_for(n, 256, ctx->num_sms * 16), 256, 0, (int64_t)L.ne, L.elems.p, L.rowptr.p, L.colidx.p, L.elem_pos.p);
+}
+
+void Domain::finalize() {
+    if (finalized) return;
+    const int nl = (int)mesh.levels.size();
+    dev.resize(nl);
+    for (int l = 0; l < nl; ++l) {
+        HostLevel& H = mesh.levels[l];
+        HostPattern P;
+        build_pattern(H, P);
+        LevelDev& L = dev[l];
+        L.nv = H.nv; L.ne = H.ne; L.nvc = H.nv_coarse; L.nnzb = (int64_t)P.colidx.size();
+        int mr = 0;
+        for (int i = 0; i < H.nv; ++i) mr = std::max(mr, P.rowptr[i + 1] - P.rowptr[i]);
+        L.maxrow = mr;
+        L.rowptr.upload(P.rowptr, ctx->stream);
+        L.colidx.upload(P.colidx, ctx->stream);
+        L.diagpos.upload(P.diagpos, ctx->stream);
+        if (l < nl - 1) L.mid.upload(P.mid, ctx->stream);
+        if (l > 0) { L.pa.upload(H.pa, ctx->stream); L.pb.upload(H.pb, ctx->stream); }
+        L.vsub.upload(H.vsub, ctx->stream);
+        if (l == nl - 1) {
+            L.xyz.upload(H.xyz, ctx->stream);
+            L.elems.upload(H.elems, ctx->stream);
+            L.elem_pos.alloc((size_t)H.ne * (H.dim + 1) * (H.dim + 1));
+            if (H.dim == 2) launch_elem_pos<2>(ctx, L); else launch_elem_pos<3>(ctx, L);
+        }
+        if (l < nl - 1) { H.edges.clear(); H.edges.shrink_to_fit(); H.have_edges = false; }
+    }
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    finalized = true;
+}
+
+struct Space {
+    Domain* dom;
+    int kind, ncomp;
+    int64_t ndofs;
+};
+
+struct Vector {
+    Space* sp;
+    DevBuf<double> d;
+    int storage = AB_PST_CONSISTENT;
+    uint64_t version = 0, id = 0;
+    int64_t n() const { return sp->ndofs; }
+    void touch() { version = ++g_version_counter; }
+};
+
+struct ElemDisc {
+    Space* sp;
+    int kind;
+    double params[16];
+    Vector *imp_u = nullptr, *imp_lam = nullptr, *imp_q = nullptr;
+};
+
+struct DomainDisc {
+    Space* sp;
+    std::vector<ElemDisc*> discs;
+    std::vector<std::pair<int, int>> dir;          // (subset index, comp)
+    std::vector<DevBuf<unsigned char>> masks;      // per level, built lazily
+    bool masks_valid = false;
+    const unsigned char* mask(int level);
+};
+
+const unsigned char* DomainDisc::mask(int level) {
+    if (dir.empty()) return nullptr;
+    Domain* dom = sp->dom;
+    if (!masks_valid) {
+        masks.clear();
+        masks.resize(dom->mesh.levels.size());
+        for (size_t l = 0; l < dom->mesh.levels.size(); ++l) {
+            const HostLevel& H = dom->mesh.levels[l];
+            std::vector<unsigned char> m((size_t)H.nv, 0);
+            for (auto& e : dir)
+                for (int v = 0; v < H.nv; ++v)
+                    if (H.vsub[v] == e.first) m[v] |= (unsigned char)(1u << e.second);
+            masks[l].upload(m, dom->ctx->stream);
+        }
+        masks_valid = true;
+    }
+    return masks[level].p;
+}
+
+// =============================================================================================
+// matrices
+// =============================================================================================
+struct Signature {
+    int kind = 0;                                  // 1 = P1 Hessian BSR, 2 = P0 diagonal mass
+    double c = 0, lam_vol = 0, lam_b[3] = {0, 0, 0};
+    uint64_t u_id = 0, u_version = 0, coords_version = 0;
+    std::vector<std::pair<int, int>> dir;
+    bool operator==(const Signature& o) const {
+        return kind == o.kind && c == o.c && lam_vol == o.lam_vol && lam_b[0] == o.lam_b[0] && lam_b[1] == o.lam_b[1] &&
+               lam_b[2] == o.lam_b[2] && u_id == o.u_id && u_version == o.u_version && coords_version == o.coords_version && dir == o.dir;
+    }
+};
+
+struct Gmg;
+struct MatrixData {
+    Domain* dom = nullptr;
+    int kind = 0;                                  // 1 BSR (top level pattern), 2 diagonal
+    DevBuf<double> vals;
+    Signature sig;
+    bool assembled = false;
+    DomainDisc* dd = nullptr;                      // for Dirichlet masks on coarse levels
+    std::map<std::string, std::shared_ptr<Gmg>> gmg;   // hierarchies built on this matrix, keyed by descriptor
+};
+
+struct Operator {
+    DomainDisc* dd;
+    std::shared_ptr<MatrixData> data;
+};
+
+// =============================================================================================
+// small launch helpers
+// =============================================================================================
+static inline int ew_grid(Context* ctx, int64_t n) { return grid_for(n, 256, ctx->num_sms * 8); }
+static inline int red_grid(Context* ctx, int64_t n) { return grid_for(n, 256, Context::kMaxBlocks); }
+
+static void dev_fill(Context* ctx, double* x, int64_t n, double c) {
+    if (c == 0.0) { AB_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), ctx->stream)); return; }
+    AB_LAUNCH(ctx, k_fill, ew_grid(ctx, n), 256, 0, n, c, x);
+}
+static void dev_axpby(Context* ctx, int64_t n, double a, const double* x, double b, const double* y, double* out) {
+    AB_LAUNCH(ctx, k_axpby, ew_grid(ctx, n), 256, 0, n, a, x, b, y, out);
+}
+static void dev_copy(Context* ctx, int64_t n, const double* src, double* dst) {
+    AB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+}
+// read `cnt` device doubles (synchronises the stream)
+static void read_back(Context* ctx, const double* dptr, int cnt, double* out) {
+    AB_CUDA(cudaMemcpyAsync(ctx->h_results, dptr, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < cnt; ++i) out[i] = ctx->h_results[i];
+}
+static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, const double* y, double* dout) {
+    const double* x[4] = {xs[0], nx > 1 ? xs[1] : xs[0], nx > 2 ? xs[2] : xs[0], nx > 3 ? xs[3] : xs[0]};
+    const int g = red_grid(ctx, n);
+    switch (nx) {
+        case 1: AB_LAUNCH(ctx, (k_dot_multi<1>), g, 256, 0, n, x[0], x[1], x[2], x[3], y, ctx->d_partials, ctx->d_tickets, dout); break;
+        case 2: AB_LAUNCH(ctx, (k_dot_multi<2>), g, 256, 0, n, x[0], x[1], x[2], x[3], y, ctx->d_partials, ctx->d_tickets, dout); break;
+        case 3: AB_LAUNCH(ctx, (k_dot_multi<3>), g, 256, 0, n, x[0], x[1], x[2], x[3], y, ctx->d_partials, ctx->d_tickets, dout); break;
+        default: AB_LAUNCH(ctx, (k_dot_multi<4>), g, 256, 0, n, x[0], x[1], x[2], x[3], y, ctx->d_partials, ctx->d_tickets, dout); break;
+    }
+}
+
+// SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
+template <int D>
+static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
+                        const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+    constexpr int LPR = D == 3 ? 16 : 8;
+    const int64_t groups_per_block = 256 / LPR;
+    const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * 8);
+    const int g = std::max(grid, 1);
+#define AB_SPMV(MODE, DOTS) \
+    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    if (mode == 0) {
+        if (dots == 0) AB_SPMV(0, 0);
+        else if (dots == 1) AB_SPMV(0, 1);
+        else AB_SPMV(0, 2);
+    } else if (mode == 1) AB_SPMV(1, 0);
+    else AB_SPMV(2, 0);
+#undef AB_SPMV
+}
+static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
+                 const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
+    if (dim == 2) spmv_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+    else spmv_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+}
+
+// =============================================================================================
+// geometric multigrid hierarchy on one assembled matrix (obstacle_optim_3d_util.lua:13-31)
+// =============================================================================================
+struct GmgLevel {
+    DevBuf<double> vals_own;          // Galerkin operator (levels below top)
+    const double* vals = nullptr;
+    DevBuf<double> dinv, x, b, r, d, x2;
+    double lmax = 0;
+    std::vector<std::pair<double, double>> coef_pre, coef_post;   // (c1,c2) per smoothing step
+    const unsigned char* mask = nullptr;
+};
+
+struct Gmg {
+    Domain* dom = nullptr;
+    ab_gmg_desc desc;
+    std::vector<GmgLevel> L;
+    // coarse level: dense inverse on the free dofs
+    int n_free = 0, n0 = 0;
+    DevBuf<double> Ainv, Mwork;
+    DevBuf<int> free2dof, dof2free, pivrow, fail;
+    std::shared_ptr<MatrixData> keep_alive_unused;
+    void setup(const std::shared_ptr<MatrixData>& A);
+    void vcycle(int l, const double* b, double* x);
+    void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef);
+    void apply(const double* r, double* z) { vcycle((int)L.size() - 1, r, z); }
+};
+
+static std::string gmg_key(const ab_gmg_desc& d) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "%d/%d/%d/%d/%.17g/%.17g", d.smoother, d.pre_smooth, d.post_smooth, d.base_level, d.cheb_ratio, d.jacobi_damp);
+    return buf;
+}
+
+static void smoother_coefs(const ab_gmg_desc& desc, double lmax, int nu, std::vector<std::pair<double, double>>& out) {
+    out.clear();
+    if (desc.smoother == AB_SMOOTHER_JACOBI) {
+        for (int k = 0; k < nu; ++k) out.push_back({0.0, desc.jacobi_damp});
+        return;
+    }
+    const double lmin = lmax / desc.cheb_ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+    double rho = 1.0 / sigma1;
+    out.push_back({0.0, 1.0 / theta});
+    for (int k = 1; k < nu; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        out.push_back({rho_new * rho, 2.0 * rho_new / delta});
+        rho = rho_new;
+    }
+}
+
+template <int D>
+static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
+    Domain* dom = G.dom;
+    Context* ctx = dom->ctx;
+    const int top = dom->top();
+    constexpr int DD = D * D;
+    // Galerkin coarse operators, top-down
+    for (int l = top; l > 0; --l) {
+        const LevelDev& F = dom->dev[l];
+        const LevelDev& C = dom->dev[l - 1];
+        GmgLevel& gc = G.L[l - 1];
+        gc.vals_own.alloc((size_t)C.nnzb * DD);
+        gc.vals = gc.vals_own.p;
+        const int warps = 8;
+        const size_t smem = (size_t)warps * C.maxrow * (DD * sizeof(double) + sizeof(int));
+        static bool attr_set[2] = {false, false};
+        if (smem > 48 * 1024 && !attr_set[D - 2]) {
+            AB_CUDA(cudaFuncSetAttribute(k_rap<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[D - 2] = true;
+        }
+        AB_REQUIRE(smem <= 200 * 1024, AB_ERR_UNSUPPORTED, "coarse row too long for k_rap shared memory");
+        const int grid = (int)std::min<int64_t>(((int64_t)C.nv + warps - 1) / warps, (int64_t)ctx->num_sms * 4);
+        AB_LAUNCH(ctx, (k_rap<D>), std::max(grid, 1), warps * 32, smem, C.nv, C.maxrow, C.rowptr.p, C.colidx.p, C.mid.p, C.diagpos.p, F.rowptr.p,
+                  F.colidx.p, G.L[l].vals, F.pa.p, F.pb.p, gc.mask, gc.vals_own.p);
+    }
+    // smoother data on levels >= 1
+    for (int l = 1; l <= top; ++l) {
+        const LevelDev& Ld = dom->dev[l];
+        GmgLevel& g = G.L[l];
+        AB_LAUNCH(ctx, (k_diag_gershgorin<D>), red_grid(ctx, (int64_t)Ld.nv * D), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p,
+                  ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
+    }
+    // dense inverse of level 0 (free dofs)
+    {
+        const LevelDev& L0 = dom->dev[0];
+        const int n = G.n_free;
+        if (n > 0) {
+            AB_CUDA(cudaMemsetAsync(G.Mwork.p, 0, (size_t)n * 2 * n * sizeof(double), ctx->stream));
+            AB_LAUNCH(ctx, (k_bsr_to_dense<D>), grid_for(L0.nnzb * DD, 256, ctx->num_sms * 8), 256, 0, L0.nv, L0.rowptr.p, L0.colidx.p, G.L[0].vals,
+                      G.dof2free.p, n, G.Mwork.p);
+            AB_LAUNCH(ctx, k_dense_identity, grid_for(n, 256, 64), 256, 0, n, G.Mwork.p);
+            AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
+            int nn = n;
+            double* M = G.Mwork.p;
+            int* piv = G.pivrow.p;
+            int* fail = G.fail.p;
+            void* args[] = {&nn, &M, &piv, &fail};
+            int grid = std::min(ctx->num_sms, n);
+            AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
+            ctx->launches++;
+            AB_LAUNCH(ctx, k_extract_inverse, grid_for((int64_t)n * n, 256, ctx->num_sms * 8), 256, 0, n, G.Mwork.p, G.pivrow.p, G.Ainv.p);
+        }
+    }
+}
+
+void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
+    Context* ctx = dom->ctx;
+    const int top = dom->top(), dim = dom->dim();
+    const bool first = L.empty();
+    if (first) {
+        L.resize(top + 1);
+        for (int l = 0; l <= top; ++l) {
+            const int64_t n = (int64_t)dom->dev[l].nv * dim;
+            GmgLevel& g = L[l];
+            if (l < top) { g.x.alloc(n); g.b.alloc(n); }
+            if (l > 0) { g.r.alloc(n); g.d.alloc(n); g.x2.alloc(n); g.dinv.alloc(n); }
+        }
+        // free-dof numbering of level 0
+        const HostLevel& H0 = dom->mesh.levels[0];
+        n0 = H0.nv * dim;
+        std::vector<unsigned char> m((size_t)H0.nv, 0);
+        if (A->dd)
+            for (auto& e : A->dd->dir)
+                for (int v = 0; v < H0.nv; ++v)
+                    if (H0.vsub[v] == e.first) m[v] |= (unsigned char)(1u << e.second);
+        std::vector<int> f2d, d2f((size_t)n0, -1);
+        for (int v = 0; v < H0.nv; ++v)
+            for (int c = 0; c < dim; ++c)
+                if (!((m[v] >> c) & 1)) { d2f[(size_t)v * dim + c] = (int)f2d.size(); f2d.push_back(v * dim + c); }
+        n_free = (int)f2d.size();
+        free2dof.upload(f2d, ctx->stream);
+        dof2free.upload(d2f, ctx->stream);
+        if (n_free) { Ainv.alloc((size_t)n_free * n_free); Mwork.alloc((size_t)n_free * 2 * n_free); }
+        pivrow.alloc(std::max(n_free, 1));
+        fail.alloc(1);
+    }
+    for (int l = 0; l <= top; ++l) L[l].mask = A->dd ? A->dd->mask(l) : nullptr;
+    L[top].vals = A->vals.p;
+    if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
+    // one synchronisation per setup: Gershgorin bounds (+ singularity flag) -> smoother coefficients
+    if (top >= 1) {
+        std::vector<double> lm(top + 1, 0.0);
+        read_back(ctx, ctx->d_results + 1, top, lm.data() + 1);
+        for (int l = 1; l <= top; ++l) {
+            L[l].lmax = lm[l];
+            smoother_coefs(desc, lm[l], desc.pre_smooth, L[l].coef_pre);
+            smoother_coefs(desc, lm[l], desc.post_smooth, L[l].coef_post);
+        }
+    }
+    int hfail = 0;
+    AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
+}
+
+void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef) {
+    if (nu <= 0) { if (zero_guess) dev_fill(dom->ctx, x, (int64_t)dom->dev[l].nv * dom->dim(), 0.0); return; }
+    Context* ctx = dom->ctx;
+    const LevelDev& Ld = dom->dev[l];
+    GmgLevel& g = L[l];
+    const int64_t n = (int64_t)Ld.nv * dom->dim();
+    double* bufs[2] = {x, g.x2.p};
+    int cur;   // buffer holding the current iterate
+    int k = 0;
+    if (zero_guess) {
+        cur = ((nu - 1) % 2 == 0) ? 0 : 1;
+        AB_LAUNCH(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, g.d.p, bufs[cur]);
+        k = 1;
+    } else {
+        cur = 0;   // caller guarantees: iterate is in x if nu even, in x2 if nu odd  (see vcycle)
+        if (nu % 2 == 1) cur = 1;
+    }
+    for (; k < nu; ++k) {
+        spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, coef[k].first, coef[k].second);
+        cur = 1 - cur;
+    }
+}
+
+void Gmg::vcycle(int l, const double* b, double* x) {
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim();
+    if (l == 0) {
+        const int n = n_free;
+        const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
+        AB_LAUNCH(ctx, k_coarse_solve, grid, 256, 0, n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+        return;
+    }
+    const LevelDev& Ld = dom->dev[l];
+    const LevelDev& Lc = dom->dev[l - 1];
+    GmgLevel& g = L[l];
+    GmgLevel& gc = L[l - 1];
+    const int64_t n = (int64_t)Ld.nv * dim, nc = (int64_t)Lc.nv * dim;
+    smooth(l, b, x, desc.pre_smooth, true, g.coef_pre);
+    spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p);
+    if (dim == 2) AB_LAUNCH(ctx, (k_restrict<2>), ew_grid(ctx, nc), 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    else AB_LAUNCH(ctx, (k_restrict<3>), ew_grid(ctx, nc), 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    vcycle(l - 1, gc.b.p, gc.x.p);
+    // x (+)= P xc ; written to x2 when the post-smoother runs an odd number of steps so that it ends in x
+    double* target = (desc.post_smooth % 2 == 1) ? g.x2.p : x;
+    if (target != x) dev_copy(ctx, n, x, target);
+    if (dim == 2) AB_LAUNCH(ctx, (k_prolong_add<2>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, target);
+    else AB_LAUNCH(ctx, (k_prolong_add<3>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, target);
+    smooth(l, b, x, desc.post_smooth, false, g.coef_post);
+}
+
+// =============================================================================================
+// solvers
+// =============================================================================================
+struct Solver {
+    Space* sp = nullptr;
+    int type = 0;                      // 1 = BiCGStab + GMG, 2 = CG + Jacobi (diagonal operators)
+    ab_gmg_desc desc{};
+    double damp = 0.66;
+    std::shared_ptr<MatrixData> A;
+    std::shared_ptr<Gmg> gmg;
+    DevBuf<double> r, rh, p, v, s, t, ph, sh, sc, out2;
+    int last_steps = 0;
+    double last_defect = 0;
+    void ensure_vectors();
+};
+
+void Solver::ensure_vectors() {
+    const int64_t n = sp->ndofs;
+    if (sc.n == 0) { sc.alloc(SC_COUNT + 3); out2.alloc(2); }
+    if (type == 1 && r.n == 0) {
+        r.alloc(n); rh.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); t.alloc(n); ph.alloc(n); sh.alloc(n);
+    }
+    if (type == 2 && r.n == 0) { r.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); }
+}
+
+static void solver_init(Solver* S, Operator* A) {
+    AB_REQUIRE(A->data && A->data->assembled, AB_ERR_STATE, "solver:init called with an operator that was never assembled");
+    S->A = A->data;
+    S->ensure_vectors();
+    if (S->type == 1) {
+        AB_REQUIRE(A->data->kind == 1, AB_ERR_ARG, "BiCGStab+GMG needs a P1 (BSR) operator");
+        const std::string key = gmg_key(S->desc);
+        auto it = A->data->gmg.find(key);
+        if (it != A->data->gmg.end() && !env_flag("ADMM_B200_NO_CACHE")) { S->gmg = it->second; return; }
+        // reuse this solver's own hierarchy buffers when nobody else holds them
+        std::shared_ptr<Gmg> G = (S->gmg && S->gmg.use_count() == 1) ? S->gmg : std::make_shared<Gmg>();
+        G->dom = S->sp->dom;
+        G->desc = S->desc;
+        G->setup(A->data);
+        A->data->gmg[key] = G;
+        S->gmg = G;
+    } else {
+        AB_REQUIRE(A->data->kind == 2, AB_ERR_ARG, "CG+Jacobi is implemented for diagonal (P0 mass) operators");
+    }
+}
+
+static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) {
+    Domain* dom = S->sp->dom;
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim();
+    const LevelDev& Lt = dom->dev[dom->top()];
+    const int64_t n = S->sp->ndofs;
+    const double* Av = S->A->vals.p;
+    double* sc = S->sc.p;
+    const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
+    double h[SC_COUNT];
+    // r = b - A x ; rh = r ; rho = <r,r>
+    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);
+    dev_copy(ctx, n, S->r.p, S->rh.p);
+    {
+        const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        const double* xs[1] = {S->r.p};
+        dev_dots(ctx, n, 1, xs, S->r.p, sc + SC_RR);
+        AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    dev_fill(ctx, S->p.p, n, 0.0);
+    dev_fill(ctx, S->v.p, n, 0.0);
+    read_back(ctx, sc, SC_COUNT, h);
+    const double rr0 = h[SC_RR];
+    double rr = rr0;
+    bool ok = rr < tol2;
+    int it = 0;
+    if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
+    while (!ok && it < S->desc.max_iterations) {
+        ++it;
+        AB_LAUNCH(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
+        S->gmg->apply(S->p.p, S->ph.p);
+        spmv(ctx, dim, Lt, Av, 0, 1, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, S->rh.p, sc + SC_RV);
+        AB_LAUNCH(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);
+        S->gmg->apply(S->s.p, S->sh.p);
+        spmv(ctx, dim, Lt, Av, 0, 2, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, S->s.p, sc + SC_TS);
+        AB_LAUNCH(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
+                  ctx->d_tickets, S->out2.p);
+        AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
+        read_back(ctx, sc, SC_COUNT, h);
+        rr = h[SC_RR];
+        if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
+        if (!(rr == rr) || std::isinf(rr)) break;                       // NaN/Inf: breakdown
+        if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
+        if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;               // breakdown
+    }
+    x->touch();
+    S->last_steps = it;
+    S->last_defect = std::sqrt(rr);
+    if (return_defect) { dev_copy(ctx, n, S->r.p, b->d.p); b->touch(); }
+    return ok;
+}
+
+static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect) {
+    Context* ctx = S->sp->dom->ctx;
+    const int64_t n = S->sp->ndofs;
+    const double* diag = S->A->vals.p;
+    double* sc = S->sc.p;
+    double *r = S->r.p, *z = S->s.p, *p = S->p.p, *q = S->v.p;
+    const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
+    double h[SC_COUNT];
+    AB_LAUNCH(ctx, k_cg_init, red_grid(ctx, n), 256, 0, n, S->damp, diag, b->d.p, x->d.p, r, z, p, ctx->d_partials, ctx->d_tickets, S->out2.p);
+    AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
+    read_back(ctx, sc, SC_COUNT, h);
+    double rr = h[SC_RR];
+    const double rr0 = rr;
+    bool ok = rr < tol2;
+    int it = 0;
+    if (S->desc.verbose) printf("  CG+Jacobi: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
+    while (!ok && it < S->desc.max_iterations) {
+        ++it;
+        AB_LAUNCH(ctx, k_diag_apply_dot, red_grid(ctx, n), 256, 0, n, diag, p, q, ctx->d_partials, ctx->d_tickets, sc + SC_PQ);
+        AB_LAUNCH(ctx, k_cg_step, red_grid(ctx, n), 256, 0, n, S->damp, sc, diag, p, q, x->d.p, r, z, ctx->d_partials, ctx->d_tickets, S->out2.p);
+        AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
+        AB_LAUNCH(ctx, k_cg_p, ew_grid(ctx, n), 256, 0, n, sc, z, p);
+        read_back(ctx, sc, SC_COUNT, h);
+        rr = h[SC_RR];
+        if (S->desc.verbose) printf("  CG+Jacobi: iter %4d  defect %.6e\n", it, std::sqrt(rr));
+        if (!(rr == rr)) break;
+        if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
+    }
+    x->touch();
+    S->last_steps = it;
+    S->last_defect = std::sqrt(rr);
+    if (return_defect) { dev_copy(ctx, n, r, b->d.p); b->touch(); }
+    return ok;
+}
+
+// =============================================================================================
+// assembly
+// =============================================================================================
+static Vector* import_u(ElemDisc* d, Vector* arg) { return d->imp_u ? d->imp_u : arg; }
+
+template <int D>
+static void assemble_hessian_kernels(Domain* dom, DomainDisc* dd, ElemDisc* h, const double* u, double* vals) {
+    Context* ctx = dom->ctx;
+    const LevelDev& L = dom->dev[dom->top()];
+    HessParams P;
+    P.c = h->params[AB_PARAM_STEP_LENGTH];
+    P.lam_vol = h->params[AB_PARAM_LAMBDA_VOL];
+    P.lam_b[0] = h->params[AB_PARAM_LAMBDA_BARY_X];
+    P.lam_b[1] = h->params[AB_PARAM_LAMBDA_BARY_Y];
+    P.lam_b[2] = D == 3 ? h->params[AB_PARAM_LAMBDA_BARY_Z] : 0.0;
+    P.has_lam = (P.lam_vol != 0.0 || P.lam_b[0] != 0.0 || P.lam_b[1] != 0.0 || P.lam_b[2] != 0.0) ? 1 : 0;
+    AB_CUDA(cudaMemsetAsync(vals, 0, (size_t)L.nnzb * D * D * sizeof(double), ctx->stream));
+    const unsigned char* mask = dd->mask(dom->top());
+    AB_LAUNCH(ctx, (k_assemble_hessian<D>), grid_for(L.ne, 128, ctx->num_sms * 16), 128, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u, L.elem_pos.p, mask, P, vals);
+    if (mask) AB_LAUNCH(ctx, (k_dirichlet_diag<D>), ew_grid(ctx, (int64_t)L.nv * D), 256, 0, L.nv, mask, L.diagpos.p, vals);
+}
+
+static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
+    Domain* dom = dd->sp->dom;
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim();
+    ElemDisc* jac = nullptr;
+    for (ElemDisc* d : dd->discs)
+        if (d->kind == AB_DISC_DEFORMATION_EQUATION || d->kind == AB_DISC_MASS_MODEL) {
+            AB_REQUIRE(!jac, AB_ERR_UNSUPPORTED, "more than one jacobian-contributing ElemDisc in a DomainDiscretization");
+            jac = d;
+        }
+    AB_REQUIRE(jac, AB_ERR_STATE, "assemble_jacobian: DomainDiscretization has no jacobian-contributing ElemDisc");
+    Signature sig;
+    sig.coords_version = dom->coords_version;
+    sig.dir = dd->dir;
+    std::sort(sig.dir.begin(), sig.dir.end());
+    Vector* u = import_u(jac, uarg);
+    const LevelDev& L = dom->dev[dom->top()];
+    if (jac->kind == AB_DISC_DEFORMATION_EQUATION) {
+        AB_REQUIRE(dd->sp->kind == AB_SPACE_P1 && dd->sp->ncomp == dim, AB_ERR_ARG, "DeformationEquation needs a P1 space with dim components");
+        AB_REQUIRE(jac->params[AB_PARAM_SECOND_ORDER] == 0.0, AB_ERR_UNSUPPORTED,
+                   "set_second_order(true) (J'' terms, 2d_admm.lua:389) needs the Navier-Stokes fields and is outside the hot path");
+        sig.kind = 1;
+        sig.c = jac->params[AB_PARAM_STEP_LENGTH];
+        sig.lam_vol = jac->params[AB_PARAM_LAMBDA_VOL];
+        sig.lam_b[0] = jac->params[AB_PARAM_LAMBDA_BARY_X];
+        sig.lam_b[1] = jac->params[AB_PARAM_LAMBDA_BARY_Y];
+        sig.lam_b[2] = dim == 3 ? jac->params[AB_PARAM_LAMBDA_BARY_Z] : 0.0;
+        const bool has_lam = sig.lam_vol != 0 || sig.lam_b[0] != 0 || sig.lam_b[1] != 0 || sig.lam_b[2] != 0;
+        if (has_lam && u) { sig.u_id = u->id; sig.u_version = u->version; }
+    } else {
+        AB_REQUIRE(dd->sp->kind == AB_SPACE_P0 && dd->sp->ncomp == dim * dim, AB_ERR_ARG, "MassModel needs a P0 space with dim*dim components");
+        sig.kind = 2;
+    }
+    const bool cache = !env_flag("ADMM_B200_NO_CACHE");
+    if (cache && A->data && A->data->assembled && A->data->sig == sig) return;
+    if (cache) {
+        auto& live = dom->live;
+        live.erase(std::remove_if(live.begin(), live.end(), [](const std::weak_ptr<MatrixData>& w) { return w.expired(); }), live.end());
+        for (auto& w : live) {
+            auto m = w.lock();
+            if (m && m->assembled && m->sig == sig) { A->data = m; return; }
+        }
+    }
+    if (!A->data || A->data.use_count() > 1 || A->data->kind != sig.kind) {
+        auto m = std::make_shared<MatrixData>();
+        m->dom = dom;
+        m->kind = sig.kind;
+        m->vals.alloc(sig.kind == 1 ? (size_t)L.nnzb * dim * dim : (size_t)dd->sp->ndofs);
+        A->data = m;
+        dom->live.push_back(m);
+    }
+    MatrixData& M = *A->data;
+    M.assembled = false;
+    M.gmg.clear();
+    M.dd = dd;
+    if (sig.kind == 1) {
+        const double* up = u ? u->d.p : nullptr;
+        if (dim == 2) assemble_hessian_kernels<2>(dom, dd, jac, up, M.vals.p);
+        else assemble_hessian_kernels<3>(dom, dd, jac, up, M.vals.p);
+    } else {
+        if (dim == 2) AB_LAUNCH(ctx, (k_mass_model<2>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, (const double*)nullptr, (const double*)nullptr, M.vals.p, (double*)nullptr);
+        else AB_LAUNCH(ctx, (k_mass_model<3>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, (const double*)nullptr, (const double*)nullptr, M.vals.p, (double*)nullptr);
+    }
+    M.sig = sig;
+    M.assembled = true;
+}
+
+template <int D>
+static void load_launch(Context* ctx, const LevelDev& L, const double* u, const double* lam, const double* q, const LoadParams& P, double* out) {
+    AB_LAUNCH(ctx, (k_assemble_load<D>), grid_for(L.ne, 128, ctx->num_sms * 16), 128, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u, lam, q, P, out);
+}
+
+static void assemble_defect(DomainDisc* dd, Vector* dvec, Vector* uarg) {
+    Domain* dom = dd->sp->dom;
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim();
+    const LevelDev& L = dom->dev[dom->top()];
+    AB_REQUIRE(dvec->sp->kind == dd->sp->kind && dvec->sp->ncomp == dd->sp->ncomp, AB_ERR_ARG, "assemble_defect: vector/space mismatch");
+    dev_fill(ctx, dvec->d.p, dvec->n(), 0.0);
+    for (ElemDisc* d : dd->discs) {
+        Vector* u = import_u(d, uarg);
+        const double* up = u ? u->d.p : nullptr;
+        const double* lam = d->imp_lam ? d->imp_lam->d.p : nullptr;
+        const double* q = d->imp_q ? d->imp_q->d.p : nullptr;
+        LoadParams P;
+        memset(&P, 0, sizeof P);
+        switch (d->kind) {
+            case AB_DISC_DEFORMATION_EQUATION: continue;   // jacobian only (DESIGN.md "Model")
+            case AB_DISC_DEFORMATION_RHS:
+            case AB_DISC_DEFORMATION_LARGE_RHS: {
+                P.use_S = 1;
+                P.tau = d->params[AB_PARAM_TAU];
+                P.w[0] = d->params[AB_PARAM_LAMBDA_VOL];
+                P.w[1] = d->params[AB_PARAM_LAMBDA_BARY_X];
+                P.w[2] = d->params[AB_PARAM_LAMBDA_BARY_Y];
+                P.w[3] = dim == 3 ? d->params[AB_PARAM_LAMBDA_BARY_Z] : 0.0;
+                if (d->kind == AB_DISC_DEFORMATION_LARGE_RHS) {
+                    P.w[0] += d->params[AB_PARAM_MULT_VOL];
+                    P.w[1] += d->params[AB_PARAM_MULT_BX];
+                    P.w[2] += d->params[AB_PARAM_MULT_BY];
+                    if (dim == 3) P.w[3] += d->params[AB_PARAM_MULT_BZ];
+                }
+                P.sign = dim == 3 ? 1.0 : -1.0;    // sign conventions of the 3D / 2D plugin generations, DESIGN.md "Signs"
+                break;
+            }
+            case AB_DISC_VOLUME_CONSTRAINT: P.w[0] = 1.0; P.sign = dim == 3 ? -1.0 : 1.0; break;
+            case AB_DISC_BARYCENTER_CONSTRAINT: {
+                const int k = (int)d->params[AB_PARAM_INDEX];
+                AB_REQUIRE(k >= 1 && k <= dim, AB_ERR_ARG, "barycenter constraint: set_index must be 1..dim");
+                P.w[k] = 1.0;
+                P.sign = dim == 3 ? -1.0 : 1.0;
+                break;
+            }
+            case AB_DISC_MASS_MODEL:
+                if (dim == 2) AB_LAUNCH(ctx, (k_mass_model<2>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, up, lam, (double*)nullptr, dvec->d.p);
+                else AB_LAUNCH(ctx, (k_mass_model<3>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, up, lam, (double*)nullptr, dvec->d.p);
+                continue;
+            case AB_DISC_LAMBDA_UPDATE:
+                if (dim == 2) AB_LAUNCH(ctx, (k_lambda_update<2>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, up, q, d->params[AB_PARAM_TAU], dvec->d.p);
+                else AB_LAUNCH(ctx, (k_lambda_update<3>), ew_grid(ctx, L.ne), 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, up, q, d->params[AB_PARAM_TAU], dvec->d.p);
+                continue;
+            default: AB_REQUIRE(false, AB_ERR_ARG, "unknown ElemDisc kind");
+        }
+        AB_REQUIRE(dd->sp->kind == AB_SPACE_P1, AB_ERR_ARG, "P1 ElemDisc in a non-P1 DomainDiscretization");
+        P.has_w = (P.w[0] != 0 || P.w[1] != 0 || P.w[2] != 0 || P.w[3] != 0) ? 1 : 0;
+        if (dim == 2) load_launch<2>(ctx, L, up, lam, q, P, dvec->d.p); else load_launch<3>(ctx, L, up, lam, q, P, dvec->d.p);
+    }
+    if (dd->sp->kind == AB_SPACE_P1) {
+        const unsigned char* mask = dd->mask(dom->top());
+        if (mask) {
+            if (dim == 2) AB_LAUNCH(ctx, (k_zero_dirichlet<2>), ew_grid(ctx, dvec->n()), 256, 0, L.nv, mask, dvec->d.p);
+            else AB_LAUNCH(ctx, (k_zero_dirichlet<3>), ew_grid(ctx, dvec->n()), 256, 0, L.nv, mask, dvec->d.p);
+        }
+    }
+    dvec->storage = AB_PST_ADDITIVE;
+    dvec->touch();
+}
+
+}  // namespace ab
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace ab;
+
+struct ab_context : Context {};
+struct ab_domain : Domain {};
+struct ab_space : Space {};
+struct ab_vector : Vector {};
+struct ab_elemdisc : ElemDisc {};
+struct ab_domaindisc : DomainDisc {};
+struct ab_operator : Operator {};
+struct ab_solver : Solver {};
+
+#define AB_TRY try {
+#define AB_CATCH                                                         \
+    }                                                                    \
+    catch (const ab::Error& e) { g_last_error = e.what(); return e.code; } \
+    catch (const std::exception& e) { g_last_error = e.what(); return AB_ERR_STATE; } \
+    return AB_OK;
+#define AB_CHECK_LAUNCH(ctx) AB_CUDA(cudaGetLastError())
+
+extern "C" {
+
+const char* ab_last_error(void) { return g_last_error.c_str(); }
+int ab_version(void) { return 100; }
+
+int ab_context_create(int device, void* stream, ab_context** out) {
+    AB_TRY
+    AB_REQUIRE(out, AB_ERR_ARG, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    AB_REQUIRE(e == cudaSuccess && ndev > 0, AB_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                                            " (libadmm_b200 has no CPU fallback)");
+    AB_REQUIRE(device >= 0 && device < ndev, AB_ERR_ARG, "device index out of range");
+    AB_CUDA(cudaSetDevice(device));
+    auto* c = new ab_context();
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    cudaDeviceProp prop;
+    AB_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    AB_CUDA(cudaMalloc((void**)&c->d_partials, sizeof(double) * Context::kMaxBlocks * Context::kMaxVals));
+    AB_CUDA(cudaMalloc((void**)&c->d_tickets, sizeof(unsigned int) * 4));
+    AB_CUDA(cudaMemset(c->d_tickets, 0, sizeof(unsigned int) * 4));
+    AB_CUDA(cudaMalloc((void**)&c->d_results, sizeof(double) * Context::kResultSlots));
+    AB_CUDA(cudaMallocHost((void**)&c->h_results, sizeof(double) * Context::kResultSlots));
+    *out = c;
+    AB_CATCH
+}
+int ab_context_destroy(ab_context* ctx) {
+    AB_TRY
+    if (!ctx) return AB_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_tickets); cudaFree(ctx->d_results); cudaFreeHost(ctx->h_results);
+    delete ctx;
+    AB_CATCH
+}
+int ab_context_synchronize(ab_context* ctx) {
+    AB_TRY
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_CATCH
+}
+int ab_context_launch_count(ab_context* ctx, int64_t* out) {
+    AB_TRY
+    *out = ctx->launches;
+    AB_CATCH
+}
+int ab_context_init_comm(ab_context*, int, int nranks, const void*) {
+    AB_TRY
+    AB_REQUIRE(nranks == 1, AB_ERR_UNSUPPORTED, "multi-GPU communicator not built in this revision");
+    AB_CATCH
+}
+int ab_nccl_unique_id(void*) {
+    AB_TRY
+    AB_REQUIRE(false, AB_ERR_UNSUPPORTED, "multi-GPU communicator not built in this revision");
+    AB_CATCH
+}
+
+// ---- domain ---------------------------------------------------------------------------------
+int ab_domain_load_ugx(ab_context* ctx, const char* path, ab_domain** out) {
+    AB_TRY
+    AB_REQUIRE(path && out, AB_ERR_ARG, "NULL argument");   // ctx may be NULL for host-only use (no ApproximationSpace)
+    auto d = std::make_unique<ab_domain>();
+    d->ctx = ctx;
+    std::string err;
+    AB_REQUIRE(load_ugx(path, d->mesh, err), AB_ERR_IO, err);
+    *out = d.release();
+    AB_CATCH
+}
+int ab_domain_create(ab_context* ctx, int dim, int nv, const double* xyz, int ne, const int32_t* elems, int nsubsets,
+                     const char* const* subset_names, const int32_t* vsub, const int32_t* esub, int n_sp_edges, const int32_t* sp_edges,
+                     const int32_t* sp_edges_sub, int n_sp_faces, const int32_t* sp_faces, const int32_t* sp_faces_sub, ab_domain** out) {
+    AB_TRY
+    AB_REQUIRE(xyz && elems && vsub && esub && out, AB_ERR_ARG, "NULL argument");
+    AB_REQUIRE(dim == 2 || dim == 3, AB_ERR_ARG, "dim must be 2 or 3");
+    auto d = std::make_unique<ab_domain>();
+    d->ctx = ctx;
+    d->mesh.dim = dim;
+    for (int i = 0; i < nsubsets; ++i) d->mesh.subset_names.push_back(subset_names[i]);
+    HostLevel L;
+    L.dim = dim; L.nv = nv; L.ne = ne;
+    L.xyz.assign(xyz, xyz + (size_t)nv * dim);
+    L.elems.assign(elems, elems + (size_t)ne * (dim + 1));
+    L.vsub.assign(vsub, vsub + nv);
+    L.esub.assign(esub, esub + ne);
+    if (n_sp_edges) { L.sp_edges.assign(sp_edges, sp_edges + 2 * (size_t)n_sp_edges); L.sp_edges_sub.assign(sp_edges_sub, sp_edges_sub + n_sp_edges); }
+    if (n_sp_faces) { L.sp_faces.assign(sp_faces, sp_faces + 3 * (size_t)n_sp_faces); L.sp_faces_sub.assign(sp_faces_sub, sp_faces_sub + n_sp_faces); }
+    for (int e = 0; e < ne * (dim + 1); ++e) AB_REQUIRE(elems[e] >= 0 && elems[e] < nv, AB_ERR_ARG, "element vertex index out of range");
+    d->mesh.levels.push_back(std::move(L));
+    *out = d.release();
+    AB_CATCH
+}
+int ab_domain_destroy(ab_domain* dom) {
+    AB_TRY
+    delete dom;
+    AB_CATCH
+}
+int ab_domain_refine(ab_domain* dom, int num_refs) {
+    AB_TRY
+    AB_REQUIRE(dom, AB_ERR_ARG, "NULL domain");
+    AB_REQUIRE(!dom->finalized, AB_ERR_STATE, "the hierarchy is frozen once an ApproximationSpace exists");
+    AB_REQUIRE(num_refs >= 0, AB_ERR_ARG, "numRefs < 0");
+    for (int r = 0; r < num_refs; ++r) {
+        HostLevel& C = dom->mesh.levels.back();
+        ensure_edges(C);
+        AB_REQUIRE((int64_t)C.nv + C.nedges() < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "level exceeds int32 vertex ids");
+        HostLevel F;
+        refine_level(C, F);
+        dom->mesh.levels.push_back(std::move(F));
+    }
+    AB_CATCH
+}
+int ab_domain_num_levels(ab_domain* dom, int* out) {
+    AB_TRY
+    *out = (int)dom->mesh.levels.size();
+    AB_CATCH
+}
+int ab_domain_level_info(ab_domain* dom, int level, int* dim, int* nv, int* ne, int* nedges, int* nv_coarse) {
+    AB_TRY
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    HostLevel& L = dom->mesh.levels[level];
+    if (dim) *dim = L.dim;
+    if (nv) *nv = L.nv;
+    if (ne) *ne = L.ne;
+    if (nv_coarse) *nv_coarse = L.nv_coarse;
+    if (nedges) {
+        if (dom->finalized) *nedges = (int)((dom->dev[level].nnzb - L.nv) / 2);
+        else { ensure_edges(L); *nedges = (int)L.nedges(); }
+    }
+    AB_CATCH
+}
+int ab_domain_get_level(ab_domain* dom, int level, double* xyz, int32_t* elems, int32_t* vsub, int32_t* parent_a, int32_t* parent_b) {
+    AB_TRY
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    HostLevel& L = dom->mesh.levels[level];
+    if (xyz) {
+        if (dom->host_xyz_stale) {
+            HostLevel& T = dom->mesh.levels.back();
+            AB_CUDA(cudaMemcpy(T.xyz.data(), dom->dev[dom->top()].xyz.p, T.xyz.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int l = dom->top() - 1; l >= 0; --l) {
+                HostLevel& H = dom->mesh.levels[l];
+                std::copy(T.xyz.begin(), T.xyz.begin() + H.xyz.size(), H.xyz.begin());
+            }
+            dom->host_xyz_stale = false;
+        }
+        memcpy(xyz, L.xyz.data(), L.xyz.size() * sizeof(double));
+    }
+    if (elems) memcpy(elems, L.elems.data(), L.elems.size() * sizeof(int32_t));
+    if (vsub) memcpy(vsub, L.vsub.data(), L.vsub.size() * sizeof(int32_t));
+    if (parent_a && !L.pa.empty()) memcpy(parent_a, L.pa.data(), L.pa.size() * sizeof(int32_t));
+    if (parent_b && !L.pb.empty()) memcpy(parent_b, L.pb.data(), L.pb.size() * sizeof(int32_t));
+    AB_CATCH
+}
+int ab_domain_subset_index(ab_domain* dom, const char* name, int* out) {
+    AB_TRY
+    const int i = dom->mesh.subset_index(name);
+    AB_REQUIRE(i >= 0, AB_ERR_ARG, std::string("unknown subset '") + name + "'");
+    *out = i;
+    AB_CATCH
+}
+int ab_transform_domain_by_displacement(ab_domain* dom, ab_vector* u) {
+    AB_TRY
+    AB_REQUIRE(dom->finalized, AB_ERR_STATE, "domain has no ApproximationSpace yet");
+    AB_REQUIRE(u->sp->kind == AB_SPACE_P1 && u->sp->ncomp == dom->dim() && u->sp->dom == dom, AB_ERR_ARG, "displacement must be a P1 dim-vector on this domain");
+    LevelDev& L = dom->dev[dom->top()];
+    dev_axpby(dom->ctx, u->n(), 1.0, L.xyz.p, 1.0, u->d.p, L.xyz.p);
+    dom->coords_version = ++g_version_counter;
+    dom->host_xyz_stale = true;
+    AB_CHECK_LAUNCH(dom->ctx);
+    AB_CATCH
+}
+
+// ---- space ----------------------------------------------------------------------------------
+int ab_space_create(ab_domain* dom, int kind, int ncomp, ab_space** out) {
+    AB_TRY
+    AB_REQUIRE(dom && out, AB_ERR_ARG, "NULL argument");
+    AB_REQUIRE(kind == AB_SPACE_P0 || kind == AB_SPACE_P1, AB_ERR_ARG, "unknown space kind");
+    AB_REQUIRE(ncomp >= 1 && ncomp <= 9, AB_ERR_ARG, "ncomp out of range");
+    AB_REQUIRE(dom->ctx, AB_ERR_STATE, "domain was created without a context (host-only); ApproximationSpace needs a GPU context");
+    dom->finalize();
+    auto* s = new ab_space();
+    s->dom = dom; s->kind = kind; s->ncomp = ncomp;
+    const HostLevel& T = dom->mesh.levels.back();
+    s->ndofs = (int64_t)(kind == AB_SPACE_P1 ? T.nv : T.ne) * ncomp;
+    *out = s;
+    AB_CATCH
+}
+int ab_space_destroy(ab_space* sp) {
+    AB_TRY
+    delete sp;
+    AB_CATCH
+}
+int ab_space_num_dofs(ab_space* sp, int64_t* out) {
+    AB_TRY
+    *out = sp->ndofs;
+    AB_CATCH
+}
+
+// ---- vectors --------------------------------------------------------------------------------
+int ab_vector_create(ab_space* sp, ab_vector** out) {
+    AB_TRY
+    auto v = std::make_unique<ab_vector>();
+    v->sp = sp;
+    v->d.alloc((size_t)sp->ndofs);
+    v->d.zero(sp->dom->ctx->stream);
+    v->id = ++g_version_counter;
+    v->touch();
+    *out = v.release();
+    AB_CATCH
+}
+int ab_vector_destroy(ab_vector* v) {
+    AB_TRY
+    delete v;
+    AB_CATCH
+}
+int ab_vector_set(ab_vector* v, double c) {
+    AB_TRY
+    dev_fill(v->sp->dom->ctx, v->d.p, v->n(), c);
+    v->storage = AB_PST_CONSISTENT;
+    v->touch();
+    AB_CHECK_LAUNCH(v->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_vector_upload(ab_vector* v, const double* host, int storage) {
+    AB_TRY
+    Context* ctx = v->sp->dom->ctx;
+    AB_CUDA(cudaMemcpyAsync(v->d.p, host, v->n() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    v->storage = storage ? storage : AB_PST_CONSISTENT;
+    v->touch();
+    AB_CATCH
+}
+int ab_vector_download(ab_vector* v, double* host) {
+    AB_TRY
+    Context* ctx = v->sp->dom->ctx;
+    AB_CUDA(cudaMemcpyAsync(host, v->d.p, v->n() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_CATCH
+}
+int ab_vector_device_ptr(ab_vector* v, void** out, int64_t* n) {
+    AB_TRY
+    *out = v->d.p;
+    if (n) *n = v->n();
+    v->touch();   // the caller may write through the pointer
+    AB_CATCH
+}
+int ab_vector_storage(ab_vector* v, int* out) {
+    AB_TRY
+    *out = v->storage;
+    AB_CATCH
+}
+int ab_vector_change_storage(ab_vector* v, int storage) {
+    AB_TRY
+    // single-GPU: additive, consistent and unique representations coincide; only the flag changes.
+    v->storage = storage;
+    AB_CATCH
+}
+int ab_vec_scale_assign(ab_vector* dst, double a, ab_vector* src) {
+    AB_TRY
+    AB_REQUIRE(dst->n() == src->n(), AB_ERR_ARG, "VecScaleAssign: size mismatch");
+    dev_axpby(dst->sp->dom->ctx, dst->n(), a, src->d.p, 0.0, nullptr, dst->d.p);
+    dst->storage = src->storage;
+    dst->touch();
+    AB_CHECK_LAUNCH(dst->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_vec_scale_add2(ab_vector* dst, double a, ab_vector* x, double b, ab_vector* y) {
+    AB_TRY
+    AB_REQUIRE(dst->n() == x->n() && dst->n() == y->n(), AB_ERR_ARG, "VecScaleAdd2: size mismatch");
+    dev_axpby(dst->sp->dom->ctx, dst->n(), a, x->d.p, b, y->d.p, dst->d.p);
+    dst->storage = (x->storage == y->storage) ? x->storage : (x->storage & y->storage ? (x->storage & y->storage) : x->storage);
+    dst->touch();
+    AB_CHECK_LAUNCH(dst->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_vec_prod_multi(int n, ab_vector* const* xs, ab_vector* y, double* out) {
+    AB_TRY
+    AB_REQUIRE(n >= 1 && n <= 4, AB_ERR_ARG, "ab_vec_prod_multi: n must be 1..4");
+    Context* ctx = y->sp->dom->ctx;
+    const double* p[4];
+    for (int i = 0; i < n; ++i) { AB_REQUIRE(xs[i]->n() == y->n(), AB_ERR_ARG, "VecProd: size mismatch"); p[i] = xs[i]->d.p; }
+    dev_dots(ctx, y->n(), n, p, y->d.p, ctx->d_results);
+    read_back(ctx, ctx->d_results, n, out);
+    AB_CATCH
+}
+int ab_vec_prod(ab_vector* x, ab_vector* y, double* out) {
+    ab_vector* xs[1] = {x};
+    return ab_vec_prod_multi(1, xs, y, out);
+}
+int ab_vec_norm(ab_vector* x, double* out) {
+    double v = 0;
+    int rc = ab_vec_prod(x, x, &v);
+    if (rc == AB_OK) *out = std::sqrt(v);
+    return rc;
+}
+int ab_l2norm_all(ab_vector* v, double* out) {
+    AB_TRY
+    Domain* dom = v->sp->dom;
+    Context* ctx = dom->ctx;
+    const LevelDev& L = dom->dev[dom->top()];
+    const int dim = dom->dim();
+    const int g = red_grid(ctx, L.ne);
+    int nc;
+    if (v->sp->kind == AB_SPACE_P1) {
+        AB_REQUIRE(v->sp->ncomp == dim, AB_ERR_UNSUPPORTED, "L2Norm: P1 spaces with ncomp != dim are not supported");
+        nc = dim;
+        if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p1<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+        else AB_LAUNCH(ctx, (k_l2norm_p1<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    } else {
+        AB_REQUIRE(v->sp->ncomp == dim * dim, AB_ERR_UNSUPPORTED, "L2Norm: P0 spaces with ncomp != dim*dim are not supported");
+        nc = dim * dim;
+        if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p0<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+        else AB_LAUNCH(ctx, (k_l2norm_p0<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    }
+    read_back(ctx, ctx->d_results, nc, out);
+    for (int i = 0; i < nc; ++i) out[i] = std::sqrt(out[i]);
+    AB_CATCH
+}
+int ab_l2norm(ab_vector* v, int comp, double* out) {
+    double tmp[9];
+    int rc = ab_l2norm_all(v, tmp);
+    if (rc != AB_OK) return rc;
+    if (comp < 0 || comp >= v->sp->ncomp) { g_last_error = "L2Norm: component out of range"; return AB_ERR_ARG; }
+    *out = tmp[comp];
+    return AB_OK;
+}
+
+// ---- elem discs -----------------------------------------------------------------------------
+int ab_elemdisc_create(ab_space* sp, int kind, ab_elemdisc** out) {
+    AB_TRY
+    AB_REQUIRE(kind >= AB_DISC_DEFORMATION_EQUATION && kind <= AB_DISC_LAMBDA_UPDATE, AB_ERR_ARG, "unknown ElemDisc kind");
+    auto* d = new ab_elemdisc();
+    d->sp = sp; d->kind = kind;
+    for (double& p : d->params) p = 0.0;
+    d->params[AB_PARAM_STEP_LENGTH] = 1.0;
+    d->params[AB_PARAM_TAU] = 1.0;
+    d->params[AB_PARAM_INDEX] = 1.0;
+    d->params[AB_PARAM_QUAD_ORDER] = 1.0;
+    *out = d;
+    AB_CATCH
+}
+int ab_elemdisc_destroy(ab_elemdisc* d) {
+    AB_TRY
+    delete d;
+    AB_CATCH
+}
+int ab_elemdisc_set_param(ab_elemdisc* d, int param, double value) {
+    AB_TRY
+    AB_REQUIRE(param >= 1 && param <= 15, AB_ERR_ARG, "unknown ElemDisc parameter");
+    d->params[param] = value;
+    AB_CATCH
+}
+int ab_elemdisc_get_param(ab_elemdisc* d, int param, double* value) {
+    AB_TRY
+    AB_REQUIRE(param >= 1 && param <= 15, AB_ERR_ARG, "unknown ElemDisc parameter");
+    *value = d->params[param];
+    AB_CATCH
+}
+int ab_elemdisc_bind(ab_elemdisc* d, int import, ab_vector* v) {
+    AB_TRY
+    const int dim = d->sp->dom->dim();
+    if (import == AB_IMPORT_DEFORMATION) {
+        AB_REQUIRE(!v || (v->sp->kind == AB_SPACE_P1 && v->sp->ncomp == dim), AB_ERR_ARG, "deformation import must be a P1 dim-vector");
+        d->imp_u = v;
+    } else if (import == AB_IMPORT_LAMBDA || import == AB_IMPORT_Q) {
+        AB_REQUIRE(!v || (v->sp->kind == AB_SPACE_P0 && v->sp->ncomp == dim * dim), AB_ERR_ARG, "tensor import must be a P0 dim*dim function");
+        (import == AB_IMPORT_LAMBDA ? d->imp_lam : d->imp_q) = v;
+    } else AB_REQUIRE(false, AB_ERR_ARG, "unknown import");
+    AB_CATCH
+}
+
+// ---- domain disc ----------------------------------------------------------------------------
+int ab_domaindisc_create(ab_space* sp, ab_domaindisc** out) {
+    AB_TRY
+    auto* dd = new ab_domaindisc();
+    dd->sp = sp;
+    *out = dd;
+    AB_CATCH
+}
+int ab_domaindisc_destroy(ab_domaindisc* dd) {
+    AB_TRY
+    delete dd;
+    AB_CATCH
+}
+int ab_domaindisc_add_elemdisc(ab_domaindisc* dd, ab_elemdisc* d) {
+    AB_TRY
+    AB_REQUIRE(d->sp->dom == dd->sp->dom, AB_ERR_ARG, "ElemDisc and DomainDiscretization live on different domains");
+    dd->discs.push_back(d);
+    AB_CATCH
+}
+int ab_domaindisc_add_dirichlet(ab_domaindisc* dd, const char* subset, int comp, double value) {
+    AB_TRY
+    AB_REQUIRE(value == 0.0, AB_ERR_UNSUPPORTED, "only homogeneous Dirichlet values are used on the hot path (3d_admm.lua:447-457)");
+    AB_REQUIRE(dd->sp->kind == AB_SPACE_P1 && comp >= 0 && comp < dd->sp->ncomp, AB_ERR_ARG, "Dirichlet component out of range");
+    const int si = dd->sp->dom->mesh.subset_index(subset);
+    AB_REQUIRE(si >= 0, AB_ERR_ARG, std::string("unknown subset '") + subset + "'");
+    dd->dir.push_back({si, comp});
+    dd->masks_valid = false;
+    AB_CATCH
+}
+int ab_domaindisc_assemble_jacobian(ab_domaindisc* dd, ab_operator* A, ab_vector* u) {
+    AB_TRY
+    assemble_jacobian(dd, A, u);
+    AB_CHECK_LAUNCH(dd->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_domaindisc_assemble_defect(ab_domaindisc* dd, ab_vector* d, ab_vector* u) {
+    AB_TRY
+    assemble_defect(dd, d, u);
+    AB_CHECK_LAUNCH(dd->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_domaindisc_adjust_solution(ab_domaindisc* dd, ab_vector* u) {
+    AB_TRY
+    Domain* dom = dd->sp->dom;
+    const unsigned char* mask = dd->mask(dom->top());
+    if (mask) {
+        const LevelDev& L = dom->dev[dom->top()];
+        if (dom->dim() == 2) AB_LAUNCH(dom->ctx, (k_zero_dirichlet<2>), ew_grid(dom->ctx, u->n()), 256, 0, L.nv, mask, u->d.p);
+        else AB_LAUNCH(dom->ctx, (k_zero_dirichlet<3>), ew_grid(dom->ctx, u->n()), 256, 0, L.nv, mask, u->d.p);
+        u->touch();
+    }
+    AB_CHECK_LAUNCH(dom->ctx);
+    AB_CATCH
+}
+
+// ---- operator -------------------------------------------------------------------------------
+int ab_operator_create(ab_domaindisc* dd, ab_operator** out) {
+    AB_TRY
+    auto* A = new ab_operator();
+    A->dd = dd;
+    *out = A;
+    AB_CATCH
+}
+int ab_operator_destroy(ab_operator* A) {
+    AB_TRY
+    delete A;
+    AB_CATCH
+}
+int ab_operator_apply(ab_operator* A, ab_vector* y, ab_vector* x) {
+    AB_TRY
+    AB_REQUIRE(A->data && A->data->assembled, AB_ERR_STATE, "operator not assembled");
+    Domain* dom = A->data->dom;
+    Context* ctx = dom->ctx;
+    if (A->data->kind == 1) spmv(ctx, dom->dim(), dom->dev[dom->top()], A->data->vals.p, 0, 0, x->d.p, nullptr, y->d.p);
+    else AB_LAUNCH(ctx, k_diag_apply_dot, red_grid(ctx, x->n()), 256, 0, x->n(), A->data->vals.p, x->d.p, y->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    y->storage = AB_PST_ADDITIVE;
+    y->touch();
+    AB_CHECK_LAUNCH(ctx);
+    AB_CATCH
+}
+int ab_operator_info(ab_operator* A, int* block, int64_t* nb, int64_t* nnzb) {
+    AB_TRY
+    AB_REQUIRE(A->data, AB_ERR_STATE, "operator not assembled");
+    Domain* dom = A->data->dom;
+    if (A->data->kind == 1) {
+        if (block) *block = dom->dim();
+        if (nb) *nb = dom->dev[dom->top()].nv;
+        if (nnzb) *nnzb = dom->dev[dom->top()].nnzb;
+    } else {
+        if (block) *block = 1;
+        if (nb) *nb = (int64_t)A->data->vals.n;
+        if (nnzb) *nnzb = (int64_t)A->data->vals.n;
+    }
+    AB_CATCH
+}
+int ab_operator_download(ab_operator* A, int32_t* rowptr, int32_t* colidx, double* vals) {
+    AB_TRY
+    AB_REQUIRE(A->data && A->data->assembled, AB_ERR_STATE, "operator not assembled");
+    Domain* dom = A->data->dom;
+    AB_CUDA(cudaStreamSynchronize(dom->ctx->stream));
+    if (A->data->kind == 1) {
+        const LevelDev& L = dom->dev[dom->top()];
+        if (rowptr) AB_CUDA(cudaMemcpy(rowptr, L.rowptr.p, ((size_t)L.nv + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        if (colidx) AB_CUDA(cudaMemcpy(colidx, L.colidx.p, (size_t)L.nnzb * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+        const int64_t n = (int64_t)A->data->vals.n;
+        if (rowptr) for (int64_t i = 0; i <= n; ++i) rowptr[i] = (int32_t)i;
+        if (colidx) for (int64_t i = 0; i < n; ++i) colidx[i] = (int32_t)i;
+    }
+    if (vals) AB_CUDA(cudaMemcpy(vals, A->data->vals.p, A->data->vals.n * sizeof(double), cudaMemcpyDeviceToHost));
+    AB_CATCH
+}
+
+// ---- solvers --------------------------------------------------------------------------------
+int ab_solver_create_bicgstab_gmg(ab_space* sp, const ab_gmg_desc* desc, ab_solver** out) {
+    AB_TRY
+    AB_REQUIRE(sp && desc && out, AB_ERR_ARG, "NULL argument");
+    AB_REQUIRE(sp->kind == AB_SPACE_P1 && sp->ncomp == sp->dom->dim(), AB_ERR_ARG, "BiCGStab+GMG needs the P1 deformation space");
+    AB_REQUIRE(desc->rap != 0, AB_ERR_UNSUPPORTED, "rap=false (re-discretised coarse operators) is not implemented; the reference uses rap=true (u3:27)");
+    AB_REQUIRE(desc->base_level == 0, AB_ERR_UNSUPPORTED, "baseLevel must be 0 (u3:19)");
+    AB_REQUIRE(desc->smoother == AB_SMOOTHER_CHEBYSHEV || desc->smoother == AB_SMOOTHER_JACOBI, AB_ERR_ARG, "unknown smoother");
+    auto* s = new ab_solver();
+    s->sp = sp; s->type = 1; s->desc = *desc;
+    if (s->desc.cheb_ratio <= 1.0) s->desc.cheb_ratio = 6.0;
+    if (s->desc.jacobi_damp <= 0.0) s->desc.jacobi_damp = 0.66;
+    *out = s;
+    AB_CATCH
+}
+int ab_solver_create_cg_jacobi(ab_space* sp, double damp, int max_iterations, double abs_tol, double red_tol, int verbose, ab_solver** out) {
+    AB_TRY
+    auto* s = new ab_solver();
+    s->sp = sp; s->type = 2; s->damp = damp;
+    s->desc.max_iterations = max_iterations; s->desc.abs_tol = abs_tol; s->desc.red_tol = red_tol; s->desc.verbose = verbose;
+    *out = s;
+    AB_CATCH
+}
+int ab_solver_destroy(ab_solver* s) {
+    AB_TRY
+    delete s;
+    AB_CATCH
+}
+int ab_solver_init(ab_solver* s, ab_operator* A, ab_vector*) {
+    AB_TRY
+    solver_init(s, A);
+    AB_CHECK_LAUNCH(s->sp->dom->ctx);
+    AB_CATCH
+}
+static int solver_apply_impl(ab_solver* s, ab_vector* x, ab_vector* b, int* converged, bool ret_def) {
+    AB_TRY
+    AB_REQUIRE(s->A, AB_ERR_STATE, "solver:apply before solver:init");
+    AB_REQUIRE(x->n() == s->sp->ndofs && b->n() == s->sp->ndofs, AB_ERR_ARG, "solver:apply: vector size mismatch");
+    const bool ok = s->type == 1 ? bicgstab_apply(s, x, b, ret_def) : cg_jacobi_apply(s, x, b, ret_def);
+    x->storage = AB_PST_CONSISTENT;
+    if (converged) *converged = ok ? 1 : 0;
+    AB_CHECK_LAUNCH(s->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_solver_apply(ab_solver* s, ab_vector* x, ab_vector* b, int* converged) { return solver_apply_impl(s, x, b, converged, false); }
+int ab_solver_apply_return_defect(ab_solver* s, ab_vector* x, ab_vector* b, int* converged) { return solver_apply_impl(s, x, b, converged, true); }
+int ab_solver_step(ab_solver* s, int* out) {
+    AB_TRY
+    *out = s->last_steps;
+    AB_CATCH
+}
+int ab_solver_last_defect(ab_solver* s, double* out) {
+    AB_TRY
+    *out = s->last_defect;
+    AB_CATCH
+}
+int ab_solver_vcycle(ab_solver* s, ab_vector* z, ab_vector* r) {
+    AB_TRY
+    AB_REQUIRE(s->type == 1 && s->gmg, AB_ERR_STATE, "ab_solver_vcycle needs an initialised BiCGStab+GMG solver");
+    s->gmg->apply(r->d.p, z->d.p);
+    z->touch();
+    AB_CHECK_LAUNCH(s->sp->dom->ctx);
+    AB_CATCH
+}
+int ab_solver_level_info(ab_solver* s, int level, int64_t* nb, int64_t* nnzb) {
+    AB_TRY
+    Domain* dom = s->sp->dom;
+    AB_REQUIRE(level >= 0 && level <= dom->top(), AB_ERR_ARG, "level out of range");
+    if (nb) *nb = dom->dev[level].nv;
+    if (nnzb) *nnzb = dom->dev[level].nnzb;
+    AB_CATCH
+}
+
+// ---- ADMM free functions ----------------------------------------------------------------------
+static int project_impl(ab_vector* qp, ab_vector* q, double sigma, bool spectral) {
+    AB_TRY
+    Domain* dom = q->sp->dom;
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim();
+    AB_REQUIRE(q->sp->kind == AB_SPACE_P0 && q->sp->ncomp == dim * dim && qp->n() == q->n(), AB_ERR_ARG, "projection needs P0 dim*dim tensors");
+    const int64_t ne = dom->dev[dom->top()].ne;
+    if (spectral) {
+        AB_REQUIRE(dim == 2, AB_ERR_UNSUPPORTED, "ProjectWithSpectralNorm exists for 2D only (2d_admm.lua:902)");
+        AB_LAUNCH(ctx, k_project_spectral, ew_grid(ctx, ne), 256, 0, ne, sigma, q->d.p, qp->d.p);
+    } else if (dim == 2) AB_LAUNCH(ctx, (k_project_frobenius<4>), ew_grid(ctx, ne), 256, 0, ne, sigma, q->d.p, qp->d.p);
+    else AB_LAUNCH(ctx, (k_project_frobenius<9>), ew_grid(ctx, ne), 256, 0, ne, sigma, q->d.p, qp->d.p);
+    qp->storage = q->storage;
+    qp->touch();
+    AB_CHECK_LAUNCH(ctx);
+    AB_CATCH
+}
+int ab_project_frobenius(ab_vector* qp, ab_vector* q, double sigma) { return project_impl(qp, q, sigma, false); }
+int ab_project_spectral(ab_vector* qp, ab_vector* q, double sigma) { return project_impl(qp, q, sigma, true); }
+
+static int max_norm_impl(ab_vector* u, double* out, bool spectral) {
+    AB_TRY
+    Domain* dom = u->sp->dom;
+    Context* ctx = dom->ctx;
+    const LevelDev& L = dom->dev[dom->top()];
+    AB_REQUIRE(u->sp->kind == AB_SPACE_P1 && u->sp->ncomp == dom->dim(), AB_ERR_ARG, "needs the P1 deformation function");
+    const int g = red_grid(ctx, L.ne);
+    if (dom->dim() == 2) {
+        if (spectral) AB_LAUNCH(ctx, (k_max_grad_norm<2, 1>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+        else AB_LAUNCH(ctx, (k_max_grad_norm<2, 0>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    } else {
+        AB_REQUIRE(!spectral, AB_ERR_UNSUPPORTED, "MaxSpectralNorm exists for 2D only (2d_admm.lua:901)");
+        AB_LAUNCH(ctx, (k_max_grad_norm<3, 0>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    }
+    read_back(ctx, ctx->d_results, 1, out);
+    AB_CATCH
+}
+int ab_max_frobenius_norm(ab_vector* u, double* out) { return max_norm_impl(u, out, false); }
+int ab_max_spectral_norm(ab_vector* u, double* out) { return max_norm_impl(u, out, true); }
+
+static int vol_bary_impl(ab_vector* u, double* out4) {
+    AB_TRY
+    Domain* dom = u->sp->dom;
+    Context* ctx = dom->ctx;
+    const LevelDev& L = dom->dev[dom->top()];
+    AB_REQUIRE(u->sp->kind == AB_SPACE_P1 && u->sp->ncomp == dom->dim(), AB_ERR_ARG, "needs the P1 deformation function");
+    const int g = red_grid(ctx, L.ne);
+    if (dom->dim() == 2) AB_LAUNCH(ctx, (k_volume_barycenter<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    else AB_LAUNCH(ctx, (k_volume_barycenter<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    read_back(ctx, ctx->d_results, dom->dim() + 1, out4);
+    AB_CATCH
+}
+int ab_volume_defect(ab_vector* u, double reference_volume, double* out) {
+    double t[4];
+    int rc = vol_bary_impl(u, t);
+    if (rc == AB_OK) *out = t[0] - reference_volume;
+    return rc;
+}
+int ab_barycenter_defect(ab_vector* u, double* out_dim) {
+    double t[4];
+    int rc = vol_bary_impl(u, t);
+    if (rc == AB_OK) for (int k = 0; k < u->sp->dom->dim(); ++k) out_dim[k] = t[1 + k];
+    return rc;
+}
+int ab_set_zero_away_from_subset(ab_vector* v, const char* subset) {
+    AB_TRY
+    Domain* dom = v->sp->dom;
+    Context* ctx = dom->ctx;
+    AB_REQUIRE(v->sp->kind == AB_SPACE_P1, AB_ERR_ARG, "SetZeroAwayFromSubset needs a P1 function");
+    const int si = dom->mesh.subset_index(subset);
+    AB_REQUIRE(si >= 0, AB_ERR_ARG, std::string("unknown subset '") + subset + "'");
+    AB_LAUNCH(ctx, k_zero_away_from_subset, ew_grid(ctx, v->n()), 256, 0, v->n(), v->sp->ncomp, dom->dev[dom->top()].vsub.p, si, v->d.p);
+    v->touch();
+    AB_CHECK_LAUNCH(ctx);
+    AB_CATCH
+}
+
+}  // extern "C"

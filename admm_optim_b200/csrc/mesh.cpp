@@ -1,0 +1,345 @@
+// Host-side grid hierarchy (see mesh.hpp).  Compiled with -ffp-contract=off so that the
+// shortest-diagonal rule evaluates exactly the same doubles as the NumPy oracle.
+#include "mesh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#if defined(_OPENMP)
+#include <omp.h>
+#include <parallel/algorithm>
+#define AB_SORT(b, e) __gnu_parallel::sort((b), (e))
+#else
+#define AB_SORT(b, e) std::sort((b), (e))
+#endif
+
+namespace ab {
+
+int HostMesh::subset_index(const std::string& name) const {
+    for (size_t i = 0; i < subset_names.size(); ++i)
+        if (subset_names[i] == name) return (int)i;
+    return -1;
+}
+
+static const int LE2[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+static const int LE3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+
+static inline uint64_t ekey(int32_t a, int32_t b) {
+    uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    return ((uint64_t)lo << 32) | hi;
+}
+
+void ensure_edges(HostLevel& L) {
+    if (L.have_edges) return;
+    const int nen = L.dim + 1, nle = L.dim == 3 ? 6 : 3;
+    std::vector<uint64_t> keys((size_t)L.ne * nle);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < L.ne; ++e) {
+        const int32_t* v = &L.elems[(size_t)e * nen];
+        for (int k = 0; k < nle; ++k) {
+            const int* le = L.dim == 3 ? LE3[k] : LE2[k];
+            keys[(size_t)e * nle + k] = ekey(v[le[0]], v[le[1]]);
+        }
+    }
+    AB_SORT(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    L.edges.resize(keys.size() * 2);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)keys.size(); ++i) {
+        L.edges[2 * i] = (int32_t)(keys[i] >> 32);
+        L.edges[2 * i + 1] = (int32_t)(keys[i] & 0xffffffffu);
+    }
+    L.have_edges = true;
+}
+
+namespace {
+struct EdgeFinder {
+    const int32_t* e;
+    int64_t n;
+    std::vector<int64_t> start;   // first edge with lo == v  (size nv+1)
+    EdgeFinder(const HostLevel& L) : e(L.edges.data()), n(L.nedges()), start((size_t)L.nv + 1, 0) {
+        for (int64_t i = 0; i < n; ++i) start[e[2 * i] + 1]++;
+        for (int v = 0; v < L.nv; ++v) start[v + 1] += start[v];
+    }
+    inline int64_t find(int32_t a, int32_t b) const {
+        int32_t lo = a < b ? a : b, hi = a < b ? b : a;
+        int64_t l = start[lo], r = start[lo + 1];
+        while (l < r) {
+            int64_t m = (l + r) >> 1;
+            if (e[2 * m + 1] < hi) l = m + 1; else r = m;
+        }
+        return l;   // caller guarantees existence
+    }
+};
+
+inline double sqdist(const double* p, const double* q, int dim) {
+    double d0 = p[0] - q[0];
+    double acc = d0 * d0;
+    for (int c = 1; c < dim; ++c) {
+        double dc = p[c] - q[c];
+        acc = acc + dc * dc;
+    }
+    return acc;
+}
+inline double det3(const double* x0, const double* x1, const double* x2, const double* x3) {
+    double a[3], b[3], c[3];
+    for (int k = 0; k < 3; ++k) { a[k] = x1[k] - x0[k]; b[k] = x2[k] - x0[k]; c[k] = x3[k] - x0[k]; }
+    return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+struct SpEdge { int32_t lo, hi, sub; };
+}  // namespace
+
+void refine_level(const HostLevel& C, HostLevel& F) {
+    const int dim = C.dim, nv = C.nv;
+    const int64_t ned = C.nedges();
+    EdgeFinder ef(C);
+    F.dim = dim;
+    F.nv_coarse = nv;
+    F.nv = nv + (int)ned;
+    F.xyz.resize((size_t)F.nv * dim);
+    std::copy(C.xyz.begin(), C.xyz.end(), F.xyz.begin());
+    F.pa.resize(ned);
+    F.pb.resize(ned);
+    const int vol_sub = C.esub.empty() ? 0 : C.esub[0];
+    F.vsub.assign((size_t)F.nv, vol_sub);
+    std::copy(C.vsub.begin(), C.vsub.end(), F.vsub.begin());
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < ned; ++k) {
+        int32_t a = C.edges[2 * k], b = C.edges[2 * k + 1];
+        F.pa[k] = a;
+        F.pb[k] = b;
+        for (int c = 0; c < dim; ++c) F.xyz[(size_t)(nv + k) * dim + c] = 0.5 * (C.xyz[(size_t)a * dim + c] + C.xyz[(size_t)b * dim + c]);
+    }
+    const int64_t nse = (int64_t)C.sp_edges_sub.size();
+    for (int64_t i = 0; i < nse; ++i) F.vsub[nv + ef.find(C.sp_edges[2 * i], C.sp_edges[2 * i + 1])] = C.sp_edges_sub[i];
+    auto mid = [&](int32_t a, int32_t b) -> int32_t { return (int32_t)(nv + ef.find(a, b)); };
+
+    const int nch = dim == 3 ? 8 : 4, nen = dim + 1;
+    F.ne = C.ne * nch;
+    F.elems.resize((size_t)F.ne * nen);
+    F.esub.resize((size_t)F.ne);
+    const double* X = F.xyz.data();
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < C.ne; ++e) {
+        const int32_t* v = &C.elems[(size_t)e * nen];
+        int32_t* out = &F.elems[(size_t)e * nch * nen];
+        for (int c = 0; c < nch; ++c) F.esub[(size_t)e * nch + c] = C.esub[e];
+        if (dim == 2) {
+            int32_t a = v[0], b = v[1], c = v[2];
+            int32_t mab = mid(a, b), mbc = mid(b, c), mca = mid(c, a);
+            int32_t ch[4][3] = {{a, mab, mca}, {mab, b, mbc}, {mca, mbc, c}, {mab, mbc, mca}};
+            std::memcpy(out, ch, sizeof(ch));
+        } else {
+            int32_t m01 = mid(v[0], v[1]), m02 = mid(v[0], v[2]), m03 = mid(v[0], v[3]);
+            int32_t m12 = mid(v[1], v[2]), m13 = mid(v[1], v[3]), m23 = mid(v[2], v[3]);
+            double d0 = sqdist(X + 3 * (size_t)m01, X + 3 * (size_t)m23, 3);
+            double d1 = sqdist(X + 3 * (size_t)m02, X + 3 * (size_t)m13, 3);
+            double d2 = sqdist(X + 3 * (size_t)m03, X + 3 * (size_t)m12, 3);
+            int choice = 0;
+            double best = d0;
+            if (d1 < best) { choice = 1; best = d1; }
+            if (d2 < best) { choice = 2; }
+            int32_t p, q, c0, c1, c2, c3;
+            if (choice == 0)      { p = m01; q = m23; c0 = m02; c1 = m03; c2 = m13; c3 = m12; }
+            else if (choice == 1) { p = m02; q = m13; c0 = m01; c1 = m03; c2 = m23; c3 = m12; }
+            else                  { p = m03; q = m12; c0 = m01; c1 = m02; c2 = m23; c3 = m13; }
+            int32_t ch[8][4] = {{v[0], m01, m02, m03}, {m01, v[1], m12, m13}, {m02, m12, v[2], m23}, {m03, m13, m23, v[3]},
+                                {p, q, c0, c1}, {p, q, c1, c2}, {p, q, c2, c3}, {p, q, c3, c0}};
+            for (int c = 0; c < 8; ++c) {
+                if (det3(X + 3 * (size_t)ch[c][0], X + 3 * (size_t)ch[c][1], X + 3 * (size_t)ch[c][2], X + 3 * (size_t)ch[c][3]) < 0)
+                    std::swap(ch[c][2], ch[c][3]);
+            }
+            std::memcpy(out, ch, sizeof(ch));
+        }
+    }
+    // special entities of the fine level
+    std::vector<SpEdge> ne_;
+    ne_.reserve((size_t)nse * 2 + C.sp_faces_sub.size() * 3);
+    auto push = [&](int32_t a, int32_t b, int32_t s) { ne_.push_back({a < b ? a : b, a < b ? b : a, s}); };
+    for (int64_t i = 0; i < nse; ++i) {
+        int32_t a = C.sp_edges[2 * i], b = C.sp_edges[2 * i + 1], m = mid(a, b);
+        push(a, m, C.sp_edges_sub[i]);
+        push(b, m, C.sp_edges_sub[i]);
+    }
+    const int64_t nsf = (int64_t)C.sp_faces_sub.size();
+    F.sp_faces.clear();
+    F.sp_faces_sub.clear();
+    if (dim == 3) {
+        F.sp_faces.reserve((size_t)nsf * 12);
+        for (int64_t i = 0; i < nsf; ++i) {
+            int32_t a = C.sp_faces[3 * i], b = C.sp_faces[3 * i + 1], c = C.sp_faces[3 * i + 2], s = C.sp_faces_sub[i];
+            int32_t mab = mid(a, b), mbc = mid(b, c), mca = mid(c, a);
+            push(mab, mbc, s); push(mbc, mca, s); push(mca, mab, s);
+            int32_t ch[4][3] = {{a, mab, mca}, {mab, b, mbc}, {mca, mbc, c}, {mab, mbc, mca}};
+            for (auto& f : ch) {
+                std::sort(f, f + 3);
+                F.sp_faces.insert(F.sp_faces.end(), f, f + 3);
+                F.sp_faces_sub.push_back(s);
+            }
+        }
+    }
+    std::sort(ne_.begin(), ne_.end(), [](const SpEdge& x, const SpEdge& y) { return x.lo != y.lo ? x.lo < y.lo : x.hi < y.hi; });
+    F.sp_edges.resize(ne_.size() * 2);
+    F.sp_edges_sub.resize(ne_.size());
+    for (size_t i = 0; i < ne_.size(); ++i) {
+        F.sp_edges[2 * i] = ne_[i].lo;
+        F.sp_edges[2 * i + 1] = ne_[i].hi;
+        F.sp_edges_sub[i] = ne_[i].sub;
+    }
+    F.have_edges = false;
+    F.edges.clear();
+}
+
+void build_pattern(HostLevel& L, HostPattern& P) {
+    ensure_edges(L);
+    const int nv = L.nv;
+    const int64_t ned = L.nedges();
+    std::vector<int32_t> nlow((size_t)nv, 0), nup((size_t)nv, 0);
+    for (int64_t k = 0; k < ned; ++k) { nup[L.edges[2 * k]]++; nlow[L.edges[2 * k + 1]]++; }
+    P.rowptr.resize((size_t)nv + 1);
+    P.rowptr[0] = 0;
+    for (int i = 0; i < nv; ++i) P.rowptr[i + 1] = P.rowptr[i] + nlow[i] + nup[i] + 1;
+    const int64_t nnz = P.rowptr[nv];
+    P.colidx.resize(nnz);
+    P.mid.resize(nnz);
+    P.diagpos.resize(nv);
+    std::vector<int32_t> clow((size_t)nv), cup((size_t)nv);
+    for (int i = 0; i < nv; ++i) {
+        clow[i] = P.rowptr[i];
+        P.diagpos[i] = P.rowptr[i] + nlow[i];
+        cup[i] = P.diagpos[i] + 1;
+        P.colidx[P.diagpos[i]] = i;
+        P.mid[P.diagpos[i]] = i;
+    }
+    for (int64_t k = 0; k < ned; ++k) {
+        int32_t lo = L.edges[2 * k], hi = L.edges[2 * k + 1];
+        int32_t m = (int32_t)(nv + k);
+        P.colidx[cup[lo]] = hi; P.mid[cup[lo]++] = m;
+        P.colidx[clow[hi]] = lo; P.mid[clow[hi]++] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UGX reader (the subset of the format the shipped grids use)
+// ---------------------------------------------------------------------------------------------
+namespace {
+bool tag_body(const std::string& s, size_t from, size_t to, const std::string& tag, std::string& body, size_t* end_pos = nullptr) {
+    size_t p = s.find("<" + tag, from);
+    while (p != std::string::npos && p < to) {
+        char c = s[p + 1 + tag.size()];
+        if (c == '>' || c == ' ') break;
+        p = s.find("<" + tag, p + 1);
+    }
+    if (p == std::string::npos || p >= to) return false;
+    size_t gt = s.find('>', p);
+    size_t close = s.find("</" + tag + ">", gt);
+    if (gt == std::string::npos || close == std::string::npos || close > to) return false;
+    body = s.substr(gt + 1, close - gt - 1);
+    if (end_pos) *end_pos = close + tag.size() + 3;
+    return true;
+}
+void parse_ints(const std::string& b, std::vector<int64_t>& out) {
+    const char* p = b.c_str();
+    char* q;
+    while (true) {
+        long long v = strtoll(p, &q, 10);
+        if (q == p) break;
+        out.push_back(v);
+        p = q;
+    }
+}
+void parse_doubles(const std::string& b, std::vector<double>& out) {
+    const char* p = b.c_str();
+    char* q;
+    while (true) {
+        double v = strtod(p, &q);
+        if (q == p) break;
+        out.push_back(v);
+        p = q;
+    }
+}
+}  // namespace
+
+bool load_ugx(const std::string& path, HostMesh& mesh, std::string& err) {
+    std::ifstream f(path);
+    if (!f) { err = "cannot open " + path; return false; }
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string s = ss.str();
+    size_t sh = s.find("<subset_handler");
+    if (sh == std::string::npos) { err = "no <subset_handler> in " + path; return false; }
+    size_t vp = s.find("<vertices coords=\"");
+    if (vp == std::string::npos || vp > sh) { err = "no <vertices coords=..> in " + path; return false; }
+    int nc = s[vp + 18] - '0';
+    std::string body;
+    tag_body(s, vp, sh, "vertices", body);
+    std::vector<double> xyz3;
+    parse_doubles(body, xyz3);
+    std::vector<int64_t> edges, tris, tets;
+    if (tag_body(s, 0, sh, "edges", body)) parse_ints(body, edges);
+    if (tag_body(s, 0, sh, "triangles", body)) parse_ints(body, tris);
+    if (tag_body(s, 0, sh, "tetrahedrons", body)) parse_ints(body, tets);
+    const int dim = tets.empty() ? 2 : 3;
+    if (dim == 2 && tris.empty()) { err = "grid has neither triangles nor tetrahedrons"; return false; }
+    HostLevel L;
+    L.dim = dim;
+    L.nv = (int)(xyz3.size() / nc);
+    L.xyz.resize((size_t)L.nv * dim);
+    for (int v = 0; v < L.nv; ++v)
+        for (int c = 0; c < dim; ++c) L.xyz[(size_t)v * dim + c] = xyz3[(size_t)v * nc + c];
+    const std::vector<int64_t>& el = dim == 3 ? tets : tris;
+    L.ne = (int)(el.size() / (dim + 1));
+    L.elems.assign(el.begin(), el.end());
+    L.vsub.assign(L.nv, -1);
+    L.esub.assign(L.ne, -1);
+    std::vector<int32_t> esubs(edges.size() / 2, -1), fsubs(tris.size() / 3, -1);
+    mesh.subset_names.clear();
+    size_t pos = sh;
+    int si = 0;
+    while (true) {
+        size_t p = s.find("<subset name=\"", pos);
+        if (p == std::string::npos) break;
+        size_t q = s.find('"', p + 14);
+        mesh.subset_names.push_back(s.substr(p + 14, q - p - 14));
+        size_t end = s.find("</subset>", q);
+        std::vector<int64_t> ids;
+        if (tag_body(s, q, end, "vertices", body)) { ids.clear(); parse_ints(body, ids); for (auto i : ids) L.vsub[i] = si; }
+        if (tag_body(s, q, end, "edges", body)) { ids.clear(); parse_ints(body, ids); for (auto i : ids) esubs[i] = si; }
+        if (tag_body(s, q, end, "faces", body)) {
+            ids.clear(); parse_ints(body, ids);
+            for (auto i : ids) { if (dim == 3) fsubs[i] = si; else L.esub[i] = si; }
+        }
+        if (tag_body(s, q, end, "volumes", body)) { ids.clear(); parse_ints(body, ids); for (auto i : ids) L.esub[i] = si; }
+        pos = end + 9;
+        ++si;
+    }
+    for (int v = 0; v < L.nv; ++v) if (L.vsub[v] < 0) { err = "vertex without subset"; return false; }
+    for (int e = 0; e < L.ne; ++e) if (L.esub[e] != L.esub[0] || L.esub[e] < 0) { err = "exactly one element subset expected"; return false; }
+    const int vol_sub = L.esub[0];
+    std::vector<SpEdge> sp;
+    for (size_t i = 0; i < esubs.size(); ++i)
+        if (esubs[i] != vol_sub && esubs[i] >= 0) {
+            int32_t a = (int32_t)edges[2 * i], b = (int32_t)edges[2 * i + 1];
+            sp.push_back({a < b ? a : b, a < b ? b : a, esubs[i]});
+        }
+    std::sort(sp.begin(), sp.end(), [](const SpEdge& x, const SpEdge& y) { return x.lo != y.lo ? x.lo < y.lo : x.hi < y.hi; });
+    for (auto& e : sp) { L.sp_edges.push_back(e.lo); L.sp_edges.push_back(e.hi); L.sp_edges_sub.push_back(e.sub); }
+    if (dim == 3)
+        for (size_t i = 0; i < fsubs.size(); ++i)
+            if (fsubs[i] != vol_sub && fsubs[i] >= 0) {
+                int32_t t[3] = {(int32_t)tris[3 * i], (int32_t)tris[3 * i + 1], (int32_t)tris[3 * i + 2]};
+                std::sort(t, t + 3);
+                L.sp_faces.insert(L.sp_faces.end(), t, t + 3);
+                L.sp_faces_sub.push_back(fsubs[i]);
+            }
+    mesh.dim = dim;
+    mesh.levels.clear();
+    mesh.levels.push_back(std::move(L));
+    return true;
+}
+
+}  // namespace ab

@@ -1,0 +1,663 @@
+"""Host-side mirror of the UG4 Lua-registered objects the reference's driver scripts call
+(3d_admm.lua / 2d_admm.lua / obstacle_optim_*_util.lua), backed by libadmm_b200.so through ctypes.
+
+The reference's host side is Lua on top of C++ (UG4); neither a Lua interpreter nor UG4 exists in this
+image, so the mirror is Python: same names, same argument meaning, same error behaviour (solvers return
+False on non-convergence, hard misuse raises).  A `Backend` instance plays the role of the Lua global
+namespace after `InitUG(dim, AlgebraType("CPU",1))` (3d_admm.lua:105): `ug.Domain()`, `ug.VecProd(a,b)` ...
+
+Everything numerical happens in the CUDA library; this file only forwards handles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import AdmmB200Error, GmgDesc, call
+
+PST_CONSISTENT, PST_ADDITIVE, PST_UNIQUE = 1, 2, 4
+_DISC = {"DeformationEquation": 1, "DeformationEquationRHS": 2, "DeformationEquationLargeProblemRHS": 3,
+         "VolumeConstraintSecondDerivative": 4, "SecondDerivativeVolume": 4,
+         "SecondDerivativeBarycenter": 5, "XBarycenterConstraintSecondDerivative": 5,
+         "MassModel": 6, "LambdaUpdate": 7}
+_PARAM = {"lambda_vol": 1, "lambda_bary_x": 2, "lambda_bary_y": 3, "lambda_bary_z": 4, "step_length": 5, "tau": 6,
+          "multiplier_vol": 7, "multiplier_bx": 8, "multiplier_by": 9, "multiplier_bz": 10, "index": 11, "quad_order": 12,
+          "scaling": 13, "high_order_scaling": 14, "second_order": 15}
+_IMPORT_U, _IMPORT_LAMBDA, _IMPORT_Q = 1, 2, 3
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            if self._destroy and self.h:
+                getattr(_lib.load(), self._destroy)(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+
+class Domain(_Handle):
+    """Domain() + LoadDomain(dom, gridName)   3d_admm.lua:108-109"""
+    _destroy = "ab_domain_destroy"
+
+    def __init__(self, ug):
+        super().__init__()
+        self.ug = ug
+        self.dim = None
+        self.subset_names = []
+
+    def _loaded(self):
+        d = C.c_int()
+        call("ab_domain_level_info", self.h, 0, C.byref(d), None, None, None, None)
+        self.dim = d.value
+
+    def num_levels(self):
+        n = C.c_int()
+        call("ab_domain_num_levels", self.h, C.byref(n))
+        return n.value
+
+    def level_info(self, level):
+        v = [C.c_int() for _ in range(5)]
+        call("ab_domain_level_info", self.h, level, *[C.byref(x) for x in v])
+        return dict(dim=v[0].value, nv=v[1].value, ne=v[2].value, nedges=v[3].value, nv_coarse=v[4].value)
+
+    def get_level(self, level):
+        i = self.level_info(level)
+        d, nv, ne, nvc = i["dim"], i["nv"], i["ne"], i["nv_coarse"]
+        xyz = np.empty((nv, d))
+        elems = np.empty((ne, d + 1), np.int32)
+        vsub = np.empty(nv, np.int32)
+        pa = np.empty(max(nv - nvc, 0) if level > 0 else 0, np.int32)
+        pb = np.empty_like(pa)
+        call("ab_domain_get_level", self.h, level, _dp(xyz), _ip(elems), _ip(vsub), _ip(pa) if len(pa) else None, _ip(pb) if len(pb) else None)
+        return dict(xyz=xyz, elems=elems, vsub=vsub, parent_a=pa, parent_b=pb, nv_coarse=nvc)
+
+    def subset_index(self, name):
+        out = C.c_int()
+        call("ab_domain_subset_index", self.h, name.encode(), C.byref(out))
+        return out.value
+
+    class _Info:
+        def __init__(self, dom):
+            self.dom = dom
+
+        def num_surface_elements(self):
+            return self.dom.level_info(self.dom.num_levels() - 1)["ne"]
+
+        def to_string(self):
+            return "\n".join("lvl %d: %s" % (l, self.dom.level_info(l)) for l in range(self.dom.num_levels()))
+
+    def domain_info(self):
+        """dom:domain_info()  3d_admm.lua:112,189"""
+        return Domain._Info(self)
+
+
+class ApproximationSpace(_Handle):
+    """ApproximationSpace(dom); add_fct; init_levels; init_top_surface   3d_admm.lua:329-333,367-370"""
+    _destroy = "ab_space_destroy"
+
+    def __init__(self, ug, dom):
+        super().__init__()
+        self.ug, self.dom = ug, dom
+        self.names, self.kind = [], None
+
+    def add_fct(self, names, fe_type, order=None):
+        if self.h:
+            raise AdmmB200Error("add_fct after the space was initialised")
+        names = [n.strip() for n in names.split(",")]
+        kind = {"Lagrange": 1, "Piecewise-Constant": 0}.get(fe_type)
+        if kind is None or (kind == 1 and order != 1):
+            raise AdmmB200Error("the hot path supports ('Lagrange',1) and 'Piecewise-Constant' spaces only "
+                                "(P2/P1 Navier-Stokes spaces stay on UG4, SURVEY.md E12)")
+        if self.kind is not None and self.kind != kind:
+            raise AdmmB200Error("mixed function spaces are not supported on the hot path")
+        self.kind = kind
+        self.names += names
+
+    def _ensure(self):
+        if not self.h:
+            call("ab_space_create", self.dom.h, self.kind, len(self.names), C.byref(self.h))
+
+    def init_levels(self):
+        self._ensure()
+
+    def init_top_surface(self):
+        self._ensure()
+
+    def print_statistic(self):
+        self._ensure()
+        n = C.c_int64()
+        call("ab_space_num_dofs", self.h, C.byref(n))
+        print("  %s space %s: %d dofs on the surface level" % ("P1" if self.kind else "P0", ",".join(self.names), n.value))
+
+    def num_dofs(self):
+        self._ensure()
+        n = C.c_int64()
+        call("ab_space_num_dofs", self.h, C.byref(n))
+        return n.value
+
+    def fct_index(self, name):
+        return self.names.index(name)
+
+
+class GridFunction(_Handle):
+    """GridFunction / AdvancedGridFunction   3d_admm.lua:337-341,375-383"""
+    _destroy = "ab_vector_destroy"
+
+    def __init__(self, ug, space):
+        super().__init__()
+        space._ensure()
+        self.ug, self.space = ug, space
+        call("ab_vector_create", space.h, C.byref(self.h))
+
+    def set(self, c):
+        call("ab_vector_set", self.h, float(c))
+
+    def _storage(self):
+        s = C.c_int()
+        call("ab_vector_storage", self.h, C.byref(s))
+        return s.value
+
+    def has_storage_type_additive(self):
+        return bool(self._storage() & PST_ADDITIVE)
+
+    def has_storage_type_consistent(self):
+        return bool(self._storage() & PST_CONSISTENT)
+
+    def change_storage_type_to_consistent(self):
+        call("ab_vector_change_storage", self.h, PST_CONSISTENT)
+
+    def change_storage_type_to_additive(self):
+        call("ab_vector_change_storage", self.h, PST_ADDITIVE)
+
+    # host <-> device (the boundary where J' enters and u leaves the hot path)
+    def from_numpy(self, a, storage=PST_CONSISTENT):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        if a.size != self.space.num_dofs():
+            raise AdmmB200Error("from_numpy: size mismatch")
+        call("ab_vector_upload", self.h, _dp(a), storage)
+
+    def to_numpy(self, out=None):
+        out = np.empty(self.space.num_dofs()) if out is None else out
+        call("ab_vector_download", self.h, _dp(out))
+        return out
+
+    def device_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        call("ab_vector_device_ptr", self.h, C.byref(p), C.byref(n))
+        return p.value, n.value
+
+
+class _Import:
+    """GlobalGridFunctionNumberData(gf,"u1") / GlobalGridFunctionGradientData(gf,"u1")   3d_admm.lua:343-363,384-389"""
+
+    def __init__(self, gf, fct, what):
+        self.gf, self.fct, self.what = gf, fct, what
+        self.comp = gf.space.fct_index(fct)
+
+
+class ElemDisc(_Handle):
+    """The deformation-space element discretisations (3d_admm.lua:393-694). Setter names as in the scripts."""
+    _destroy = "ab_elemdisc_destroy"
+
+    def __init__(self, ug, class_name, fcts, subsets):
+        super().__init__()
+        self.ug, self.class_name = ug, class_name
+        self.fcts = [f.strip() for f in fcts.split(",")]
+        self.subsets = subsets
+        self.space = None
+        self._pending_params = {}
+        self._pending_imports = {}
+        if subsets.strip() != "outer":
+            raise AdmmB200Error("element discs are assembled on subset 'outer' only (3d_admm.lua:393)")
+
+    # created lazily: the C object needs the space, which is known when the disc joins a DomainDiscretization
+    def _attach(self, space):
+        if self.h:
+            if space is not self.space:
+                raise AdmmB200Error("%s added to DomainDiscretizations of different spaces" % self.class_name)
+            return
+        if self.fcts != space.names:
+            raise AdmmB200Error("%s functions %s do not match the space %s" % (self.class_name, self.fcts, space.names))
+        self.space = space
+        call("ab_elemdisc_create", space.h, _DISC[self.class_name], C.byref(self.h))
+        for k, v in self._pending_params.items():
+            call("ab_elemdisc_set_param", self.h, k, v)
+        for k, gf in self._pending_imports.items():
+            call("ab_elemdisc_bind", self.h, k, gf.h)
+
+    def _param(self, name, v):
+        v = float(v)
+        self._pending_params[_PARAM[name]] = v
+        if self.h:
+            call("ab_elemdisc_set_param", self.h, _PARAM[name], v)
+
+    def _bind(self, which, imp, comp, what):
+        if not isinstance(imp, _Import):
+            raise AdmmB200Error("imports must be GlobalGridFunctionNumberData/GradientData objects")
+        if imp.comp != comp or imp.what != what:
+            raise AdmmB200Error("%s: import bound to component %d (%s), expected component %d (%s); "
+                                "only the canonical wiring of the scripts is supported" % (self.class_name, imp.comp, imp.what, comp, what))
+        prev = self._pending_imports.get(which)
+        if prev is not None and prev is not imp.gf:
+            raise AdmmB200Error("%s: all components of one import must come from the same grid function" % self.class_name)
+        self._pending_imports[which] = imp.gf
+        if self.h:
+            call("ab_elemdisc_bind", self.h, which, imp.gf.h)
+
+    # scalar setters
+    def set_quad_order(self, o): self._param("quad_order", o)
+    def set_lambda_vol(self, v): self._param("lambda_vol", v)
+    def set_step_length(self, v): self._param("step_length", v)
+    def set_tau(self, v): self._param("tau", v)
+    def set_index(self, k): self._param("index", k)
+    def set_multiplier_vol(self, v): self._param("multiplier_vol", v)
+    def set_multiplier_bx(self, v): self._param("multiplier_bx", v)
+    def set_multiplier_by(self, v): self._param("multiplier_by", v)
+    def set_multiplier_bz(self, v): self._param("multiplier_bz", v)
+    def set_scaling(self, v): self._param("scaling", v)
+    def set_high_order_scaling(self, v): self._param("high_order_scaling", v)
+    def set_second_order(self, b): self._param("second_order", 1.0 if b else 0.0)
+
+    def set_lambda_barycenter(self, x, y, z=0.0):
+        self._param("lambda_bary_x", x)
+        self._param("lambda_bary_y", y)
+        self._param("lambda_bary_z", z)
+
+    def __getattr__(self, name):
+        # set_deformation_d<k>, set_deformation_vector_d<k>, set_lambda<ij>, set_q<ij>, set_qproj<ij>
+        if name.startswith("set_deformation_vector_d"):
+            k = int(name[len("set_deformation_vector_d"):]) - 1
+            return lambda imp: self._bind(_IMPORT_U, imp, k, "gradient")
+        if name.startswith("set_deformation_d"):
+            k = int(name[len("set_deformation_d"):]) - 1
+            return lambda imp: self._bind(_IMPORT_U, imp, k, "value")
+        for prefix, which in (("set_lambda", _IMPORT_LAMBDA), ("set_qproj", _IMPORT_Q), ("set_q", _IMPORT_Q)):
+            if name.startswith(prefix) and name[len(prefix):].isdigit() and len(name[len(prefix):]) == 2:
+                i, j = int(name[len(prefix)]), int(name[len(prefix) + 1])
+                d = self.ug.dim
+                return lambda imp, c=i * d + j: self._bind(which, imp, c, "value")
+        raise AttributeError(name)
+
+
+class DirichletBoundary:
+    """DirichletBoundary():add(0,"u1","inlet")   3d_admm.lua:445-457"""
+
+    def __init__(self, ug):
+        self.entries = []
+
+    def add(self, value, fct, subset):
+        self.entries.append((float(value), fct, subset))
+
+
+class DomainDiscretization(_Handle):
+    """DomainDiscretization(approxSpace)   3d_admm.lua:460-466"""
+    _destroy = "ab_domaindisc_destroy"
+
+    def __init__(self, ug, space):
+        super().__init__()
+        space._ensure()
+        self.ug, self.space = ug, space
+        self._keep = []
+        call("ab_domaindisc_create", space.h, C.byref(self.h))
+
+    def add(self, obj):
+        if isinstance(obj, ElemDisc):
+            obj._attach(self.space)
+            call("ab_domaindisc_add_elemdisc", self.h, obj.h)
+        elif isinstance(obj, DirichletBoundary):
+            for value, fct, subset in obj.entries:
+                call("ab_domaindisc_add_dirichlet", self.h, subset.encode(), self.space.fct_index(fct), value)
+        else:
+            raise AdmmB200Error("DomainDiscretization:add expects an ElemDisc or a DirichletBoundary")
+        self._keep.append(obj)
+
+    def assemble_jacobian(self, A, u):
+        call("ab_domaindisc_assemble_jacobian", self.h, A.h, u.h)
+
+    def assemble_defect(self, d, u):
+        call("ab_domaindisc_assemble_defect", self.h, d.h, u.h)
+
+    def adjust_solution(self, u):
+        call("ab_domaindisc_adjust_solution", self.h, u.h)
+
+
+class AssembledLinearOperator(_Handle):
+    """AssembledLinearOperator(domainDisc)   3d_admm.lua:467"""
+    _destroy = "ab_operator_destroy"
+
+    def __init__(self, ug, dd):
+        super().__init__()
+        self.ug, self.dd = ug, dd
+        call("ab_operator_create", dd.h, C.byref(self.h))
+
+    def apply(self, y, x):
+        call("ab_operator_apply", self.h, y.h, x.h)
+
+    def info(self):
+        b, nb, nnzb = C.c_int(), C.c_int64(), C.c_int64()
+        call("ab_operator_info", self.h, C.byref(b), C.byref(nb), C.byref(nnzb))
+        return b.value, nb.value, nnzb.value
+
+    def to_scipy(self):
+        """Download as scipy BSR (tests)."""
+        import scipy.sparse as sp
+        b, nb, nnzb = self.info()
+        rowptr = np.empty(nb + 1, np.int32)
+        col = np.empty(nnzb, np.int32)
+        vals = np.empty(nnzb * b * b)
+        call("ab_operator_download", self.h, _ip(rowptr), _ip(col), _dp(vals))
+        return sp.bsr_matrix((vals.reshape(-1, b, b), col, rowptr), shape=(nb * b, nb * b))
+
+
+class ConvCheck:
+    """ConvCheck(maxIts, absTol, reduction, verbose)   3d_admm.lua:703"""
+
+    def __init__(self, max_its=100, abs_tol=1e-12, reduction=1e-12, verbose=False):
+        self.max_its, self.abs_tol, self.reduction, self.verbose = int(max_its), float(abs_tol), float(reduction), bool(verbose)
+
+
+class Jacobi:
+    def __init__(self, damp=1.0):
+        self.damp = float(damp)
+
+
+class SuperLU:
+    """SuperLU()  obstacle_optim_3d_util.lua:21 -- served by the dense coarse inverse kernel."""
+
+
+class LU(SuperLU):
+    pass
+
+
+class _LinearSolver(_Handle):
+    _destroy = "ab_solver_destroy"
+
+    def init(self, A, x=None):
+        self._create(A)
+        call("ab_solver_init", self.h, A.h, x.h if x is not None else None)
+        return True
+
+    def apply(self, x, b):
+        ok = C.c_int()
+        call("ab_solver_apply", self.h, x.h, b.h, C.byref(ok))
+        return bool(ok.value)
+
+    def apply_return_defect(self, x, b):
+        ok = C.c_int()
+        call("ab_solver_apply_return_defect", self.h, x.h, b.h, C.byref(ok))
+        return bool(ok.value)
+
+    def step(self):
+        n = C.c_int()
+        call("ab_solver_step", self.h, C.byref(n))
+        return n.value
+
+    def defect(self):
+        d = C.c_double()
+        call("ab_solver_last_defect", self.h, C.byref(d))
+        return d.value
+
+
+class CG(_LinearSolver):
+    """CG(); set_preconditioner(Jacobi(0.66)); set_convergence_check(ConvCheck(2000,1e-9,0,true))   3d_admm.lua:701-703"""
+
+    def __init__(self, ug):
+        super().__init__()
+        self.ug, self.precond, self.cc = ug, None, ConvCheck()
+
+    def set_preconditioner(self, p):
+        if not isinstance(p, Jacobi):
+            raise AdmmB200Error("CG on the hot path is used with Jacobi only (3d_admm.lua:702)")
+        self.precond = p
+
+    def set_convergence_check(self, cc):
+        self.cc = cc
+
+    def _create(self, A):
+        if not self.h:
+            damp = self.precond.damp if self.precond else 1.0
+            call("ab_solver_create_cg_jacobi", A.dd.space.h, damp, self.cc.max_its, self.cc.abs_tol, self.cc.reduction,
+                 int(self.cc.verbose), C.byref(self.h))
+
+
+class BiCGStabGMG(_LinearSolver):
+    """util.solver.CreateSolver{type="bicgstab", precond={type="gmg",...}, convCheck={...}}  obstacle_optim_3d_util.lua:10-41"""
+
+    def __init__(self, ug, desc):
+        super().__init__()
+        self.ug = ug
+        pre = desc["precond"]
+        cc = desc.get("convCheck", {})
+        if desc.get("type") != "bicgstab" or pre.get("type") != "gmg":
+            raise AdmmB200Error("only type='bicgstab' with precond.type='gmg' is served by the GPU backend")
+        if pre.get("cycle", "V") != "V" or pre.get("transfer", "std") != "std":
+            raise AdmmB200Error("only cycle='V', transfer='std' are supported (u3:23,28)")
+        smoother = pre.get("smoother", "gs")
+        env = os.environ.get("ADMM_B200_SMOOTHER", "")
+        # "gs" (sequential lexicographic Gauss-Seidel in UG4) -> stated GPU equivalent, see DESIGN.md
+        sm = {"": 1, "cheb": 1, "chebyshev": 1, "jacobi": 2, "jac": 2}.get(env.lower())
+        if sm is None:
+            raise AdmmB200Error("ADMM_B200_SMOOTHER must be 'cheb' or 'jacobi'")
+        if smoother not in ("gs", "jac", "cheb"):
+            raise AdmmB200Error("unknown smoother '%s'" % smoother)
+        if smoother == "jac":
+            sm = 2
+        self.desc = GmgDesc(smoother=sm, pre_smooth=int(pre.get("preSmooth", 3)), post_smooth=int(pre.get("postSmooth", 3)),
+                            base_level=int(pre.get("baseLevel", 0)), rap=int(bool(pre.get("rap", True))),
+                            max_iterations=int(cc.get("iterations", 100)), abs_tol=float(cc.get("absolute", 1e-12)),
+                            red_tol=float(cc.get("reduction", 0.0)), verbose=int(bool(cc.get("verbose", False))),
+                            cheb_ratio=float(os.environ.get("ADMM_B200_CHEB_RATIO", "0")), jacobi_damp=0.0)
+        self.space = pre.get("approxSpace")
+
+    def _create(self, A):
+        if not self.h:
+            call("ab_solver_create_bicgstab_gmg", A.dd.space.h, C.byref(self.desc), C.byref(self.h))
+
+    def vcycle(self, z, r):
+        call("ab_solver_vcycle", self.h, z.h, r.h)
+
+    def level_info(self, level):
+        nb, nnzb = C.c_int64(), C.c_int64()
+        call("ab_solver_level_info", self.h, level, C.byref(nb), C.byref(nnzb))
+        return nb.value, nnzb.value
+
+
+class _Namespace:
+    pass
+
+
+class Backend:
+    """The Lua global namespace of a ugshell session, GPU edition."""
+    name = "b200"
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        if stream is None:
+            stream = 0
+        call("ab_context_create", int(device), C.c_void_p(stream), C.byref(self.ctx))
+        self.dim = None
+        self.util = _Namespace()
+        self.util.refinement = _Namespace()
+        self.util.refinement.CreateRegularHierarchy = self._create_regular_hierarchy
+        self.util.solver = _Namespace()
+        self.util.solver.CreateSolver = lambda desc: BiCGStabGMG(self, desc)
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                self.lib.ab_context_destroy(self.ctx)
+                self.ctx = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- session ----------------------------------------------------------------------------
+    def InitUG(self, dim, algebra=None):
+        self.dim = int(dim)
+
+    def AlgebraType(self, name, blocksize):
+        return (name, blocksize)
+
+    def synchronize(self):
+        call("ab_context_synchronize", self.ctx)
+
+    def launch_count(self):
+        n = C.c_int64()
+        call("ab_context_launch_count", self.ctx, C.byref(n))
+        return n.value
+
+    # -- grid -------------------------------------------------------------------------------
+    def Domain(self):
+        return Domain(self)
+
+    def LoadDomain(self, dom, grid_name):
+        """LoadDomain(dom, gridName)  3d_admm.lua:109. `.ugx` is parsed natively; `.npz` is the converted
+        fixture format of tools/convert_ugx.py (same content, travels to machines without the reference tree)."""
+        if grid_name.endswith(".npz"):
+            z = np.load(grid_name)
+            names = [str(s) for s in z["subset_names"]]
+            arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+            xyz = np.ascontiguousarray(z["xyz"], np.float64)
+            elems = np.ascontiguousarray(z["elems"], np.int32)
+            vsub = np.ascontiguousarray(z["vsub"], np.int32)
+            esub = np.ascontiguousarray(z["esub"], np.int32)
+            se = np.ascontiguousarray(z["sp_edges"], np.int32)
+            ses = np.ascontiguousarray(z["sp_edges_sub"], np.int32)
+            sf = np.ascontiguousarray(z["sp_faces"], np.int32)
+            sfs = np.ascontiguousarray(z["sp_faces_sub"], np.int32)
+            call("ab_domain_create", self.ctx, int(z["dim"]), xyz.shape[0], _dp(xyz), elems.shape[0], _ip(elems), len(names), arr,
+                 _ip(vsub), _ip(esub), len(ses), _ip(se) if len(ses) else None, _ip(ses) if len(ses) else None,
+                 len(sfs), _ip(sf) if len(sfs) else None, _ip(sfs) if len(sfs) else None, C.byref(dom.h))
+            dom.subset_names = names
+        else:
+            call("ab_domain_load_ugx", self.ctx, grid_name.encode(), C.byref(dom.h))
+        dom._loaded()
+        if self.dim is not None and dom.dim != self.dim:
+            raise AdmmB200Error("grid dimension %d does not match InitUG(%d)" % (dom.dim, self.dim))
+
+    def _create_regular_hierarchy(self, dom, num_refs, verbose=False, balancer_desc=None):
+        """util.refinement.CreateRegularHierarchy(dom, numRefs, false, balancerDesc)  3d_admm.lua:186"""
+        call("ab_domain_refine", dom.h, int(num_refs))
+
+    # -- spaces / functions -------------------------------------------------------------------
+    def ApproximationSpace(self, dom):
+        return ApproximationSpace(self, dom)
+
+    def GridFunction(self, space):
+        return GridFunction(self, space)
+
+    AdvancedGridFunction = GridFunction
+
+    def GlobalGridFunctionNumberData(self, gf, fct):
+        return _Import(gf, fct, "value")
+
+    def GlobalGridFunctionGradientData(self, gf, fct):
+        return _Import(gf, fct, "gradient")
+
+    # -- discretisation -----------------------------------------------------------------------
+    def DirichletBoundary(self):
+        return DirichletBoundary(self)
+
+    def DomainDiscretization(self, space):
+        return DomainDiscretization(self, space)
+
+    def AssembledLinearOperator(self, dd):
+        return AssembledLinearOperator(self, dd)
+
+    def __getattr__(self, name):
+        if name in _DISC:
+            return lambda fcts, subsets: ElemDisc(self, name, fcts, subsets)
+        raise AttributeError(name)
+
+    # -- solvers --------------------------------------------------------------------------------
+    def CG(self):
+        return CG(self)
+
+    Jacobi = staticmethod(Jacobi)
+    ConvCheck = staticmethod(ConvCheck)
+    SuperLU = staticmethod(SuperLU)
+    LU = staticmethod(LU)
+
+    # -- algebra (ugcore bridge)  3d_admm.lua:760,976,994 ----------------------------------------
+    def VecScaleAssign(self, dst, a, src):
+        call("ab_vec_scale_assign", dst.h, float(a), src.h)
+
+    def VecScaleAdd2(self, dst, a, x, b, y):
+        call("ab_vec_scale_add2", dst.h, float(a), x.h, float(b), y.h)
+
+    def VecProd(self, x, y):
+        out = C.c_double()
+        call("ab_vec_prod", x.h, y.h, C.byref(out))
+        return out.value
+
+    def VecProdMulti(self, xs, y):
+        """Batched VecProd(x_k, y), one reduction (extension; the scripts call VecProd 4x per S column, 3d_admm.lua:1014-1017)."""
+        arr = (C.c_void_p * len(xs))(*[x.h for x in xs])
+        out = (C.c_double * len(xs))()
+        call("ab_vec_prod_multi", len(xs), arr, y.h, out)
+        return list(out)
+
+    def VecNorm(self, x):
+        out = C.c_double()
+        call("ab_vec_norm", x.h, C.byref(out))
+        return out.value
+
+    def L2Norm(self, gf, fct, quad_order=None, subsets=None):
+        out = C.c_double()
+        call("ab_l2norm", gf.h, gf.space.fct_index(fct), C.byref(out))
+        return out.value
+
+    def L2NormAll(self, gf):
+        out = (C.c_double * 9)()
+        call("ab_l2norm_all", gf.h, out)
+        return list(out)[:len(gf.space.names)]
+
+    # -- plugin free functions ------------------------------------------------------------------
+    def Testing(self, q_projected, q, cmps, sigma):
+        call("ab_project_frobenius", q_projected.h, q.h, float(sigma))
+
+    def ProjectWithSpectralNorm(self, q_projected, q, cmps, sigma):
+        call("ab_project_spectral", q_projected.h, q.h, float(sigma))
+
+    def MaximumFrobeniusNorm(self, u, cmps, subsets, quad_order):
+        out = C.c_double()
+        call("ab_max_frobenius_norm", u.h, C.byref(out))
+        return out.value
+
+    def MaxSpectralNorm(self, u, cmps, subsets, quad_order):
+        out = C.c_double()
+        call("ab_max_spectral_norm", u.h, C.byref(out))
+        return out.value
+
+    def VolumeDefect(self, u, ref_volume, subsets, cmps, quad_order, *unused):
+        out = C.c_double()
+        call("ab_volume_defect", u.h, float(ref_volume), C.byref(out))
+        return out.value
+
+    def BarycenterDefect(self, u, cmps, subsets, quad_order):
+        out = (C.c_double * 3)()
+        call("ab_barycenter_defect", u.h, out)
+        return list(out)[:self.dim]
+
+    def SetZeroAwayFromSubset(self, gf, cmps, subset):
+        call("ab_set_zero_away_from_subset", gf.h, subset.encode())
+
+    def TransformDomainByDisplacement(self, u, cmps):
+        call("ab_transform_domain_by_displacement", u.space.dom.h, u.h)

@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path (through the C ABI / Python mirror) against the CPU oracle on the same
+seeded inputs.  fp64 throughout; tolerances are written next to each comparison.  north_star asks for 1e-8
+relative on per-iteration scalars and 1e-9 relative L2 on the deformation at matched solver tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import GRID2D, GRID3D
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(3, GRID3D, 1), (2, GRID2D, 2)]
+
+
+def _pair(gpu_backend, dim, grid, refs, **kw):
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    g = ObstacleOptim(gpu_backend, dim, numRefs=refs, grid=grid, **kw).setup()
+    o = ObstacleOptim(ug4_np.Backend(smoother="cheb"), dim, numRefs=refs, grid=grid, **kw).setup()
+    return g, o
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _seed_state(g, o, seed=0, amp=0.02):
+    rng = np.random.default_rng(seed)
+    n = o.u.v.size
+    u = amp * rng.standard_normal(n)
+    lam = 0.1 * rng.standard_normal(o.lambda_piecewise.v.size)
+    q = 0.1 * rng.standard_normal(o.q_projected.v.size)
+    for p in (g, o):
+        p.u.from_numpy(u)
+        p.DeformationEquation_DomainDisc.adjust_solution(p.u)
+        p.lambda_piecewise.from_numpy(lam)
+        p.q_projected.from_numpy(q)
+    return u, lam, q
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_mesh_and_reference_volume(gpu_backend, dim, grid, refs):
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    top = g.dom.num_levels() - 1
+    lv = g.dom.get_level(top)
+    assert np.array_equal(lv["xyz"], o.dom.top.xyz) and np.array_equal(lv["elems"], o.dom.top.elems)
+    assert abs(g.ReferenceVolume - (719.0 if dim == 3 else 83.0)) < 1e-9        # known answer, SURVEY App. B
+    assert abs(g.ReferenceVolume - o.ReferenceVolume) < 1e-10
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+@pytest.mark.parametrize("lam", [(0.0, 0.0, 0.0, 0.0), (0.3, -0.2, 0.1, 0.05)])
+def test_hessian_assembly(gpu_backend, dim, grid, refs, lam):
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    _seed_state(g, o)
+    for p in (g, o):
+        p.Hessian_ElemDisc.set_lambda_vol(lam[0])
+        p.Hessian_ElemDisc.set_lambda_barycenter(lam[1], lam[2], lam[3] if dim == 3 else 0.0)
+        p.DeformationEquation_DomainDisc.assemble_jacobian(p.A_u_Hessian, p.u)
+    A = g.A_u_Hessian.to_scipy().tocsr()
+    B = o.A_u_Hessian.to_scipy().tocsr()
+    diff = abs(A - B).max()
+    assert diff <= 1e-12 * abs(B).max(), diff        # atomics reorder the element sums: rounding only
+    assert abs(A - A.T).max() <= 1e-12 * abs(B).max()   # symmetric Dirichlet elimination
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_defect_assembly_all_discs(gpu_backend, dim, grid, refs):
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    _seed_state(g, o)
+    for p in (g, o):
+        for disc in (p.RHS_ElemDisc, p.LargeRHS_ElemDisc):
+            disc.set_lambda_vol(0.3)
+            disc.set_lambda_barycenter(-0.2, 0.1, 0.05 if dim == 3 else 0.0)
+        p.LargeRHS_ElemDisc.set_multiplier_vol(0.7)
+        p.LargeRHS_ElemDisc.set_multiplier_bx(-0.4)
+        p.LargeRHS_ElemDisc.set_multiplier_by(0.2)
+        if dim == 3:
+            p.LargeRHS_ElemDisc.set_multiplier_bz(0.9)
+    pairs = [("DeformationEquation_DomainDisc", "Lu"), ("Large_DomainDisc", "MinusLu_BdeltaLambda")]
+    for ddn, vn in pairs:
+        outs = []
+        for p in (g, o):
+            getattr(p, ddn).assemble_defect(getattr(p, vn), p.u)
+            assert getattr(p, vn).has_storage_type_additive()
+            outs.append(getattr(p, vn).to_numpy())
+        assert _rel(outs[0], outs[1]) < 1e-13, ddn
+    for i in range(dim + 1):
+        outs = []
+        for p in (g, o):
+            p.B_DomainDisc[i].assemble_defect(p.B_vector[i], p.u)
+            outs.append(p.B_vector[i].to_numpy())
+        assert _rel(outs[0], outs[1]) < 1e-13, i
+    # P0 discs
+    outs = []
+    for p in (g, o):
+        p.MassModel_DomainDisc.assemble_jacobian(p.DiagQ, p.u_negative)
+        p.MassModel_DomainDisc.assemble_defect(p.rhs_piecewise, p.u_negative)
+        p.LambdaUpdate_DomainDisc.assemble_defect(p.temp1_piecewise, p.u_negative)
+        outs.append((p.DiagQ.to_scipy().diagonal(), p.rhs_piecewise.to_numpy(), p.temp1_piecewise.to_numpy()))
+    for a, b in zip(*outs):
+        assert _rel(a, b) < 1e-13
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_vector_ops_norms_and_integrals(gpu_backend, dim, grid, refs):
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    u, lam, q = _seed_state(g, o, seed=3, amp=0.05)
+    res = []
+    for p in (g, o):
+        ug = p.ug
+        ug.VecScaleAdd2(p.u_diff, 2.0, p.u, -0.5, p.u_old)
+        ug.VecScaleAssign(p.sigma, -1.5, p.u_diff)
+        r = dict(prod=ug.VecProd(p.u, p.sigma), norm=ug.VecNorm(p.sigma),
+                 l2=[ug.L2Norm(p.u, c, 4, "outer") for c in p.ucmps.split(",")],
+                 l2p0=[ug.L2Norm(p.lambda_piecewise, c, 4, "outer") for c in p.lcmps.split(",")],
+                 vol=ug.VolumeDefect(p.u, p.ReferenceVolume, "outer", p.ucmps, 4, False, 1, False),
+                 bary=ug.BarycenterDefect(p.u, p.ucmps, "outer", 4),
+                 maxf=ug.MaximumFrobeniusNorm(p.u, p.ucmps, "outer", 4))
+        if dim == 2:
+            r["maxs"] = ug.MaxSpectralNorm(p.u, p.ucmps, "outer", 4)
+        ug.Testing(p.q_projected, p.lambda_piecewise, p.lcmps, 0.15)
+        r["proj"] = p.q_projected.to_numpy()
+        if dim == 2:
+            ug.ProjectWithSpectralNorm(p.q_projected, p.lambda_piecewise, p.lcmps, 0.1)
+            r["projs"] = p.q_projected.to_numpy()
+        ug.SetZeroAwayFromSubset(p.sigma, p.ucmps, "obstacle_surface")
+        r["masked"] = p.sigma.to_numpy()
+        res.append(r)
+    a, b = res
+    for k in ("prod", "norm", "vol", "maxf") + (("maxs",) if dim == 2 else ()):
+        assert abs(a[k] - b[k]) <= 1e-11 * max(1.0, abs(b[k])), (k, a[k], b[k])
+    for k in ("l2", "l2p0", "bary"):
+        assert np.allclose(a[k], b[k], rtol=1e-11, atol=1e-12), k
+    for k in ("proj", "masked") + (("projs",) if dim == 2 else ()):
+        assert _rel(a[k], b[k]) < 1e-13, k
+    assert np.count_nonzero(a["masked"]) > 0
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_spmv_matches_scipy(gpu_backend, dim, grid, refs):
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    _seed_state(g, o)
+    for p in (g, o):
+        p.Hessian_ElemDisc.set_lambda_vol(0.2)
+        p.DeformationEquation_DomainDisc.assemble_jacobian(p.A_u_Hessian, p.u)
+    x = np.random.default_rng(1).standard_normal(o.u.v.size)
+    g.sigma.from_numpy(x)
+    g.A_u_Hessian.apply(g.Lu, g.sigma)
+    y = g.Lu.to_numpy()
+    yref = o.A_u_Hessian.to_scipy() @ x
+    assert _rel(y, yref) < 1e-14 * 10
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+@pytest.mark.parametrize("lamvol", [0.0, 0.25])
+def test_gmg_bicgstab_solve(gpu_backend, dim, grid, refs, lamvol):
+    """Same preconditioner (V(3,3), Chebyshev-Jacobi, RAP, direct base solve) on both sides: iteration counts must
+    agree and the solutions must agree to 1e-9 relative L2 when both are converged well below the script tolerance."""
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    _seed_state(g, o, amp=0.01)
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(o.u.v.size)
+    sols, its = [], []
+    for p in (g, o):
+        p.Hessian_ElemDisc.set_lambda_vol(lamvol)
+        DD = p.DeformationEquation_DomainDisc
+        DD.assemble_jacobian(p.A_u_Hessian, p.u)
+        p.Lu.from_numpy(b, 2)
+        DD.adjust_solution(p.Lu)
+        p.sigma.set(0.0)
+        s = p.SmallProblemRHS_Solver
+        if isinstance(getattr(s, "desc", None), dict):
+            s.desc["convCheck"]["absolute"] = 1e-12
+        else:
+            s.desc.abs_tol = 1e-12
+        s.init(p.A_u_Hessian, p.sigma)
+        assert s.apply(p.sigma, p.Lu)
+        sols.append(p.sigma.to_numpy())
+        its.append(s.step())
+    assert abs(its[0] - its[1]) <= 1, its
+    assert _rel(sols[0], sols[1]) < 1e-9
+    A = o.A_u_Hessian.to_scipy()
+    bb = b.copy(); bb[o.DeformationEquation_DomainDisc.dmask(o.dom.top)] = 0
+    assert np.linalg.norm(A @ sols[0] - bb) < 1e-10
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_admm_trace_parity(gpu_backend, dim, grid, refs):
+    """Two ADMM iterations of the script replay: per-iteration scalars within 1e-8 relative, deformation within
+    1e-9 relative L2 (north_star), Newton iteration counts equal."""
+    g, o = _pair(gpu_backend, dim, grid, refs, admmSteps=2)
+    J = o.synthetic_sensitivity(0.5)
+    Jg = g.synthetic_sensitivity(0.5)
+    assert _rel(Jg, J) < 1e-13
+    for p in (g, o):
+        for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:   # matched, tighter tolerance
+            if isinstance(getattr(s, "desc", None), dict):
+                s.desc["convCheck"]["absolute"] = 1e-13
+            else:
+                s.desc.abs_tol = 1e-13
+        p.set_sensitivity(J)
+        p.run_admm()
+        assert not p.p_solver_failure
+    assert len(g.admm_trace) == len(o.admm_trace) == 2
+    for a, b in zip(g.admm_trace, o.admm_trace):
+        assert len(a["newton"]) == len(b["newton"])
+        for k in ("u_diff", "lambda_inc", "max_norm"):
+            assert abs(a[k] - b[k]) <= 1e-8 * max(abs(b[k]), 1e-3), (k, a[k], b[k])
+        for x, y in zip(a["Lambda"], b["Lambda"]):
+            assert abs(x - y) <= 1e-8 * max(abs(y), 1e-2)
+    assert _rel(g.u.to_numpy(), o.u.to_numpy()) < 1e-9
+    assert _rel(g.lambda_piecewise.to_numpy(), o.lambda_piecewise.to_numpy()) < 1e-8
+
+
+def test_solver_failure_is_a_value_not_an_error(gpu_backend):
+    from admm_optim_b200.driver import ObstacleOptim
+    g = ObstacleOptim(gpu_backend, 3, numRefs=1, grid=GRID3D).setup()
+    g.DeformationEquation_DomainDisc.assemble_jacobian(g.A_u_Hessian, g.u)
+    s = g.SmallProblemRHS_Solver
+    s.desc.max_iterations = 1
+    s.desc.abs_tol = 1e-30
+    g.Lu.from_numpy(np.random.default_rng(0).standard_normal(g.DeformationSpace_ApproxSpace.num_dofs()), 2)
+    g.DeformationEquation_DomainDisc.adjust_solution(g.Lu)
+    s.init(g.A_u_Hessian, g.sigma)
+    assert s.apply(g.sigma, g.Lu) is False
+    assert s.step() == 1
+
+
+def test_transform_domain_and_cache_invalidation(gpu_backend):
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    g, o = _pair(gpu_backend, 3, GRID3D, 1)
+    _seed_state(g, o, amp=0.01)
+    for p in (g, o):
+        p.DeformationEquation_DomainDisc.assemble_jacobian(p.A_u_Hessian, p.u)
+        p.ug.TransformDomainByDisplacement(p.u, p.ucmps)
+        p.DeformationEquation_DomainDisc.assemble_jacobian(p.A_u_Hessian, p.u)   # must re-assemble on moved coordinates
+    A = g.A_u_Hessian.to_scipy().tocsr()
+    B = o.A_u_Hessian.to_scipy().tocsr()
+    assert abs(A - B).max() <= 1e-12 * abs(B).max()
+    top = g.dom.num_levels() - 1
+    assert np.allclose(g.dom.get_level(top)["xyz"], o.dom.top.xyz, rtol=0, atol=1e-15)
+    vol = [p.ug.VolumeDefect(p.u_zeros, 0.0, "outer", p.ucmps, 4, False, 1, False) for p in (g, o)]
+    assert abs(vol[0] - vol[1]) < 1e-10
