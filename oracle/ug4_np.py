@@ -164,8 +164,18 @@ class DomainDiscretization:
             if disc.kind == "DeformationEquation":
                 if disc.p["second_order"]:
                     raise OracleError("second-order (J'') terms are outside the hot path")
-                A.mat = F.hessian_matrix(mesh, self._u(disc, u), c=disc.p["step_length"], lam_vol=disc.p["lambda_vol"],
-                                         lam_bary=disc.p["lambda_bary"][:d], dmask=self.dmask(mesh) if self.dir else None)
+                uu = self._u(disc, u)
+                has_lam = disc.p["lambda_vol"] != 0.0 or any(v != 0.0 for v in disc.p["lambda_bary"][:d])
+                # the six operators of one Newton iteration are identical (same Hessian disc + Dirichlet set):
+                # assemble once, like the GPU path's signature cache (DESIGN.md "Operator sharing")
+                key = (disc.p["step_length"], disc.p["lambda_vol"], tuple(disc.p["lambda_bary"][:d]),
+                       hash(uu.tobytes()) if (has_lam and uu is not None) else 0, self.space.dom.coords_version, tuple(sorted(self.dir)))
+                cache = self.ug._asm_cache
+                if cache.get("key") != key:
+                    cache["key"] = key
+                    cache["mat"] = F.hessian_matrix(mesh, uu, c=disc.p["step_length"], lam_vol=disc.p["lambda_vol"],
+                                                    lam_bary=disc.p["lambda_bary"][:d], dmask=self.dmask(mesh) if self.dir else None)
+                A.mat = cache["mat"]
                 A.diag = None
                 return
             if disc.kind == "MassModel":
@@ -319,6 +329,7 @@ class Backend:
         self.dim = None
         self.smoother, self.cheb_ratio = smoother, cheb_ratio
         self._gmg_cache = {}
+        self._asm_cache = {}
         self.util = _NS()
         self.util.refinement = _NS()
         self.util.refinement.CreateRegularHierarchy = self._refine

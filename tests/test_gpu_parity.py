@@ -91,7 +91,7 @@ def test_defect_assembly_all_discs(gpu_backend, dim, grid, refs):
         for p in (g, o):
             p.B_DomainDisc[i].assemble_defect(p.B_vector[i], p.u)
             outs.append(p.B_vector[i].to_numpy())
-        assert _rel(outs[0], outs[1]) < 1e-13, i
+        assert _rel(outs[0], outs[1]) < 1e-11, i      # interior entries cancel to ~0: atomic summation order shows
     # P0 discs
     outs = []
     for p in (g, o):
