@@ -38,6 +38,7 @@ PROTOTYPES = {
     "ab_context_destroy": [_P],
     "ab_context_synchronize": [_P],
     "ab_context_launch_count": [_P, _I64P],
+    "ab_context_set_tuning": [_P, _S, _I],
     "ab_context_init_comm": [_P, _I, _I, _P],
     "ab_nccl_unique_id": [_P],
     "ab_domain_load_ugx": [_P, _S, _PP],

@@ -34,13 +34,15 @@ struct Context {
     cudaStream_t stream = nullptr;
     int num_sms = 148;
     int64_t launches = 0;
+    int spmv_variant = 0;   // ADMM_B200_SPMV_VARIANT
+    int spmv_waves = 4;     // ADMM_B200_SPMV_WAVES: CTAs per SM slot for the grid-stride SpMV
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
     unsigned int* d_tickets = nullptr;
     double* d_results = nullptr;    // kResultSlots doubles (device)
     double* h_results = nullptr;    // pinned mirror
     std::shared_ptr<Comm> comm;
-    static constexpr int kMaxBlocks = 1184;   // 148 SMs x 8
+    static constexpr int kMaxBlocks = 4736;   // 148 SMs x 32
     static constexpr int kMaxVals = 16;
     static constexpr int kResultSlots = 64;
 };

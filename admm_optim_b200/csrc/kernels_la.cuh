@@ -112,14 +112,20 @@ __global__ void k_bicg_half_x(int64_t n, const double* __restrict__ sc, const do
 //   MODE 2: Chebyshev/Jacobi step  r = b - A xin ; d = c1*d + c2*dinv*r ; xout = xin + d
 // DOTS (MODE 0 only): 0 none, 1: <w,y> -> red[0], 2: <w,y>, <y,y> -> red[0..1]   (w given)
 // ---------------------------------------------------------------------------------------------
-template <int D, int LPR, int MODE, int DOTS>
-__global__ void __launch_bounds__(256) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+// streaming (read-once) load: keep the matrix stream out of L1 so that the x gathers stay cached
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int D, int LPR, int MODE, int DOTS, int BATCH = D * D, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                                   const double* __restrict__ vals, const double* __restrict__ x,
                                                   const double* __restrict__ b, double* __restrict__ y,
                                                   const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
                                                   const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
     constexpr int DD = D * D;
-    constexpr int GPW = 32 / LPR;                       // groups per warp
     const int lane = threadIdx.x & 31;
     const int gl = lane % LPR;                          // lane within group
     const int gbase = lane - gl;                        // first lane of my group
@@ -127,38 +133,62 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(int nb, const int* __restrict_
     const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
     const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
     double dot[2] = {0.0, 0.0};
-    (void)GPW;
-    // every lane of a warp iterates the same number of times (rows padded with idle groups)
+    // every lane of a warp iterates the same number of rounds (rows padded with idle groups)
     const int64_t nrounds = (nb + ngroups - 1) / ngroups;
+    // software pipeline over rounds: the next row's extent and first column chunk are in flight while the
+    // current row's values stream in
+    int s_n = 0, e_n = 0, col_n = 0;
+    if (gid < nb) {
+        s_n = __ldg(rowptr + gid);
+        e_n = __ldg(rowptr + gid + 1);
+        if (s_n + gl < e_n) col_n = __ldg(colidx + s_n + gl);
+    }
     for (int64_t round = 0; round < nrounds; ++round) {
         const int64_t row = gid + round * ngroups;
         const bool active = row < nb;
-        int s = 0, e = 0;
-        if (active) { s = rowptr[row]; e = rowptr[row + 1]; }
+        const int s = s_n, e = e_n;
+        int mycol = col_n;
+        {
+            const int64_t nrow = row + ngroups;
+            s_n = 0; e_n = 0; col_n = 0;
+            if (nrow < nb) {
+                s_n = __ldg(rowptr + nrow);
+                e_n = __ldg(rowptr + nrow + 1);
+                if (s_n + gl < e_n) col_n = __ldg(colidx + s_n + gl);
+            }
+        }
         double acc[D];
 #pragma unroll
         for (int r = 0; r < D; ++r) acc[r] = 0.0;
-        for (int cs = s; cs < e; cs += LPR) {           // chunks of LPR blocks
-            const int nblk = min(LPR, e - cs);
-            int mycol = 0;
-            if (gl < nblk) mycol = __ldg(colidx + cs + gl);
-            const int64_t base = (int64_t)cs * DD;
-            const int nent = nblk * DD;
-#pragma unroll 4
-            for (int k0 = 0; k0 < nent; k0 += LPR) {   // uniform trip count within the group (shuffles inside)
-                const int k = k0 + gl;
-                const bool valid = k < nent;
-                const int blk = valid ? k / DD : 0;
-                const int wq = k - blk * DD;
-                const int r = wq / D;
-                const int c = wq - r * D;
-                const double a = valid ? __ldg(vals + base + k) : 0.0;
-                const int col = __shfl_sync(gmask, mycol, gbase + blk);
-                const double xv = valid ? __ldg(x + (int64_t)col * D + c) : 0.0;
-                const double pr = a * xv;
+        for (int cs = s; cs < e; cs += LPR) {           // chunks of LPR blocks (one chunk for most rows)
+            const int nent = min(LPR, e - cs) * DD;
+            int col_next = 0;
+            if (cs + LPR + gl < e) col_next = __ldg(colidx + cs + LPR + gl);
+            const double* vp = vals + (int64_t)cs * DD + gl;
+            // DD iterations cover the LPR*DD entries of a chunk; they are issued in phases of BATCH fully
+            // unrolled, independent loads (BATCH trades bytes in flight per lane against registers)
+#pragma unroll 1
+            for (int it0 = 0; it0 < DD; it0 += BATCH) {
+                if (it0 * LPR >= nent) break;            // group-uniform
+                double a[BATCH];
 #pragma unroll
-                for (int rr = 0; rr < D; ++rr) acc[rr] += (rr == r) ? pr : 0.0;
+                for (int j = 0; j < BATCH; ++j)
+                    a[j] = (it0 + j < DD && (it0 + j) * LPR + gl < nent) ? ld_stream(vp + (it0 + j) * LPR) : 0.0;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const int k = (it0 + j) * LPR + gl;
+                    const int blk = min(k / DD, LPR - 1);
+                    const int wq = k - (k / DD) * DD;
+                    const int r = wq / D;
+                    const int c = wq - r * D;
+                    const int col = __shfl_sync(gmask, mycol, gbase + blk);
+                    const double xv = (it0 + j < DD && k < nent) ? __ldg(x + (unsigned)(col * D + c)) : 0.0;
+                    const double pr = a[j] * xv;
+#pragma unroll
+                    for (int rr = 0; rr < D; ++rr) acc[rr] += (rr == r) ? pr : 0.0;
+                }
             }
+            mycol = col_next;
         }
 #pragma unroll
         for (int r = 0; r < D; ++r) {
@@ -166,18 +196,18 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(int nb, const int* __restrict_
             for (int o = LPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(gmask, acc[r], o);
         }
         if (active && gl < D) {
-            double a = acc[0];
+            double av = acc[0];
 #pragma unroll
-            for (int r = 1; r < D; ++r) a = (gl == r) ? acc[r] : a;
+            for (int r = 1; r < D; ++r) av = (gl == r) ? acc[r] : av;
             const int64_t i = row * D + gl;
             if (MODE == 0) {
-                y[i] = a;
-                if (DOTS >= 1) dot[0] += w[i] * a;
-                if (DOTS >= 2) dot[1] += a * a;
+                y[i] = av;
+                if (DOTS >= 1) dot[0] += w[i] * av;
+                if (DOTS >= 2) dot[1] += av * av;
             } else if (MODE == 1) {
-                y[i] = b[i] - a;
+                y[i] = b[i] - av;
             } else {
-                const double res = b[i] - a;
+                const double res = b[i] - av;
                 const double dn = (c1 != 0.0 ? c1 * dvec[i] : 0.0) + c2 * dinv[i] * res;   // c1 == 0: dvec may be uninitialised
                 dvec[i] = dn;
                 y[i] = x[i] + dn;

@@ -201,15 +201,15 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 }
 
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
-template <int D>
+template <int D, int BATCH, int MINB>
 static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                         const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
     constexpr int LPR = D == 3 ? 16 : 8;
     const int64_t groups_per_block = 256 / LPR;
-    const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * 8);
-    const int g = std::max(grid, 1);
+    const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * MINB * ctx->spmv_waves);
+    const int g = std::min(std::max(grid, 1), (int)Context::kMaxBlocks);
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -220,8 +220,13 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
-    if (dim == 2) spmv_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-    else spmv_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+    if (dim == 2) { spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); return; }
+    switch (ctx->spmv_variant) {   // tuning knob ADMM_B200_SPMV_VARIANT (bytes in flight per lane vs occupancy)
+        case 1: spmv_launch<3, 9, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
+        case 2: spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
+        case 3: spmv_launch<3, 9, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
+        default: spmv_launch<3, 5, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
+    }
 }
 
 // =============================================================================================
@@ -767,6 +772,8 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     cudaDeviceProp prop;
     AB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
+    if (const char* v = getenv("ADMM_B200_SPMV_VARIANT")) c->spmv_variant = atoi(v);
+    if (const char* v = getenv("ADMM_B200_SPMV_WAVES")) c->spmv_waves = std::max(1, atoi(v));
     AB_CUDA(cudaMalloc((void**)&c->d_partials, sizeof(double) * Context::kMaxBlocks * Context::kMaxVals));
     AB_CUDA(cudaMalloc((void**)&c->d_tickets, sizeof(unsigned int) * 4));
     AB_CUDA(cudaMemset(c->d_tickets, 0, sizeof(unsigned int) * 4));
@@ -791,6 +798,14 @@ int ab_context_synchronize(ab_context* ctx) {
 int ab_context_launch_count(ab_context* ctx, int64_t* out) {
     AB_TRY
     *out = ctx->launches;
+    AB_CATCH
+}
+int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
+    AB_TRY
+    const std::string k = key;
+    if (k == "spmv_variant") ctx->spmv_variant = value;
+    else if (k == "spmv_waves") ctx->spmv_waves = std::max(1, value);
+    else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }
 int ab_context_init_comm(ab_context*, int, int nranks, const void*) {

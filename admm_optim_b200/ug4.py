@@ -518,6 +518,9 @@ class Backend:
     def synchronize(self):
         call("ab_context_synchronize", self.ctx)
 
+    def set_tuning(self, key, value):
+        call("ab_context_set_tuning", self.ctx, key.encode(), int(value))
+
     def launch_count(self):
         n = C.c_int64()
         call("ab_context_launch_count", self.ctx, C.byref(n))
