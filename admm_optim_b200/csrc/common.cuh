@@ -4,7 +4,9 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <memory>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -35,7 +37,7 @@ struct Context {
     int num_sms = 148;
     int64_t launches = 0;
     int spmv_variant = 0;   // ADMM_B200_SPMV_VARIANT
-    int spmv_waves = 4;     // ADMM_B200_SPMV_WAVES: CTAs per SM slot for the grid-stride SpMV
+    int spmv_waves = 6;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
     unsigned int* d_tickets = nullptr;
@@ -45,6 +47,43 @@ struct Context {
     static constexpr int kMaxBlocks = 4736;   // 148 SMs x 32
     static constexpr int kMaxVals = 16;
     static constexpr int kResultSlots = 64;
+};
+
+// Caching device allocator: per-Newton-iteration matrices / multigrid hierarchies come and go, and raw
+// cudaMalloc/cudaFree cost milliseconds each (and cudaFree synchronises the device).  Blocks are recycled by
+// size; reuse is safe because all work of a context is ordered on one stream.  Never returns memory to the
+// driver before process exit (sizes repeat every iteration).
+struct DevicePool {
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> size_;
+    size_t bytes_allocated = 0;
+    static DevicePool& get() { static DevicePool* p = new DevicePool(); return *p; }   // leaked on purpose (CUDA teardown order)
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        auto it = free_.lower_bound(bytes);
+        if (it != free_.end() && it->first <= bytes + bytes / 8 + 4096) {
+            void* p = it->second;
+            free_.erase(it);
+            return p;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {   // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            for (auto& kv : free_) { cudaFree(kv.second); size_.erase(kv.second); bytes_allocated -= kv.first; }
+            free_.clear();
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) throw ab::Error(-2, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+        size_[p] = bytes;
+        bytes_allocated += bytes;
+        return p;
+    }
+    void release(void* p) {
+        auto it = size_.find(p);
+        if (it == size_.end()) { cudaFree(p); return; }
+        free_.insert({it->second, p});
+    }
 };
 
 template <typename T>
@@ -64,10 +103,10 @@ struct DevBuf {
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) AB_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+        if (n) p = (T*)DevicePool::get().alloc(n * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) DevicePool::get().release(p);
         p = nullptr;
         n = 0;
     }

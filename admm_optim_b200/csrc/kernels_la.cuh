@@ -217,6 +217,83 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
     if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tile-streaming BSR SpMV (default).  A tile is a run of consecutive block rows holding <= TB blocks; its
+// value array is ONE contiguous stream which the whole CTA reads with unit-stride loads, all NIT loads of
+// a thread in flight at once (memcpy-like access, independent of the row structure).  Products are staged
+// in shared memory; thread (row, comp) then sums its row segment and applies the MODE epilogue.
+// Same MODE / DOTS semantics as k_bsr_spmv.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct SpmvTile {
+    static constexpr int DD = D * D;
+    static constexpr int TB = D == 3 ? 448 : 1024;              // max blocks per tile
+    static constexpr int NIT = (TB * DD + 255) / 256;           // loads per thread (16)
+};
+
+template <int D, int MODE, int DOTS>
+__global__ void __launch_bounds__(256) k_bsr_spmv_tile(int ntiles, const int* __restrict__ tile_row, const int* __restrict__ rowptr,
+                                                       const int* __restrict__ colidx, const double* __restrict__ vals,
+                                                       const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
+                                                       const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
+                                                       const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
+    constexpr int DD = SpmvTile<D>::DD, TB = SpmvTile<D>::TB, NIT = SpmvTile<D>::NIT;
+    __shared__ double sprod[TB * DD];
+    __shared__ int scol[TB];
+    __shared__ int srow[TB + 1];
+    const int tid = threadIdx.x;
+    double dot[2] = {0.0, 0.0};
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = __ldg(tile_row + tile), nr = __ldg(tile_row + tile + 1) - r0;
+        for (int i = tid; i <= nr; i += 256) srow[i] = __ldg(rowptr + r0 + i);
+        __syncthreads();
+        const int b0 = srow[0], nblk = srow[nr] - b0, nent = nblk * DD;
+        const double* vp = vals + (int64_t)b0 * DD;
+        double a[NIT];
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {                          // the matrix stream: NIT independent loads per thread
+            const int k = tid + j * 256;
+            a[j] = k < nent ? ld_stream(vp + k) : 0.0;
+        }
+        for (int i = tid; i < nblk; i += 256) scol[i] = __ldg(colidx + b0 + i);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NIT; ++j) {
+            const int k = tid + j * 256;
+            if (k < nent) {
+                const int blk = k / DD;
+                const int c = (k - blk * DD) % D;
+                sprod[k] = a[j] * __ldg(x + (unsigned)(scol[blk] * D + c));
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < nr * D; q += 256) {
+            const int lr = q / D, i = q - lr * D;
+            const int bs = srow[lr] - b0, be = srow[lr + 1] - b0;
+            double av = 0.0;
+            for (int blk = bs; blk < be; ++blk) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) av += sprod[blk * DD + i * D + c];
+            }
+            const int64_t gi = (int64_t)(r0 + lr) * D + i;
+            if (MODE == 0) {
+                y[gi] = av;
+                if (DOTS >= 1) dot[0] += w[gi] * av;
+                if (DOTS >= 2) dot[1] += av * av;
+            } else if (MODE == 1) {
+                y[gi] = b[gi] - av;
+            } else {
+                const double res = b[gi] - av;
+                const double dn = (c1 != 0.0 ? c1 * dvec[gi] : 0.0) + c2 * dinv[gi] * res;
+                dvec[gi] = dn;
+                y[gi] = x[gi] + dn;
+            }
+        }
+        __syncthreads();
+    }
+    if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
+}
+
 // first Chebyshev/Jacobi step from a zero initial guess: d = c2*dinv*b ; x = d   (no matrix pass)
 __global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* __restrict__ b,
                                double* __restrict__ d, double* __restrict__ x) {

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 
 #include "../../include/admm_b200.h"
@@ -17,9 +18,19 @@ namespace ab {
 
 static thread_local std::string g_last_error;
 static uint64_t g_version_counter = 1;
+struct TraceTimer {   // ADMM_B200_TRACE=1: wall-clock of setup phases (synchronising; diagnostics only)
+    cudaStream_t st; const char* what; bool on; double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    TraceTimer(cudaStream_t s, const char* w);
+    ~TraceTimer() { if (on) { cudaStreamSynchronize(st); fprintf(stderr, "[ab trace] %-28s %9.3f ms\n", what, 1e3 * (now() - t0)); } }
+};
 static bool env_flag(const char* name) {
     const char* v = getenv(name);
     return v && *v && strcmp(v, "0") != 0;
+}
+
+TraceTimer::TraceTimer(cudaStream_t s, const char* w) : st(s), what(w), on(env_flag("ADMM_B200_TRACE")), t0(0) {
+    if (on) { cudaStreamSynchronize(st); t0 = now(); }
 }
 
 // =============================================================================================
@@ -29,6 +40,8 @@ struct LevelDev {
     int nv = 0, ne = 0, nvc = 0, maxrow = 0;
     int64_t nnzb = 0;
     DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
+    DevBuf<int> tile_row;                        // SpMV tiles: first block row of every tile (ntiles+1)
+    int ntiles = 0;
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
     DevBuf<double> xyz;                          // top level only
@@ -69,6 +82,19 @@ void Domain::finalize() {
         int mr = 0;
         for (int i = 0; i < H.nv; ++i) mr = std::max(mr, P.rowptr[i + 1] - P.rowptr[i]);
         L.maxrow = mr;
+        {   // SpMV tiles: greedy runs of consecutive rows with <= TB blocks
+            const int TB = H.dim == 3 ? SpmvTile<3>::TB : SpmvTile<2>::TB;
+            std::vector<int> tr;
+            tr.push_back(0);
+            int start = 0;
+            for (int i = 0; i < H.nv; ++i) {
+                AB_REQUIRE(P.rowptr[i + 1] - P.rowptr[i] <= TB, AB_ERR_UNSUPPORTED, "vertex valence exceeds the SpMV tile size");
+                if (P.rowptr[i + 1] - P.rowptr[start] > TB) { tr.push_back(i); start = i; }
+            }
+            tr.push_back(H.nv);
+            L.ntiles = (int)tr.size() - 1;
+            L.tile_row.upload(tr, ctx->stream);
+        }
         L.rowptr.upload(P.rowptr, ctx->stream);
         L.colidx.upload(P.colidx, ctx->stream);
         L.diagpos.upload(P.diagpos, ctx->stream);
@@ -218,13 +244,31 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
     else AB_SPMV(2, 0);
 #undef AB_SPMV
 }
+template <int D>
+static void spmv_tile_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
+                             const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+    const int g = std::max(1, std::min(L.ntiles, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
+#define AB_SPMV(MODE, DOTS) \
+    AB_LAUNCH(ctx, (k_bsr_spmv_tile<D, MODE, DOTS>), g, 256, 0, L.ntiles, L.tile_row.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    if (mode == 0) {
+        if (dots == 0) AB_SPMV(0, 0);
+        else if (dots == 1) AB_SPMV(0, 1);
+        else AB_SPMV(0, 2);
+    } else if (mode == 1) AB_SPMV(1, 0);
+    else AB_SPMV(2, 0);
+#undef AB_SPMV
+}
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
+    if (ctx->spmv_variant == 0) {   // default: tile-streaming kernel
+        if (dim == 2) spmv_tile_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+        else spmv_tile_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+        return;
+    }
     if (dim == 2) { spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); return; }
-    switch (ctx->spmv_variant) {   // tuning knob ADMM_B200_SPMV_VARIANT (bytes in flight per lane vs occupancy)
+    switch (ctx->spmv_variant) {   // row-group kernels kept for comparison (tuning knob "spmv_variant")
         case 1: spmv_launch<3, 9, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
         case 2: spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
-        case 3: spmv_launch<3, 9, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
         default: spmv_launch<3, 5, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
     }
 }
@@ -287,6 +331,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     constexpr int DD = D * D;
     // Galerkin coarse operators, top-down
     for (int l = top; l > 0; --l) {
+        TraceTimer tt(ctx->stream, "gmg: rap level");
         const LevelDev& F = dom->dev[l];
         const LevelDev& C = dom->dev[l - 1];
         GmgLevel& gc = G.L[l - 1];
@@ -313,6 +358,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     }
     // dense inverse of level 0 (free dofs)
     {
+        TraceTimer tt(ctx->stream, "gmg: dense inverse");
         const LevelDev& L0 = dom->dev[0];
         const int n = G.n_free;
         if (n > 0) {
@@ -336,6 +382,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
 
 void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     Context* ctx = dom->ctx;
+    TraceTimer tt(ctx->stream, "gmg: setup total");
     const int top = dom->top(), dim = dom->dim();
     const bool first = L.empty();
     if (first) {
@@ -641,6 +688,7 @@ static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
         A->data = m;
         dom->live.push_back(m);
     }
+    TraceTimer tt(ctx->stream, "assemble_jacobian (miss)");
     MatrixData& M = *A->data;
     M.assembled = false;
     M.gmg.clear();
