@@ -37,7 +37,7 @@ struct Context {
     int num_sms = 148;
     int64_t launches = 0;
     int spmv_variant = 0;   // ADMM_B200_SPMV_VARIANT
-    int spmv_waves = 6;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
+    int spmv_waves = 8;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
     unsigned int* d_tickets = nullptr;

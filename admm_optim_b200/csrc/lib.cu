@@ -258,15 +258,40 @@ static void spmv_tile_launch(Context* ctx, const LevelDev& L, const double* vals
     else AB_SPMV(2, 0);
 #undef AB_SPMV
 }
+template <int D, int U>
+static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
+                             const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+    const int64_t want = ((int64_t)L.nv + 7) / 8;        // 8 warps (rows) per CTA
+    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
+#define AB_SPMV(MODE, DOTS) \
+    AB_LAUNCH(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    if (mode == 0) {
+        if (dots == 0) AB_SPMV(0, 0);
+        else if (dots == 1) AB_SPMV(0, 1);
+        else AB_SPMV(0, 2);
+    } else if (mode == 1) AB_SPMV(1, 0);
+    else AB_SPMV(2, 0);
+#undef AB_SPMV
+}
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
-    if (ctx->spmv_variant == 0) {   // default: tile-streaming kernel
-        if (dim == 2) spmv_tile_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-        else spmv_tile_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-        return;
+    switch (ctx->spmv_variant) {   // tuning knob "spmv_variant"; 0 = default
+        case 0:
+            if (dim == 2) spmv_warp_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_warp_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
+        case 5:
+            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
+        case 4:   // tile-streaming kernel
+            if (dim == 2) spmv_tile_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_tile_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
+        default: break;
     }
     if (dim == 2) { spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); return; }
-    switch (ctx->spmv_variant) {   // row-group kernels kept for comparison (tuning knob "spmv_variant")
+    switch (ctx->spmv_variant) {   // row-group kernels kept for comparison
         case 1: spmv_launch<3, 9, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
         case 2: spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
         default: spmv_launch<3, 5, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
