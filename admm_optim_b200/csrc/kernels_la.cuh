@@ -318,27 +318,35 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double dot[2] = {0.0, 0.0};
-    int s_n = 0, e_n = 0;
-    if (wid < nb) { s_n = __ldg(rowptr + wid); e_n = __ldg(rowptr + wid + 1); }
+    // software pipeline over the rows of this warp: row extents are fetched two rows ahead, the row's block-column
+    // indices (one coalesced load, lane l <- colidx[s+l]) one row ahead, so that inside a row the value stream and
+    // the x gathers are issued together with nothing in front of them.
+    int s0 = 0, e0 = 0, s1 = 0, e1 = 0, cols0 = 0;
+    if (wid < nb) { s0 = __ldg(rowptr + wid); e0 = __ldg(rowptr + wid + 1); }
+    if (wid + nwarps < nb) { s1 = __ldg(rowptr + wid + nwarps); e1 = __ldg(rowptr + wid + nwarps + 1); }
+    if (s0 + lane < e0) cols0 = __ldg(colidx + s0 + lane);
     for (int64_t row = wid; row < nb; row += nwarps) {
-        const int s = s_n, e = e_n;
-        if (row + nwarps < nb) { s_n = __ldg(rowptr + row + nwarps); e_n = __ldg(rowptr + row + nwarps + 1); }
+        const int s = s0, e = e0, mycols = cols0;
+        s0 = s1; e0 = e1;
+        cols0 = (s0 + lane < e0) ? __ldg(colidx + s0 + lane) : 0;          // next row's columns
+        s1 = 0; e1 = 0;
+        if (row + 2 * nwarps < nb) { s1 = __ldg(rowptr + row + 2 * nwarps); e1 = __ldg(rowptr + row + 2 * nwarps + 1); }
         double acc = 0.0;
         for (int blk0 = s; blk0 < e; blk0 += BPS * U) {
             double a[U];
-            int col[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int blk = blk0 + u * BPS + lb;
-                const bool valid = lane_on && blk < e;
-                a[u] = valid ? ld_stream(vals + (int64_t)blk * DD + wq) : 0.0;
-                col[u] = valid ? __ldg(colidx + blk) : 0;
+                a[u] = (lane_on && blk < e) ? ld_stream(vals + (int64_t)blk * DD + wq) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int blk = blk0 + u * BPS + lb;
+                const int rel = blk - s;                                     // block index within the row
+                int col = __shfl_sync(0xffffffffu, mycols, rel & 31);
                 const bool valid = lane_on && blk < e;
-                const double xv = valid ? __ldg(x + (unsigned)(col[u] * D + c)) : 0.0;
+                if (rel >= 32 && valid) col = __ldg(colidx + blk);           // rows longer than 32 blocks (rare)
+                const double xv = valid ? __ldg(x + (unsigned)(col * D + c)) : 0.0;
                 acc = fma(a[u], xv, acc);
             }
         }

@@ -284,6 +284,10 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
             if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;
+        case 6:
+            if (dim == 2) spmv_warp_launch<2, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_warp_launch<3, 8>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
         case 4:   // tile-streaming kernel
             if (dim == 2) spmv_tile_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_tile_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
