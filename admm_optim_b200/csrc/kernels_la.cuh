@@ -218,88 +218,12 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile-streaming BSR SpMV (default).  A tile is a run of consecutive block rows holding <= TB blocks; its
-// value array is ONE contiguous stream which the whole CTA reads with unit-stride loads, all NIT loads of
-// a thread in flight at once (memcpy-like access, independent of the row structure).  Products are staged
-// in shared memory; thread (row, comp) then sums its row segment and applies the MODE epilogue.
-// Same MODE / DOTS semantics as k_bsr_spmv.
-// ---------------------------------------------------------------------------------------------
-template <int D>
-struct SpmvTile {
-    static constexpr int DD = D * D;
-    static constexpr int TB = D == 3 ? 448 : 1024;              // max blocks per tile
-    static constexpr int NIT = (TB * DD + 255) / 256;           // loads per thread (16)
-};
-
-template <int D, int MODE, int DOTS>
-__global__ void __launch_bounds__(256) k_bsr_spmv_tile(int ntiles, const int* __restrict__ tile_row, const int* __restrict__ rowptr,
-                                                       const int* __restrict__ colidx, const double* __restrict__ vals,
-                                                       const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
-                                                       const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
-                                                       const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
-    constexpr int DD = SpmvTile<D>::DD, TB = SpmvTile<D>::TB, NIT = SpmvTile<D>::NIT;
-    __shared__ double sprod[TB * DD];
-    __shared__ int scol[TB];
-    __shared__ int srow[TB + 1];
-    const int tid = threadIdx.x;
-    double dot[2] = {0.0, 0.0};
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int r0 = __ldg(tile_row + tile), nr = __ldg(tile_row + tile + 1) - r0;
-        for (int i = tid; i <= nr; i += 256) srow[i] = __ldg(rowptr + r0 + i);
-        __syncthreads();
-        const int b0 = srow[0], nblk = srow[nr] - b0, nent = nblk * DD;
-        const double* vp = vals + (int64_t)b0 * DD;
-        double a[NIT];
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {                          // the matrix stream: NIT independent loads per thread
-            const int k = tid + j * 256;
-            a[j] = k < nent ? ld_stream(vp + k) : 0.0;
-        }
-        for (int i = tid; i < nblk; i += 256) scol[i] = __ldg(colidx + b0 + i);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-            const int k = tid + j * 256;
-            if (k < nent) {
-                const int blk = k / DD;
-                const int c = (k - blk * DD) % D;
-                sprod[k] = a[j] * __ldg(x + (unsigned)(scol[blk] * D + c));
-            }
-        }
-        __syncthreads();
-        for (int q = tid; q < nr * D; q += 256) {
-            const int lr = q / D, i = q - lr * D;
-            const int bs = srow[lr] - b0, be = srow[lr + 1] - b0;
-            double av = 0.0;
-            for (int blk = bs; blk < be; ++blk) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) av += sprod[blk * DD + i * D + c];
-            }
-            const int64_t gi = (int64_t)(r0 + lr) * D + i;
-            if (MODE == 0) {
-                y[gi] = av;
-                if (DOTS >= 1) dot[0] += w[gi] * av;
-                if (DOTS >= 2) dot[1] += av * av;
-            } else if (MODE == 1) {
-                y[gi] = b[gi] - av;
-            } else {
-                const double res = b[gi] - av;
-                const double dn = (c1 != 0.0 ? c1 * dvec[gi] : 0.0) + c2 * dinv[gi] * res;
-                dvec[gi] = dn;
-                y[gi] = x[gi] + dn;
-            }
-        }
-        __syncthreads();
-    }
-    if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
-}
-
-// ---------------------------------------------------------------------------------------------
 // Warp-per-row BSR SpMV with a FIXED lane -> (block slot, r, c) map (default kernel).
 // D*D lanes cover one block, 32/(D*D) blocks per step (3 for 3x3: 27 active lanes reading 216 contiguous
 // bytes; 8 for 2x2).  Because a lane's (r,c) never changes there is no index division, no select and a
-// single accumulator: ~7 instructions per 8-byte matrix entry instead of ~25 in k_bsr_spmv.  U steps are
-// unrolled with all their loads in flight; the next row's extent is prefetched while the current row streams.
+// single accumulator.  U steps are unrolled with all their loads in flight; the next row's extent is prefetched
+// while the current row streams.  32 registers -> 64 resident warps per SM (measured: occupancy beats deeper
+// per-warp pipelining for this kernel, profiles/r01_spmv_notes.md).
 // Same MODE / DOTS semantics as k_bsr_spmv.
 // ---------------------------------------------------------------------------------------------
 template <int D, int MODE, int DOTS, int U>
@@ -318,35 +242,27 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double dot[2] = {0.0, 0.0};
-    // software pipeline over the rows of this warp: row extents are fetched two rows ahead, the row's block-column
-    // indices (one coalesced load, lane l <- colidx[s+l]) one row ahead, so that inside a row the value stream and
-    // the x gathers are issued together with nothing in front of them.
-    int s0 = 0, e0 = 0, s1 = 0, e1 = 0, cols0 = 0;
-    if (wid < nb) { s0 = __ldg(rowptr + wid); e0 = __ldg(rowptr + wid + 1); }
-    if (wid + nwarps < nb) { s1 = __ldg(rowptr + wid + nwarps); e1 = __ldg(rowptr + wid + nwarps + 1); }
-    if (s0 + lane < e0) cols0 = __ldg(colidx + s0 + lane);
+    int s_n = 0, e_n = 0;
+    if (wid < nb) { s_n = __ldg(rowptr + wid); e_n = __ldg(rowptr + wid + 1); }
     for (int64_t row = wid; row < nb; row += nwarps) {
-        const int s = s0, e = e0, mycols = cols0;
-        s0 = s1; e0 = e1;
-        cols0 = (s0 + lane < e0) ? __ldg(colidx + s0 + lane) : 0;          // next row's columns
-        s1 = 0; e1 = 0;
-        if (row + 2 * nwarps < nb) { s1 = __ldg(rowptr + row + 2 * nwarps); e1 = __ldg(rowptr + row + 2 * nwarps + 1); }
+        const int s = s_n, e = e_n;
+        if (row + nwarps < nb) { s_n = __ldg(rowptr + row + nwarps); e_n = __ldg(rowptr + row + nwarps + 1); }
         double acc = 0.0;
         for (int blk0 = s; blk0 < e; blk0 += BPS * U) {
             double a[U];
+            int col[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int blk = blk0 + u * BPS + lb;
-                a[u] = (lane_on && blk < e) ? ld_stream(vals + (int64_t)blk * DD + wq) : 0.0;
+                const bool valid = lane_on && blk < e;
+                a[u] = valid ? ld_stream(vals + (int64_t)blk * DD + wq) : 0.0;
+                col[u] = valid ? __ldg(colidx + blk) : 0;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int blk = blk0 + u * BPS + lb;
-                const int rel = blk - s;                                     // block index within the row
-                int col = __shfl_sync(0xffffffffu, mycols, rel & 31);
                 const bool valid = lane_on && blk < e;
-                if (rel >= 32 && valid) col = __ldg(colidx + blk);           // rows longer than 32 blocks (rare)
-                const double xv = valid ? __ldg(x + (unsigned)(col * D + c)) : 0.0;
+                const double xv = valid ? __ldg(x + (unsigned)(col[u] * D + c)) : 0.0;
                 acc = fma(a[u], xv, acc);
             }
         }

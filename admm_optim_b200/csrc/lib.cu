@@ -40,8 +40,6 @@ struct LevelDev {
     int nv = 0, ne = 0, nvc = 0, maxrow = 0;
     int64_t nnzb = 0;
     DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
-    DevBuf<int> tile_row;                        // SpMV tiles: first block row of every tile (ntiles+1)
-    int ntiles = 0;
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
     DevBuf<double> xyz;                          // top level only
@@ -82,19 +80,6 @@ void Domain::finalize() {
         int mr = 0;
         for (int i = 0; i < H.nv; ++i) mr = std::max(mr, P.rowptr[i + 1] - P.rowptr[i]);
         L.maxrow = mr;
-        {   // SpMV tiles: greedy runs of consecutive rows with <= TB blocks
-            const int TB = H.dim == 3 ? SpmvTile<3>::TB : SpmvTile<2>::TB;
-            std::vector<int> tr;
-            tr.push_back(0);
-            int start = 0;
-            for (int i = 0; i < H.nv; ++i) {
-                AB_REQUIRE(P.rowptr[i + 1] - P.rowptr[i] <= TB, AB_ERR_UNSUPPORTED, "vertex valence exceeds the SpMV tile size");
-                if (P.rowptr[i + 1] - P.rowptr[start] > TB) { tr.push_back(i); start = i; }
-            }
-            tr.push_back(H.nv);
-            L.ntiles = (int)tr.size() - 1;
-            L.tile_row.upload(tr, ctx->stream);
-        }
         L.rowptr.upload(P.rowptr, ctx->stream);
         L.colidx.upload(P.colidx, ctx->stream);
         L.diagpos.upload(P.diagpos, ctx->stream);
@@ -244,20 +229,6 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
     else AB_SPMV(2, 0);
 #undef AB_SPMV
 }
-template <int D>
-static void spmv_tile_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                             const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
-    const int g = std::max(1, std::min(L.ntiles, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
-#define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv_tile<D, MODE, DOTS>), g, 256, 0, L.ntiles, L.tile_row.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
-    if (mode == 0) {
-        if (dots == 0) AB_SPMV(0, 0);
-        else if (dots == 1) AB_SPMV(0, 1);
-        else AB_SPMV(0, 2);
-    } else if (mode == 1) AB_SPMV(1, 0);
-    else AB_SPMV(2, 0);
-#undef AB_SPMV
-}
 template <int D, int U>
 static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                              const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
@@ -275,30 +246,19 @@ static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
-    switch (ctx->spmv_variant) {   // tuning knob "spmv_variant"; 0 = default
-        case 0:
+    switch (ctx->spmv_variant) {   // tuning knob "spmv_variant"; 0 = default (warp per row, U = 3)
+        case 1:
             if (dim == 2) spmv_warp_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_warp_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;
-        case 5:
+        case 2:   // sub-warp row groups with flattened entries (first-generation kernel, kept for comparison)
+            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
+        default:
             if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;
-        case 6:
-            if (dim == 2) spmv_warp_launch<2, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_warp_launch<3, 8>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            return;
-        case 4:   // tile-streaming kernel
-            if (dim == 2) spmv_tile_launch<2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_tile_launch<3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            return;
-        default: break;
-    }
-    if (dim == 2) { spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); return; }
-    switch (ctx->spmv_variant) {   // row-group kernels kept for comparison
-        case 1: spmv_launch<3, 9, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
-        case 2: spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
-        default: spmv_launch<3, 5, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red); break;
     }
 }
 
