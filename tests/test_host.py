@@ -1,0 +1,156 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the header declares,
+the native grid front end (ugx reader + regular refinement) matches the oracle bit for bit, error behaviour,
+and the world_size-2 plumbing on gloo.  No GPU, no compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import GRID2D, GRID3D, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from admm_optim_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "admm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ab_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 60
+    for n in sorted(names):
+        assert hasattr(lib, n), "header declares %s but the library does not export it" % n
+    assert names - {"ab_last_error", "ab_version"} == set(_lib.PROTOTYPES), "ctypes prototypes out of sync with the header"
+    assert lib.ab_version() >= 100
+
+
+def _host_domain(path_or_npz, refs):
+    from admm_optim_b200 import ug4
+
+    class _UG:      # host-only: no context
+        dim = None
+        ctx = None
+    ug = ug4.Backend.__new__(ug4.Backend)
+    ug.ctx, ug.dim = C.c_void_p(), None
+    dom = ug4.Domain(ug)
+    ug4.Backend.LoadDomain(ug, dom, path_or_npz)
+    ug4.call("ab_domain_refine", dom.h, refs)
+    return dom
+
+
+@pytest.mark.parametrize("grid,refs", [(GRID3D, 2), (GRID2D, 3)])
+def test_native_refinement_is_bit_identical_to_oracle(grid, refs):
+    from oracle import mesh_np as M
+    dom = _host_domain(grid, refs)
+    levels = M.build_hierarchy(M.load_npz(grid), refs)
+    assert dom.num_levels() == refs + 1
+    for l, o in enumerate(levels):
+        g = dom.get_level(l)
+        assert np.array_equal(g["xyz"], o.xyz) and np.array_equal(g["elems"], o.elems) and np.array_equal(g["vsub"], o.vsub)
+        if l:
+            assert np.array_equal(g["parent_a"], o.parent_a) and np.array_equal(g["parent_b"], o.parent_b)
+        assert dom.level_info(l)["nedges"] == len(M.unique_edges(o))
+
+
+def test_ugx_reader_native_vs_oracle(tmp_path):
+    """A small hand-written .ugx (two tetrahedra, two subsets) through both readers; plus the shipped grids when
+    the reference tree is present (it is not on the GPU box)."""
+    from oracle import mesh_np as M
+    ugx = textwrap.dedent("""\
+        <?xml version="1.0" encoding="utf-8"?>
+        <grid name="defGrid">
+        <vertices coords="3">0 0 0 1 0 0 0 1 0 0 0 1 1 1 1</vertices>
+        <edges>0 1 0 2 0 3 1 2 1 3 2 3 1 4 2 4 3 4</edges>
+        <triangles>0 1 2 0 1 3 0 2 3 1 2 3 1 2 4 1 3 4 2 3 4</triangles>
+        <tetrahedrons>0 1 2 3 1 2 3 4</tetrahedrons>
+        <subset_handler name="defSH">
+        <subset name="outer" color="0 0 0 1"><volumes>0 1</volumes><faces>3</faces><vertices>4</vertices><edges>6 7 8</edges></subset>
+        <subset name="wall" color="1 0 0 1"><faces>0 1 2 4 5 6</faces><edges>0 1 2 3 4 5</edges><vertices>0 1 2 3</vertices></subset>
+        </subset_handler>
+        </grid>
+        """)
+    f = tmp_path / "two_tets.ugx"
+    f.write_text(ugx)
+    files = [str(f)] + [p for p in ("/root/reference/grids/refined.ugx", "/root/reference/grids/box_3D_elongated.ugx") if os.path.exists(p)]
+    for path in files:
+        dom = _host_domain(path, 1)
+        levels = M.build_hierarchy(M.load_ugx(path), 1)
+        for l, o in enumerate(levels):
+            g = dom.get_level(l)
+            assert np.array_equal(g["xyz"], o.xyz) and np.array_equal(g["elems"], o.elems) and np.array_equal(g["vsub"], o.vsub)
+        for i, n in enumerate(levels[0].subset_names):
+            assert dom.subset_index(n) == i
+
+
+def test_shipped_fixtures_match_reference_grids_when_present():
+    from oracle import mesh_np as M
+    for name, npz in (("refined", GRID2D), ("box_3D_elongated", GRID3D)):
+        src = "/root/reference/grids/%s.ugx" % name
+        if not os.path.exists(src):
+            pytest.skip("reference tree not present (GPU box)")
+        a, b = M.load_ugx(src), M.load_npz(npz)
+        assert np.array_equal(a.xyz, b.xyz) and np.array_equal(a.elems, b.elems) and np.array_equal(a.vsub, b.vsub)
+        assert a.subset_names == b.subset_names and np.array_equal(a.sp_edges, b.sp_edges) and np.array_equal(a.sp_faces, b.sp_faces)
+
+
+def test_error_behaviour_without_gpu_is_loud():
+    from admm_optim_b200 import _lib, ug4
+    lib = _lib.load()
+    with pytest.raises(_lib.AdmmB200Error):
+        _lib.call("ab_domain_load_ugx", None, b"/nonexistent/file.ugx", C.byref(C.c_void_p()))
+    assert b"cannot open" in lib.ab_last_error()
+    dom = _host_domain(GRID3D, 0)
+    sp = C.c_void_p()
+    with pytest.raises(_lib.AdmmB200Error, match="context"):      # spaces need a GPU context: no CPU fallback
+        _lib.call("ab_space_create", dom.h, 1, 3, C.byref(sp))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.AdmmB200Error, match="no CPU fallback|no CUDA"):
+            ug4.Backend(device=0)
+
+
+def test_driver_rejects_unknown_parameters_and_descriptor_mirrors_reference():
+    from admm_optim_b200 import driver
+    with pytest.raises(ValueError):
+        driver.ObstacleOptim(object(), 3, nonsense=1)
+    assert driver.DEFAULTS_3D["numRefs"] == 2 and driver.DEFAULTS_3D["admmSteps"] == 2      # 3d_admm.lua:46,48
+    assert driver.DEFAULTS_2D["numRefs"] == 3 and driver.DEFAULTS_2D["admmSteps"] == 1000   # 2d_admm.lua:43,45
+
+    class Rec:
+        def SuperLU(self):
+            return "superlu"
+
+        class util:
+            class solver:
+                @staticmethod
+                def CreateSolver(desc):
+                    return desc
+    d3 = driver.linear_solver(Rec(), "dd", "space", False, 3)
+    d2 = driver.linear_solver(Rec(), "dd", "space", True, 2)
+    assert d3["type"] == "bicgstab" and d3["precond"]["type"] == "gmg" and d3["precond"]["smoother"] == "gs"
+    assert (d3["precond"]["preSmooth"], d3["precond"]["postSmooth"], d3["precond"]["baseLevel"], d3["precond"]["rap"]) == (3, 3, 0, True)
+    assert (d3["convCheck"]["iterations"], d3["convCheck"]["absolute"]) == (3000, 1e-10)      # obstacle_optim_3d_util.lua:34-35
+    assert (d2["convCheck"]["iterations"], d2["convCheck"]["absolute"]) == (2000, 1e-12)      # obstacle_optim_util.lua:35-36
+
+
+def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
+    """N>1 contract of the reference arm: rank 0 alone prints the line, other ranks exit 0 without work.
+    Uses a tiny refinement so that the CPU suite stays fast."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    outs = []
+    procs = []
+    for rank in range(2):
+        e = dict(env, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                                       "--warmup", "0", "--refs", "0"], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err
+        outs.append(out.strip())
+    import json
+    line = json.loads(outs[0])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert outs[1] == ""

@@ -1,0 +1,168 @@
+"""CPU tests that pin the oracle (no GPU): known answers from the grids, analytic invariants of the restated
+model, lua-matrix semantics.  The reference has no tests or golden vectors -- parity is
+unpinned by the reference, these are the checks that stand in."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GRID2D, GRID3D
+from oracle import fem_np as F
+from oracle import mesh_np as M
+
+# V' = V + E ...   (V, E, T) per level
+COUNTS3D = [(338, 1786, 1216), (2124, 12786, 9728), (14910, 96476, 77824)]
+COUNTS2D = [(160, 436, 276), (596, 1700, 1104), (2296, 6712, 4416), (9008, 26672, 17664)]
+
+
+@pytest.fixture(scope="module")
+def h3():
+    return M.build_hierarchy(M.load_npz(GRID3D), 2)
+
+
+@pytest.fixture(scope="module")
+def h2():
+    return M.build_hierarchy(M.load_npz(GRID2D), 3)
+
+
+def test_entity_counts_and_volume(h3, h2):
+    for lv, (v, e, t) in zip(h3, COUNTS3D):
+        assert (lv.nv, len(M.unique_edges(lv)), lv.ne) == (v, e, t)
+        _, vol, _ = F.geometry(lv)
+        assert abs(vol.sum() - 719.0) < 1e-9                      # 20*6*6 - 1, exact under refinement
+    for lv, (v, e, t) in zip(h2, COUNTS2D):
+        assert (lv.nv, len(M.unique_edges(lv)), lv.ne) == (v, e, t)
+        _, vol, _ = F.geometry(lv)
+        assert abs(vol.sum() - 83.0) < 1e-10
+    X = h3[2].xyz[h3[2].elems]
+    assert (np.linalg.det(X[:, 1:] - X[:, :1]) > 0).all()         # children re-oriented
+    X2 = h2[0].xyz[h2[0].elems]
+    assert (np.linalg.det(X2[:, 1:] - X2[:, :1]) < 0).sum() == 134   # clockwise triangles of refined.ugx
+
+
+def test_subset_inheritance(h3):
+    # obstacle surface of the unit cube with n cells per edge has 6 n^2 + 2 vertices
+    for lv, n in zip(h3, (4, 8, 16)):
+        assert lv.vertex_mask("obstacle_surface").sum() == 6 * n * n + 2
+        on = lv.xyz[lv.vertex_mask("obstacle_surface")]
+        assert np.allclose(np.abs(on).max(axis=1), 0.5)
+        inlet = lv.xyz[lv.vertex_mask("inlet")]
+        assert np.allclose(inlet[:, 0], -10.0)
+
+
+def test_barycenter_zero_and_constants(h3):
+    m = h3[1]
+    z = np.zeros(m.nv * 3)
+    assert np.abs(F.barycenter_defect(m, z)).max() < 1e-10       # symmetric domain
+    assert abs(F.volume_defect(m, z, 719.0)) < 1e-9
+    # rigid translation: volume unchanged, barycentre moves by V * t
+    t = np.tile([0.1, -0.2, 0.05], m.nv)
+    assert abs(F.volume_defect(m, t, 719.0)) < 1e-9
+    assert np.allclose(F.barycenter_defect(m, t), 719.0 * np.array([0.1, -0.2, 0.05]), atol=1e-9)
+
+
+@pytest.mark.parametrize("which", ["3d", "2d"])
+def test_constraint_derivatives_fd(h3, h2, which):
+    m = h3[1] if which == "3d" else h2[2]
+    d = m.dim
+    rng = np.random.default_rng(0)
+    u = 0.02 * rng.standard_normal(m.nv * d)
+    v = rng.standard_normal(m.nv * d)
+    h = 1e-6
+
+    def g(uu):
+        return np.concatenate([[F.volume_defect(m, uu, 0.0)], F.barycenter_defect(m, uu)])
+    fd = (g(u + h * v) - g(u - h * v)) / (2 * h)
+    for i in range(d + 1):
+        w = np.zeros(d + 1)
+        w[i] = 1.0
+        gp = F.load_vector(m, u, None, w, 1.0)
+        assert abs(gp @ v - fd[i]) < 1e-6 * max(1.0, abs(fd[i]))
+        H = F.hessian_matrix(m, u, c=0.0, lam_vol=w[0], lam_bary=w[1:])
+        fd2 = (F.load_vector(m, u + h * v, None, w, 1.0) - F.load_vector(m, u - h * v, None, w, 1.0)) / (2 * h)
+        assert np.abs(H @ v - fd2).max() < 1e-6 * np.abs(fd2).max()
+        assert abs(H - H.T).max() < 1e-12
+
+
+def test_laplacian_kernel_and_dirichlet(h3):
+    m = h3[1]
+    A = F.hessian_matrix(m, None)
+    assert np.abs(A @ np.ones(m.nv * 3)).max() < 1e-10            # constants in the kernel when Lambda = 0
+    dm = F.dirichlet_dofs(m)
+    Ad = F.hessian_matrix(m, None, dmask=dm)
+    assert abs(Ad - Ad.T).max() == 0 or abs(Ad - Ad.T).max() < 1e-14
+    assert np.allclose(Ad.diagonal()[dm], 1.0)
+    assert dm.sum() == 3 * (m.vertex_mask("inlet").sum() + m.vertex_mask("wall").sum() + m.vertex_mask("outlet").sum())
+
+
+def test_transfer_reproduces_linear_and_rap_is_rediscretisation(h3):
+    P = F.prolongation(h3[2], 3)
+    lin_c = (h3[1].xyz @ np.array([[1.0, 2, 3], [0.5, -1, 2], [2, 0, 1]])).ravel()
+    lin_f = (h3[2].xyz @ np.array([[1.0, 2, 3], [0.5, -1, 2], [2, 0, 1]])).ravel()
+    assert np.abs(P @ lin_c - lin_f).max() < 1e-12
+    Af = F.hessian_matrix(h3[2], None)
+    Ac = F.hessian_matrix(h3[1], None)
+    assert abs(P.T @ Af @ P - Ac).max() < 1e-11                   # nested P1 spaces, constant coefficient
+
+
+def test_gmg_bicgstab_smoothers_side_by_side(h3):
+    dm = [F.dirichlet_dofs(l) for l in h3]
+    A = F.hessian_matrix(h3[2], None, dmask=dm[2])
+    b = np.random.default_rng(1).standard_normal(A.shape[0]) * (~dm[2])
+    its = {}
+    for sm in ("gs", "cheb", "jac"):
+        g = F.GMG(h3, A, dm, smoother=sm, cheb_ratio=6.0)
+        x, ok, n, r = F.bicgstab(A, b, np.zeros_like(b), g.apply, abs_tol=1e-10)
+        assert ok and np.linalg.norm(b - A @ x) < 1e-9
+        its[sm] = n
+    assert its["gs"] <= its["cheb"] <= its["jac"] <= 12, its   # 6 / 7 / 9
+
+
+def test_projections():
+    rng = np.random.default_rng(2)
+    q = rng.standard_normal(9 * 50)
+    p = F.project_frobenius(q, 0.3, 3).reshape(-1, 9)
+    assert (np.linalg.norm(p, axis=1) <= 0.3 + 1e-14).all()
+    small = 0.01 * q
+    assert np.array_equal(F.project_frobenius(small, 0.3, 3), small)
+    q2 = rng.standard_normal(4 * 200)
+    p2 = F.project_spectral(q2, 0.5).reshape(-1, 2, 2)
+    Q2 = q2.reshape(-1, 2, 2)
+    U, S, Vt = np.linalg.svd(Q2)
+    ref = U @ (np.minimum(S, 0.5)[:, :, None] * Vt)
+    assert np.allclose(p2, ref, atol=1e-12)
+
+
+def test_lua_matrix_semantics():
+    from admm_optim_b200.schur import Matrix
+    rng = np.random.default_rng(3)
+    for n in (3, 4):
+        S = rng.standard_normal((n, n)) + n * np.eye(n)
+        inv_o = np.array(F.lua_matrix_invert(S.tolist()))
+        inv_p = np.array(Matrix(S.tolist()).invert())
+        assert np.array_equal(inv_o, inv_p)                       # two independent restatements, same roundings
+        assert np.allclose(inv_o, np.linalg.inv(S), rtol=1e-12, atol=1e-13)
+        r = rng.standard_normal((n, 1))
+        assert np.array_equal(np.array(F.lua_matrix_mul(inv_o.tolist(), r.tolist())), np.array(Matrix(inv_p.tolist()).mul(Matrix(r.tolist()))))
+    # pivot rule: smallest non-zero magnitude in the column is swapped up (matrix.lua:422-442)
+    S = [[4.0, 1.0], [0.5, 3.0]]
+    assert np.allclose(np.array(Matrix(S).invert()), np.linalg.inv(np.array(S)))
+    assert Matrix([[1.0, 2.0], [2.0, 4.0]]).invert() is None and F.lua_matrix_invert([[1.0, 2.0], [2.0, 4.0]]) is None
+
+
+def test_newton_schur_replay_converges_quadratically():
+    """The driver replay on the oracle backend: Newton on the KKT system contracts quadratically and the constraint
+    residuals L_lambda vanish -- the sign conventions of DESIGN.md 'Signs' are self-consistent in 2D and 3D."""
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    for dim, grid, refs in ((3, GRID3D, 0), (2, GRID2D, 1)):
+        p = ObstacleOptim(ug4_np.Backend(smoother="cheb"), dim, numRefs=refs, grid=grid, admmSteps=1).setup()
+        p.set_sensitivity(p.synthetic_sensitivity(0.5))
+        tr = p.run_admm()
+        assert tr and not p.p_solver_failure
+        dl = [n["delta_lambda"] for n in tr[0]["newton"]]
+        assert dl[-1] <= 1e-9 and len(dl) <= 8
+        assert all(dl[i + 1] < 0.5 * dl[i] for i in range(len(dl) - 1))
+        assert max(abs(v) for v in tr[0]["L_lambda"]) < 1e-8
+        assert tr[0]["u_diff"] > 0 and tr[0]["lambda_inc"] > 0
