@@ -103,7 +103,7 @@ struct DevBuf {
     void alloc(size_t n_) {
         release();
         n = n_;
-        if (n) p = (T*)DevicePool::get().alloc(n * sizeof(T));
+        if (n) p = (T*)DevicePool::get().alloc(n * sizeof(T) + 16);   // +16: bulk copies may read up to 15 bytes past the end
     }
     void release() {
         if (p) DevicePool::get().release(p);
@@ -145,15 +145,15 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Reduce NV per-thread values over the whole grid. Block size must be 256. OP: 0 = sum, 1 = max.
-// Results are written to out[0..NV) by the last block to finish, summing the per-block partials in block
+// Reduce NV per-thread values over the whole grid (block size: multiple of 32, <= 1024). OP: 0 = sum, 1 = max.
+// Results are written to out[0..NV) by the last block to finish, combining the per-block partials in block
 // order (bitwise reproducible for a fixed launch configuration).
 template <int NV, int OP>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                             double* __restrict__ out) {
-    __shared__ double sm[NV][8];
+    __shared__ double sm[NV][32];
     __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double w = OP == 0 ? warp_sum(v[k]) : warp_max(v[k]);
@@ -162,7 +162,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
     __syncthreads();
     if (threadIdx.x < NV) {
         double acc = sm[threadIdx.x][0];
-        for (int w = 1; w < 8; ++w) acc = OP == 0 ? acc + sm[threadIdx.x][w] : fmax(acc, sm[threadIdx.x][w]);
+        for (int w = 1; w < nwarp; ++w) acc = OP == 0 ? acc + sm[threadIdx.x][w] : fmax(acc, sm[threadIdx.x][w]);
         partials[(size_t)blockIdx.x * NV + threadIdx.x] = acc;
     }
     __threadfence();
@@ -174,8 +174,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
     __syncthreads();
     if (is_last) {
         __threadfence();
-        // NV values, gridDim.x partials each: warp k reduces value k (NV <= 8 warps) -- fixed order
-        for (int k = warp; k < NV; k += 8) {
+        for (int k = warp; k < NV; k += nwarp) {      // warp k reduces value k over all blocks -- fixed order
             double acc = OP == 0 ? 0.0 : -1.0e300;
             for (unsigned int b = lane; b < gridDim.x; b += 32) {
                 double p = partials[(size_t)b * NV + k];
@@ -186,6 +185,41 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
         }
         if (threadIdx.x == 0) *ticket = 0u;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk async copy (TMA engine, no tensor map needed) -- sm_90+ PTX, used by k_bsr_spmv_tma
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// global -> shared bulk copy; src, dst 16-byte aligned, bytes a multiple of 16; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 }  // namespace ab

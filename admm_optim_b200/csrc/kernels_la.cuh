@@ -302,6 +302,180 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
     if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged BSR SpMV.  A tile is a run of consecutive block rows with <= TB blocks; its values, block
+// columns, row extents and the row slices of the vectors the epilogue needs are contiguous in global memory.
+// One producer thread per CTA streams them into a ring of NSTAGE shared-memory stages with 1-D bulk async
+// copies (cp.async.bulk, completion on an mbarrier) -- the matrix stream never touches the LSU/L1 path and
+// the bytes in flight are set by the ring depth, not by the number of resident warps.  The consumer warps
+// take rows of a landed tile (warp per row, same fixed lane -> (block slot, r, c) map as k_bsr_spmv_warp),
+// read the matrix from shared memory, gather x through L1/L2 and apply the MODE epilogue.
+// Same MODE / DOTS semantics as k_bsr_spmv.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct SpmvTma {
+    static constexpr int DD = D * D;
+    static constexpr int TB = D == 3 ? 256 : 512;            // max blocks per tile
+    static constexpr int RMAX = TB / (D + 1);                 // max rows per tile (a P1 row has >= D+1 blocks)
+    static constexpr int NSTAGE = 3;
+    static constexpr int NT = 512;                            // 15 consumer warps + 1 producer warp
+    static constexpr int NAUX = 4;
+    static constexpr int VALS_B = TB * DD * 8 + 16;
+    static constexpr int COLS_B = TB * 4 + 16;
+    static constexpr int ROWS_B = ((RMAX + 1) * 4 + 16 + 15) / 16 * 16;
+    static constexpr int AUX_B = (RMAX * D * 8 + 16 + 15) / 16 * 16;
+    static constexpr int STAGE_B = VALS_B + COLS_B + ROWS_B + NAUX * AUX_B;
+    static constexpr int META_B = 64;                         // per stage: r0, nr, b0, pre offsets
+    static constexpr int SMEM_B = 128 + NSTAGE * (STAGE_B + META_B);
+};
+
+template <int D, int MODE, int DOTS, int U>
+__global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, const int* __restrict__ tile_info, const int* __restrict__ rowptr,
+                                                                 const int* __restrict__ colidx, const double* __restrict__ vals,
+                                                                 const double* __restrict__ x, const double* __restrict__ b,
+                                                                 double* __restrict__ y, const double* __restrict__ dinv,
+                                                                 double* __restrict__ dvec, double c1, double c2, const double* __restrict__ w,
+                                                                 double* partials, unsigned int* ticket, double* red) {
+    using T = SpmvTma<D>;
+    constexpr int DD = T::DD, BPS = 32 / DD, NS = T::NSTAGE, NW = T::NT / 32 - 1;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);              // [NS]
+    uint64_t* empty = full + NS;                                       // [NS]
+    unsigned char* stage0 = smem + 128;
+    int* meta0 = reinterpret_cast<int*>(smem + 128 + NS * T::STAGE_B);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int n_my = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    double dot[2] = {0.0, 0.0};
+    // which vectors does the epilogue read per row?  (aux slot -> global pointer)
+    const double* aux_src[T::NAUX] = {nullptr, nullptr, nullptr, nullptr};
+    if (MODE == 0 && DOTS >= 1) aux_src[0] = w;
+    if (MODE == 1) aux_src[0] = b;
+    if (MODE == 2) { aux_src[0] = b; aux_src[1] = dinv; aux_src[2] = dvec; aux_src[3] = x; }
+
+    if (warp == NW) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            for (int i = 0; i < n_my; ++i) {
+                const int st = i % NS;
+                if (i >= NS) mbar_wait(empty + st, ((i / NS) - 1) & 1);
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int r0 = __ldg(tile_info + 2 * tile), b0 = __ldg(tile_info + 2 * tile + 1);
+                const int r1 = __ldg(tile_info + 2 * tile + 2), b1 = __ldg(tile_info + 2 * tile + 3);
+                const int nr = r1 - r0, nblk = b1 - b0;
+                unsigned char* sb = stage0 + (size_t)st * T::STAGE_B;
+                int* meta = meta0 + st * (T::META_B / 4);
+                // 16-byte alignment: start each copy at the aligned-down source, remember the byte offset
+                const uintptr_t pv = (uintptr_t)(vals + (int64_t)b0 * DD), pc = (uintptr_t)(colidx + b0), pr = (uintptr_t)(rowptr + r0);
+                const uint32_t ov = pv & 15, oc = pc & 15, orw = pr & 15;
+                const uint32_t nv_b = (ov + (uint32_t)nblk * DD * 8 + 15) & ~15u, nc_b = (oc + (uint32_t)nblk * 4 + 15) & ~15u,
+                               nr_b = (orw + (uint32_t)(nr + 1) * 4 + 15) & ~15u;
+                uint32_t total = nv_b + nc_b + nr_b;
+                uint32_t oa[T::NAUX], na[T::NAUX];
+#pragma unroll
+                for (int k = 0; k < T::NAUX; ++k) {
+                    oa[k] = 0; na[k] = 0;
+                    if (aux_src[k]) {
+                        const uintptr_t pa = (uintptr_t)(aux_src[k] + (int64_t)r0 * D);
+                        oa[k] = pa & 15;
+                        na[k] = (oa[k] + (uint32_t)nr * D * 8 + 15) & ~15u;
+                        total += na[k];
+                    }
+                }
+                meta[0] = r0; meta[1] = nr; meta[2] = b0; meta[3] = ov; meta[4] = oc; meta[5] = orw;
+#pragma unroll
+                for (int k = 0; k < T::NAUX; ++k) meta[6 + k] = oa[k];
+                mbar_arrive_expect_tx(full + st, total);
+                bulk_g2s(sb, (const void*)(pv - ov), nv_b, full + st);
+                bulk_g2s(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st);
+                bulk_g2s(sb + T::VALS_B + T::COLS_B, (const void*)(pr - orw), nr_b, full + st);
+#pragma unroll
+                for (int k = 0; k < T::NAUX; ++k)
+                    if (aux_src[k]) bulk_g2s(sb + T::VALS_B + T::COLS_B + T::ROWS_B + k * T::AUX_B, (const void*)((uintptr_t)(aux_src[k] + (int64_t)r0 * D) - oa[k]), na[k], full + st);
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const int lb = lane / DD, wq = lane - lb * DD, c = wq % D;
+        const bool lane_on = lb < BPS;
+        for (int i = 0; i < n_my; ++i) {
+            const int st = i % NS;
+            mbar_wait(full + st, (i / NS) & 1);
+            const unsigned char* sb = stage0 + (size_t)st * T::STAGE_B;
+            const int* meta = meta0 + st * (T::META_B / 4);
+            const int r0 = meta[0], nr = meta[1], b0 = meta[2];
+            const double* sv = reinterpret_cast<const double*>(sb + meta[3]);
+            const int* sc = reinterpret_cast<const int*>(sb + T::VALS_B + meta[4]);
+            const int* sr = reinterpret_cast<const int*>(sb + T::VALS_B + T::COLS_B + meta[5]);
+            const unsigned char* sa = sb + T::VALS_B + T::COLS_B + T::ROWS_B;
+            for (int lr = warp; lr < nr; lr += NW) {
+                const int s = sr[lr] - b0, e = sr[lr + 1] - b0;
+                double acc = 0.0;
+                for (int blk0 = s; blk0 < e; blk0 += BPS * U) {
+                    double a[U];
+                    int col[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int blk = blk0 + u * BPS + lb;
+                        const bool valid = lane_on && blk < e;
+                        a[u] = valid ? sv[blk * DD + wq] : 0.0;
+                        col[u] = valid ? sc[blk] : 0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int blk = blk0 + u * BPS + lb;
+                        const bool valid = lane_on && blk < e;
+                        const double xv = valid ? __ldg(x + (unsigned)(col[u] * D + c)) : 0.0;
+                        acc = fma(a[u], xv, acc);
+                    }
+                }
+                double v;
+                if constexpr (D == 3) {
+                    const double t1 = __shfl_down_sync(0xffffffffu, acc, 9);
+                    const double t2 = __shfl_down_sync(0xffffffffu, acc, 18);
+                    v = acc + t1 + t2;
+                    const double u1 = __shfl_down_sync(0xffffffffu, v, 1);
+                    const double u2 = __shfl_down_sync(0xffffffffu, v, 2);
+                    v = v + u1 + u2;
+                } else {
+                    v = acc;
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_down_sync(0xffffffffu, v, 1);
+                }
+                if (lane < DD && c == 0) {
+                    const int r = lane / D;
+                    const int li = lr * D + r;
+                    const int64_t gi = (int64_t)(r0 + lr) * D + r;
+                    if (MODE == 0) {
+                        y[gi] = v;
+                        if (DOTS >= 1) dot[0] += reinterpret_cast<const double*>(sa + meta[6])[li] * v;
+                        if (DOTS >= 2) dot[1] += v * v;
+                    } else if (MODE == 1) {
+                        y[gi] = reinterpret_cast<const double*>(sa + meta[6])[li] - v;
+                    } else {
+                        const double res = reinterpret_cast<const double*>(sa + meta[6])[li] - v;
+                        const double di = reinterpret_cast<const double*>(sa + T::AUX_B + meta[7])[li];
+                        const double dold = c1 != 0.0 ? reinterpret_cast<const double*>(sa + 2 * T::AUX_B + meta[8])[li] : 0.0;
+                        const double xi = reinterpret_cast<const double*>(sa + 3 * T::AUX_B + meta[9])[li];
+                        const double dn = c1 * dold + c2 * di * res;
+                        dvec[gi] = dn;
+                        y[gi] = xi + dn;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + st);
+        }
+    }
+    if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
+}
+
 // first Chebyshev/Jacobi step from a zero initial guess: d = c2*dinv*b ; x = d   (no matrix pass)
 __global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* __restrict__ b,
                                double* __restrict__ d, double* __restrict__ x) {

@@ -40,6 +40,8 @@ struct LevelDev {
     int nv = 0, ne = 0, nvc = 0, maxrow = 0;
     int64_t nnzb = 0;
     DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
+    DevBuf<int> tile_info;                       // TMA SpMV tiles: (first row, first block) per tile, ntiles+1 entries
+    int ntiles = 0;
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
     DevBuf<double> xyz;                          // top level only
@@ -80,6 +82,20 @@ void Domain::finalize() {
         int mr = 0;
         for (int i = 0; i < H.nv; ++i) mr = std::max(mr, P.rowptr[i + 1] - P.rowptr[i]);
         L.maxrow = mr;
+        {   // TMA SpMV tiles: greedy runs of consecutive rows with <= TB blocks and <= RMAX rows
+            const int TB = H.dim == 3 ? SpmvTma<3>::TB : SpmvTma<2>::TB, RMAX = H.dim == 3 ? SpmvTma<3>::RMAX : SpmvTma<2>::RMAX;
+            std::vector<int> ti;
+            ti.push_back(0); ti.push_back(0);
+            int start = 0;
+            bool ok = true;
+            for (int i = 0; i < H.nv; ++i) {
+                if (P.rowptr[i + 1] - P.rowptr[i] > TB) ok = false;
+                if (P.rowptr[i + 1] - P.rowptr[start] > TB || i + 1 - start > RMAX) { ti.push_back(i); ti.push_back(P.rowptr[i]); start = i; }
+            }
+            ti.push_back(H.nv); ti.push_back(P.rowptr[H.nv]);
+            L.ntiles = ok ? (int)ti.size() / 2 - 1 : 0;      // 0: a row exceeds the tile (fall back to the warp kernel)
+            L.tile_info.upload(ti, ctx->stream);
+        }
         L.rowptr.upload(P.rowptr, ctx->stream);
         L.colidx.upload(P.colidx, ctx->stream);
         L.diagpos.upload(P.diagpos, ctx->stream);
@@ -230,6 +246,25 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
 #undef AB_SPMV
 }
 template <int D, int U>
+static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
+                            const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+    using T = SpmvTma<D>;
+    const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
+#define AB_SPMV(MODE, DOTS)                                                                                                          \
+    do {                                                                                                                              \
+        static bool attr = false;                                                                                                     \
+        if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, MODE, DOTS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B)); attr = true; } \
+        AB_LAUNCH(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red); \
+    } while (0)
+    if (mode == 0) {
+        if (dots == 0) AB_SPMV(0, 0);
+        else if (dots == 1) AB_SPMV(0, 1);
+        else AB_SPMV(0, 2);
+    } else if (mode == 1) AB_SPMV(1, 0);
+    else AB_SPMV(2, 0);
+#undef AB_SPMV
+}
+template <int D, int U>
 static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                              const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
     const int64_t want = ((int64_t)L.nv + 7) / 8;        // 8 warps (rows) per CTA
@@ -250,6 +285,17 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
         case 1:
             if (dim == 2) spmv_warp_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_warp_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            return;
+        case 3:   // TMA-staged tiles
+        case 4:
+            if (L.ntiles > 0) {
+                if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                else if (ctx->spmv_variant == 3) spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                else spmv_tma_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                return;
+            }
+            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;
         case 2:   // sub-warp row groups with flattened entries (first-generation kernel, kept for comparison)
             if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
