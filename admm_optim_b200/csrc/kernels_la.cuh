@@ -400,8 +400,13 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
         }
     } else {
         // ---------------- consumers ----------------
-        const int lb = lane / DD, wq = lane - lb * DD, c = wq % D;
-        const bool lane_on = lb < BPS;
+        // half-warp per block row, lane <-> (block slot, column c) of the block: one x gather and D value loads
+        // (column c of the DxD block, from shared memory) feed D independent accumulators -- no idle work per entry,
+        // no index division; two rows per warp share every instruction.
+        constexpr int BPH = 16 / D;                     // blocks per step of a half-warp (5 for 3x3, 8 for 2x2)
+        const int hl = lane & 15, half = lane >> 4;
+        const int lb = hl / D, c = hl - lb * D;
+        const bool lane_on = lb < BPH;
         for (int i = 0; i < n_my; ++i) {
             const int st = i % NS;
             mbar_wait(full + st, (i / NS) & 1);
@@ -412,46 +417,39 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
             const int* sc = reinterpret_cast<const int*>(sb + T::VALS_B + meta[4]);
             const int* sr = reinterpret_cast<const int*>(sb + T::VALS_B + T::COLS_B + meta[5]);
             const unsigned char* sa = sb + T::VALS_B + T::COLS_B + T::ROWS_B;
-            for (int lr = warp; lr < nr; lr += NW) {
-                const int s = sr[lr] - b0, e = sr[lr + 1] - b0;
-                double acc = 0.0;
-                for (int blk0 = s; blk0 < e; blk0 += BPS * U) {
-                    double a[U];
-                    int col[U];
+            for (int task = warp; 2 * task < nr; task += NW) {
+                const int lr = 2 * task + half;
+                const bool row_on = lr < nr;
+                const int s = row_on ? sr[lr] - b0 : 0, e = row_on ? sr[lr + 1] - b0 : 0;
+                const int len_other = __shfl_xor_sync(0xffffffffu, e - s, 16);
+                const int len = max(e - s, len_other);                     // warp-uniform trip count
+                double acc[D];
+#pragma unroll
+                for (int r = 0; r < D; ++r) acc[r] = 0.0;
+                for (int off = 0; off < len; off += BPH * U) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int blk = blk0 + u * BPS + lb;
-                        const bool valid = lane_on && blk < e;
-                        a[u] = valid ? sv[blk * DD + wq] : 0.0;
-                        col[u] = valid ? sc[blk] : 0;
-                    }
+                        const int blk = s + off + u * BPH + lb;
+                        if (lane_on && blk < e) {
+                            const int col = sc[blk];
+                            const double xv = __ldg(x + (unsigned)(col * D + c));
+                            const double* ap = sv + blk * DD + c;
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int blk = blk0 + u * BPS + lb;
-                        const bool valid = lane_on && blk < e;
-                        const double xv = valid ? __ldg(x + (unsigned)(col[u] * D + c)) : 0.0;
-                        acc = fma(a[u], xv, acc);
+                            for (int r = 0; r < D; ++r) acc[r] = fma(ap[r * D], xv, acc[r]);
+                        }
                     }
                 }
-                double v;
-                if constexpr (D == 3) {
-                    const double t1 = __shfl_down_sync(0xffffffffu, acc, 9);
-                    const double t2 = __shfl_down_sync(0xffffffffu, acc, 18);
-                    v = acc + t1 + t2;
-                    const double u1 = __shfl_down_sync(0xffffffffu, v, 1);
-                    const double u2 = __shfl_down_sync(0xffffffffu, v, 2);
-                    v = v + u1 + u2;
-                } else {
-                    v = acc;
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_down_sync(0xffffffffu, v, 1);
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
                 }
-                if (lane < DD && c == 0) {
-                    const int r = lane / D;
-                    const int li = lr * D + r;
-                    const int64_t gi = (int64_t)(r0 + lr) * D + r;
+                if (row_on && hl < D) {
+                    double v = acc[0];
+#pragma unroll
+                    for (int r = 1; r < D; ++r) v = (hl == r) ? acc[r] : v;
+                    const int li = lr * D + hl;
+                    const int64_t gi = (int64_t)(r0 + lr) * D + hl;
                     if (MODE == 0) {
                         y[gi] = v;
                         if (DOTS >= 1) dot[0] += reinterpret_cast<const double*>(sa + meta[6])[li] * v;

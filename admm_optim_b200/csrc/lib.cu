@@ -289,9 +289,9 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
         case 3:   // TMA-staged tiles
         case 4:
             if (L.ntiles > 0) {
-                if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-                else if (ctx->spmv_variant == 3) spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-                else spmv_tma_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                else if (ctx->spmv_variant == 3) spmv_tma_launch<3, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+                else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
                 return;
             }
             if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
