@@ -281,23 +281,15 @@ static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
-    switch (ctx->spmv_variant) {   // tuning knob "spmv_variant"; 0 = default (warp per row, U = 3)
-        case 1:
-            if (dim == 2) spmv_warp_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_warp_launch<3, 6>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+    // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path,
+    // 2 = first-generation sub-warp row groups (kept for the comparisons in profiles/)
+    const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
+    switch (variant) {
+        case 0:
+            if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;
-        case 3:   // TMA-staged tiles
-        case 4:
-            if (L.ntiles > 0) {
-                if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-                else if (ctx->spmv_variant == 3) spmv_tma_launch<3, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-                else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-                return;
-            }
-            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            return;
-        case 2:   // sub-warp row groups with flattened entries (first-generation kernel, kept for comparison)
+        case 2:
             if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
             return;

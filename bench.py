@@ -249,7 +249,7 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         ach = bytes_spmv / t_spmv / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "k_bsr_spmv<3,16,0,0> (y = A x, BSR 3x3 fp64)", "peak_source": peak_src,
+                "kernel": "k_bsr_spmv_tma<3,0,0,3> (y = A x, BSR 3x3 fp64, TMA-staged tiles)", "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmv, "us_per_launch": t_spmv * 1e6,
                 "workload": "box_3D_elongated numRefs=%d: %d block rows, %d blocks (matrix %.2f GB > L2)" % (args.roofline_refs, nb, nnzb, nnzb * 76 / 1e9)}
         s = big.SmallProblemRHS_Solver
