@@ -41,14 +41,20 @@ PROTOTYPES = {
     "ab_context_set_tuning": [_P, _S, _I],
     "ab_context_init_comm": [_P, _I, _I, _P],
     "ab_nccl_unique_id": [_P],
+    "ab_context_allreduce_host": [_P, _DP, _I, _I],
     "ab_domain_load_ugx": [_P, _S, _PP],
     "ab_domain_create": [_P, _I, _I, _DP, _I, _I32P, _I, C.POINTER(_S), _I32P, _I32P, _I, _I32P, _I32P, _I, _I32P, _I32P, _PP],
     "ab_domain_destroy": [_P],
     "ab_domain_refine": [_P, _I],
+    "ab_domain_set_interface": [_P, _I, _I, _I32P, _I32P, _I32P, C.POINTER(C.c_ubyte)],
+    "ab_domain_set_global_coarse": [_P, _I, _I32P, _I32P],
     "ab_domain_num_levels": [_P, _IP],
     "ab_domain_level_info": [_P, _I, _IP, _IP, _IP, _IP, _IP],
     "ab_domain_get_level": [_P, _I, _DP, _I32P, _I32P, _I32P, _I32P],
     "ab_domain_subset_index": [_P, _S, _IP],
+    "ab_domain_subset_name": [_P, _I, C.c_char_p, _I],
+    "ab_domain_special_info": [_P, _I, _IP, _IP, _IP],
+    "ab_domain_get_special": [_P, _I, _I32P, _I32P, _I32P, _I32P, _I32P],
     "ab_transform_domain_by_displacement": [_P, _P],
     "ab_space_create": [_P, _I, _I, _PP],
     "ab_space_destroy": [_P],

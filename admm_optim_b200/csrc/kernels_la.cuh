@@ -103,6 +103,87 @@ __global__ void k_bicg_half_x(int64_t n, const double* __restrict__ sc, const do
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += alpha * ph[i];
 }
 
+// ---- distributed BiCGStab: residual-type vectors are kept in additive (_a) and consistent (_c) form ------
+// s = r - alpha v for both representations; reduce <s_c, s_a> (local part)
+__global__ void __launch_bounds__(256) k_bicg2_s(int64_t n, double* __restrict__ sc, const double* __restrict__ ra, const double* __restrict__ rc,
+                                                 const double* __restrict__ va, const double* __restrict__ vc, double* __restrict__ sa,
+                                                 double* __restrict__ scv, double* partials, unsigned int* ticket) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = ra[i] - alpha * va[i], c = rc[i] - alpha * vc[i];
+        sa[i] = a;
+        scv[i] = c;
+        acc[0] += a * c;
+    }
+    grid_reduce<1, 0>(acc, partials, ticket, sc + SC_SS);
+}
+// x += alpha ph + omega sh; r = s - omega t (both representations); reduce <r_c,r_a>, <rh,r_a> (local parts)
+__global__ void __launch_bounds__(256) k_bicg2_xr(int64_t n, double* __restrict__ sc, const double* __restrict__ ph, const double* __restrict__ sh,
+                                                  const double* __restrict__ sa, const double* __restrict__ scv, const double* __restrict__ ta,
+                                                  const double* __restrict__ tc, const double* __restrict__ rh, double* __restrict__ x,
+                                                  double* __restrict__ ra, double* __restrict__ rc, double* partials, unsigned int* ticket,
+                                                  double* out2) {
+    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    const double tt = sc[SC_TT];
+    const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] += alpha * ph[i] + omega * sh[i];
+        const double a = sa[i] - omega * ta[i], c = scv[i] - omega * tc[i];
+        ra[i] = a;
+        rc[i] = c;
+        acc[0] += a * c;
+        acc[1] += rh[i] * a;
+    }
+    grid_reduce<2, 0>(acc, partials, ticket, out2);
+}
+// point-Jacobi data, distributed: additive diagonal and additive absolute row sums (made consistent by an interface sum)
+template <int D>
+__global__ void k_diag_rowabs(int nb, const int* __restrict__ rowptr, const int* __restrict__ diagpos, const double* __restrict__ vals,
+                              double* __restrict__ diag, double* __restrict__ rowabs) {
+    constexpr int DD = D * D;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nb * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(t / D), r = (int)(t - (int64_t)row * D);
+        const int s = rowptr[row], e = rowptr[row + 1];
+        double sum = 0.0;
+        for (int k = s; k < e; ++k) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) sum += fabs(vals[(int64_t)k * DD + r * D + c]);
+        }
+        diag[t] = vals[(int64_t)diagpos[row] * DD + r * D + r];
+        rowabs[t] = sum;
+    }
+}
+__global__ void __launch_bounds__(256) k_dinv_lmax(int64_t n, double* __restrict__ diag_to_dinv, const double* __restrict__ rowabs,
+                                                   double* partials, unsigned int* ticket, double* red) {
+    double mx[1] = {0.0};
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const double aii = diag_to_dinv[t];
+        diag_to_dinv[t] = 1.0 / aii;
+        mx[0] = fmax(mx[0], rowabs[t] / aii);
+    }
+    grid_reduce<1, 1>(mx, partials, ticket, red);
+}
+// replicated coarse solve: local additive rhs -> global free-dof vector, dense GEMV, global -> local consistent solution
+__global__ void k_coarse_gather(int ndof, const int* __restrict__ dof2gfree, const double* __restrict__ b, double* __restrict__ bg) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ndof; t += gridDim.x * blockDim.x)
+        if (dof2gfree[t] >= 0) atomicAdd(bg + dof2gfree[t], b[t]);
+}
+__global__ void __launch_bounds__(256) k_dense_gemv(int n, const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        double acc = 0.0;
+        for (int c = lane; c < n; c += 32) acc += A[i * n + c] * b[c];
+        acc = warp_sum(acc);
+        if (lane == 0) x[i] = acc;
+    }
+}
+__global__ void k_coarse_scatter(int ndof, const int* __restrict__ dof2gfree, const double* __restrict__ xg, double* __restrict__ x) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ndof; t += gridDim.x * blockDim.x) x[t] = dof2gfree[t] >= 0 ? xg[dof2gfree[t]] : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // BSR SpMV family.  One group of LPR lanes per block row; the row's value array (len*D*D doubles,
 // contiguous) is streamed with unit-stride loads across the lanes, block-column indices are loaded

@@ -9,6 +9,7 @@
 #include <map>
 
 #include "../../include/admm_b200.h"
+#include "comm.cuh"
 #include "common.cuh"
 #include "kernels_fe.cuh"
 #include "kernels_la.cuh"
@@ -58,6 +59,13 @@ struct Domain {
     uint64_t coords_version = 1;
     bool host_xyz_stale = false;
     std::vector<std::weak_ptr<MatrixData>> live;   // assembled matrices, for signature sharing
+    // multi-GPU: shared-vertex interfaces per level (host staging until finalize) and the replicated level-0 numbering
+    struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
+    std::vector<HostIface> host_iface;
+    std::vector<Interface> iface;
+    int nv0_global = 0;
+    std::vector<int> l0_gid, vsub0_global;
+    bool distributed() const { return ctx && ctx->comm && ctx->comm->nranks > 1; }
     int dim() const { return mesh.dim; }
     int top() const { return (int)mesh.levels.size() - 1; }
     void finalize();
@@ -110,8 +118,53 @@ void Domain::finalize() {
         }
         if (l < nl - 1) { H.edges.clear(); H.edges.shrink_to_fit(); H.have_edges = false; }
     }
+    if (distributed()) {
+        AB_REQUIRE((int)host_iface.size() == nl, AB_ERR_STATE, "multi-GPU: ab_domain_set_interface must be called for every level before the first ApproximationSpace");
+        AB_REQUIRE((int)l0_gid.size() == mesh.levels[0].nv, AB_ERR_STATE, "multi-GPU: ab_domain_set_global_coarse missing");
+        iface.resize(nl);
+        for (int l = 0; l < nl; ++l) {
+            HostIface& H = host_iface[l];
+            Interface& I = iface[l];
+            AB_REQUIRE((int)H.owned.size() == mesh.levels[l].nv, AB_ERR_ARG, "interface: owned mask size mismatch");
+            I.neigh = H.neigh; I.offset = H.offset;
+            I.total = H.offset.empty() ? 0 : H.offset.back();
+            std::vector<int> iv(H.idx);
+            std::sort(iv.begin(), iv.end());
+            iv.erase(std::unique(iv.begin(), iv.end()), iv.end());
+            I.niv = (int)iv.size();
+            I.idx.upload(H.idx, ctx->stream);
+            I.iv.upload(iv, ctx->stream);
+            I.owned.upload(H.owned, ctx->stream);
+            const int maxc = mesh.dim;     // P1 vectors with dim components
+            I.send.alloc((size_t)std::max(I.total, 1) * maxc);
+            I.recv.alloc((size_t)std::max(I.total, 1) * maxc);
+            I.save.alloc((size_t)std::max(I.niv, 1) * 2 * maxc);
+        }
+    }
     AB_CUDA(cudaStreamSynchronize(ctx->stream));
     finalized = true;
+}
+
+// interface sum: additive -> consistent for a P1 vector with D components on `level`
+static void exchange_sum(Domain* dom, int level, double* v, int D) {
+    if (!dom->distributed()) return;
+    Context* ctx = dom->ctx;
+    Interface& I = dom->iface[level];
+    if (I.total == 0) return;
+    NcclApi& nc = NcclApi::get();
+    AB_LAUNCH(ctx, k_iface_pack, grid_for((int64_t)I.total * D, 256, ctx->num_sms * 4), 256, 0, I.total, D, I.idx.p, v, I.send.p);
+    AB_NCCL(nc.GroupStart());
+    for (size_t n = 0; n < I.neigh.size(); ++n) {
+        const size_t cnt = (size_t)(I.offset[n + 1] - I.offset[n]) * D;
+        AB_NCCL(nc.Send(I.send.p + (size_t)I.offset[n] * D, cnt, ncclFloat64, I.neigh[n], ctx->comm->comm, ctx->stream));
+        AB_NCCL(nc.Recv(I.recv.p + (size_t)I.offset[n] * D, cnt, ncclFloat64, I.neigh[n], ctx->comm->comm, ctx->stream));
+    }
+    AB_NCCL(nc.GroupEnd());
+    AB_LAUNCH(ctx, k_iface_unpack_add, grid_for((int64_t)I.total * D, 256, ctx->num_sms * 4), 256, 0, I.total, D, I.idx.p, I.recv.p, v);
+}
+// global sum / max of device scalars (no-op on one GPU)
+static void allreduce_dev(Context* ctx, double* d, int n, bool max_op = false) {
+    if (ctx->comm && ctx->comm->nranks > 1) ctx->comm->allreduce(d, n, max_op, ctx->stream);
 }
 
 struct Space {
@@ -320,7 +373,8 @@ struct Gmg {
     int n_free = 0, n0 = 0;
     DevBuf<double> Ainv, Mwork;
     DevBuf<int> free2dof, dof2free, pivrow, fail;
-    std::shared_ptr<MatrixData> keep_alive_unused;
+    DevBuf<int> dof2gfree;            // multi-GPU: local level-0 dof -> global free-dof index (-1: Dirichlet)
+    DevBuf<double> bg, xg;            // global coarse vectors (replicated solve)
     void setup(const std::shared_ptr<MatrixData>& A);
     void vcycle(int l, const double* b, double* x);
     void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef);
@@ -380,9 +434,18 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     for (int l = 1; l <= top; ++l) {
         const LevelDev& Ld = dom->dev[l];
         GmgLevel& g = G.L[l];
-        AB_LAUNCH(ctx, (k_diag_gershgorin<D>), red_grid(ctx, (int64_t)Ld.nv * D), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p,
-                  ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
+        const int64_t n = (int64_t)Ld.nv * D;
+        if (!dom->distributed()) {
+            AB_LAUNCH(ctx, (k_diag_gershgorin<D>), red_grid(ctx, n), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p,
+                      ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
+        } else {   // additive rows: diagonal and |row| sums are made consistent across the interfaces first
+            AB_LAUNCH(ctx, (k_diag_rowabs<D>), ew_grid(ctx, n), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p, g.r.p);
+            exchange_sum(dom, l, g.dinv.p, D);
+            exchange_sum(dom, l, g.r.p, D);
+            AB_LAUNCH(ctx, k_dinv_lmax, red_grid(ctx, n), 256, 0, n, g.dinv.p, g.r.p, ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
+        }
     }
+    if (top >= 1) allreduce_dev(ctx, ctx->d_results + 1, top, true);
     // dense inverse of level 0 (free dofs)
     {
         TraceTimer tt(ctx->stream, "gmg: dense inverse");
@@ -391,7 +454,9 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
         if (n > 0) {
             AB_CUDA(cudaMemsetAsync(G.Mwork.p, 0, (size_t)n * 2 * n * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, (k_bsr_to_dense<D>), grid_for(L0.nnzb * DD, 256, ctx->num_sms * 8), 256, 0, L0.nv, L0.rowptr.p, L0.colidx.p, G.L[0].vals,
-                      G.dof2free.p, n, G.Mwork.p);
+                      dom->distributed() ? G.dof2gfree.p : G.dof2free.p, n, G.Mwork.p);
+            // multi-GPU: the additive level-0 operators are summed into the replicated global coarse matrix
+            if (dom->distributed()) { AB_REQUIRE((int64_t)n * 2 * n < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "coarse matrix too large"); allreduce_dev(ctx, G.Mwork.p, n * 2 * n); }
             AB_LAUNCH(ctx, k_dense_identity, grid_for(n, 256, 64), 256, 0, n, G.Mwork.p);
             AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
             int nn = n;
@@ -433,6 +498,26 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
             for (int c = 0; c < dim; ++c)
                 if (!((m[v] >> c) & 1)) { d2f[(size_t)v * dim + c] = (int)f2d.size(); f2d.push_back(v * dim + c); }
         n_free = (int)f2d.size();
+        if (dom->distributed()) {   // replicated coarse solve on the GLOBAL level-0 mesh
+            const int nv0g = dom->nv0_global;
+            std::vector<unsigned char> mg((size_t)nv0g, 0);
+            if (A->dd)
+                for (auto& e : A->dd->dir)
+                    for (int v = 0; v < nv0g; ++v)
+                        if (dom->vsub0_global[v] == e.first) mg[v] |= (unsigned char)(1u << e.second);
+            std::vector<int> gfree((size_t)nv0g * dim, -1);
+            int cnt = 0;
+            for (int v = 0; v < nv0g; ++v)
+                for (int c = 0; c < dim; ++c)
+                    if (!((mg[v] >> c) & 1)) gfree[(size_t)v * dim + c] = cnt++;
+            std::vector<int> d2g((size_t)n0, -1);
+            for (int v = 0; v < H0.nv; ++v)
+                for (int c = 0; c < dim; ++c) d2g[(size_t)v * dim + c] = gfree[(size_t)dom->l0_gid[v] * dim + c];
+            n_free = cnt;
+            dof2gfree.upload(d2g, ctx->stream);
+            bg.alloc(std::max(cnt, 1));
+            xg.alloc(std::max(cnt, 1));
+        }
         free2dof.upload(f2d, ctx->stream);
         dof2free.upload(d2f, ctx->stream);
         if (n_free) { Ainv.alloc((size_t)n_free * n_free); Mwork.alloc((size_t)n_free * 2 * n_free); }
@@ -467,16 +552,32 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     double* bufs[2] = {x, g.x2.p};
     int cur;   // buffer holding the current iterate
     int k = 0;
+    const bool dist = dom->distributed() && dom->iface[l].niv > 0;
+    Interface* I = dist ? &dom->iface[l] : nullptr;
+    const int D = dom->dim();
     if (zero_guess) {
         cur = ((nu - 1) % 2 == 0) ? 0 : 1;
         AB_LAUNCH(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, g.d.p, bufs[cur]);
+        if (dist) {   // d = c2 D^-1 b is additive at the interfaces: sum it, then x = d there
+            AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, (const double*)nullptr, (const double*)nullptr, I->save.p);
+            exchange_sum(dom, l, g.d.p, D);
+            AB_LAUNCH(ctx, k_iface_fix, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, 0.0, I->save.p, g.d.p, bufs[cur]);
+        }
         k = 1;
     } else {
         cur = 0;   // caller guarantees: iterate is in x if nu even, in x2 if nu odd  (see vcycle)
         if (nu % 2 == 1) cur = 1;
     }
     for (; k < nu; ++k) {
+        // multi-GPU: the local step yields d_new = c1 d_old + c2 D^-1 r_local at shared vertices; the increment
+        // c2 D^-1 r_local is additive -> sum it over the interfaces and rebuild d, x there (comm.cuh)
+        if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
         spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, coef[k].first, coef[k].second);
+        if (dist) {
+            AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first, I->save.p, g.d.p);
+            exchange_sum(dom, l, g.d.p, D);
+            AB_LAUNCH(ctx, k_iface_fix, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first, I->save.p, g.d.p, bufs[1 - cur]);
+        }
         cur = 1 - cur;
     }
 }
@@ -487,7 +588,15 @@ void Gmg::vcycle(int l, const double* b, double* x) {
     if (l == 0) {
         const int n = n_free;
         const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
-        AB_LAUNCH(ctx, k_coarse_solve, grid, 256, 0, n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+        if (!dom->distributed()) {
+            AB_LAUNCH(ctx, k_coarse_solve, grid, 256, 0, n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+        } else {   // replicated solve of the global level-0 system (the reference keeps level 0 on one process, 3d_admm.lua:158-161)
+            AB_CUDA(cudaMemsetAsync(bg.p, 0, (size_t)n * sizeof(double), ctx->stream));
+            AB_LAUNCH(ctx, k_coarse_gather, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, b, bg.p);
+            allreduce_dev(ctx, bg.p, n);
+            AB_LAUNCH(ctx, k_dense_gemv, grid, 256, 0, n, Ainv.p, bg.p, xg.p);
+            AB_LAUNCH(ctx, k_coarse_scatter, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, xg.p, x);
+        }
         return;
     }
     const LevelDev& Ld = dom->dev[l];
@@ -519,6 +628,7 @@ struct Solver {
     std::shared_ptr<MatrixData> A;
     std::shared_ptr<Gmg> gmg;
     DevBuf<double> r, rh, p, v, s, t, ph, sh, sc, out2;
+    DevBuf<double> rc, vc, scons, tc;   // multi-GPU: consistent twins of the residual-type vectors
     int last_steps = 0;
     double last_defect = 0;
     void ensure_vectors();
@@ -529,6 +639,7 @@ void Solver::ensure_vectors() {
     if (sc.n == 0) { sc.alloc(SC_COUNT + 3); out2.alloc(2); }
     if (type == 1 && r.n == 0) {
         r.alloc(n); rh.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); t.alloc(n); ph.alloc(n); sh.alloc(n);
+        if (sp->dom->distributed()) { rc.alloc(n); vc.alloc(n); scons.alloc(n); tc.alloc(n); }
     }
     if (type == 2 && r.n == 0) { r.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); }
 }
@@ -607,6 +718,76 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     return ok;
 }
 
+// Multi-GPU BiCGStab: matrices and residual-type vectors are additive, iterates and preconditioned directions
+// consistent (the storage-type discipline UG4 exposes to the scripts, 3d_admm.lua:978-982).  Residual-type vectors
+// are carried in both forms so that every dot product is <consistent, additive>; one interface sum per SpMV.
+static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_defect) {
+    Domain* dom = S->sp->dom;
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim(), top = dom->top();
+    const LevelDev& Lt = dom->dev[top];
+    const int64_t n = S->sp->ndofs;
+    const double* Av = S->A->vals.p;
+    double* sc = S->sc.p;
+    const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
+    double h[SC_COUNT];
+    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);                       // r_a = b_a - A x_c
+    dev_copy(ctx, n, S->r.p, S->rc.p);
+    exchange_sum(dom, top, S->rc.p, dim);                                       // r_c
+    dev_copy(ctx, n, S->rc.p, S->rh.p);
+    {
+        const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        const double* xs[1] = {S->rc.p};
+        dev_dots(ctx, n, 1, xs, S->r.p, sc + SC_RR);
+        allreduce_dev(ctx, sc + SC_RR, 1);
+        AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    dev_fill(ctx, S->p.p, n, 0.0);
+    dev_fill(ctx, S->v.p, n, 0.0);
+    read_back(ctx, sc, SC_COUNT, h);
+    const double rr0 = h[SC_RR];
+    double rr = rr0;
+    bool ok = rr < tol2;
+    int it = 0;
+    const bool verbose = S->desc.verbose && ctx->comm->rank == 0;
+    if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
+    while (!ok && it < S->desc.max_iterations) {
+        ++it;
+        AB_LAUNCH(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
+        S->gmg->apply(S->p.p, S->ph.p);
+        spmv(ctx, dim, Lt, Av, 0, 1, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, S->rh.p, sc + SC_RV);
+        allreduce_dev(ctx, sc + SC_RV, 1);
+        dev_copy(ctx, n, S->v.p, S->vc.p);
+        exchange_sum(dom, top, S->vc.p, dim);
+        AB_LAUNCH(ctx, k_bicg2_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->rc.p, S->v.p, S->vc.p, S->s.p, S->scons.p, ctx->d_partials, ctx->d_tickets);
+        S->gmg->apply(S->s.p, S->sh.p);
+        spmv(ctx, dim, Lt, Av, 0, 1, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, S->scons.p, sc + SC_TS);
+        dev_copy(ctx, n, S->t.p, S->tc.p);
+        exchange_sum(dom, top, S->tc.p, dim);
+        {
+            const double* xs[1] = {S->tc.p};
+            dev_dots(ctx, n, 1, xs, S->t.p, sc + SC_TT);
+        }
+        allreduce_dev(ctx, sc + SC_TS, 2);
+        AB_LAUNCH(ctx, k_bicg2_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->scons.p, S->t.p, S->tc.p, S->rh.p, x->d.p, S->r.p,
+                  S->rc.p, ctx->d_partials, ctx->d_tickets, S->out2.p);
+        allreduce_dev(ctx, S->out2.p, 2);
+        AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
+        read_back(ctx, sc, SC_COUNT, h);
+        rr = h[SC_RR];
+        if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
+        if (!(rr == rr) || std::isinf(rr)) break;
+        if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
+        if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;
+    }
+    x->touch();
+    S->last_steps = it;
+    S->last_defect = std::sqrt(std::max(rr, 0.0));
+    if (return_defect) { dev_copy(ctx, n, S->r.p, b->d.p); b->storage = AB_PST_ADDITIVE; b->touch(); }
+    return ok;
+}
+
 static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect) {
     Context* ctx = S->sp->dom->ctx;
     const int64_t n = S->sp->ndofs;
@@ -616,6 +797,7 @@ static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect)
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
     AB_LAUNCH(ctx, k_cg_init, red_grid(ctx, n), 256, 0, n, S->damp, diag, b->d.p, x->d.p, r, z, p, ctx->d_partials, ctx->d_tickets, S->out2.p);
+    allreduce_dev(ctx, S->out2.p, 2);      // P0 dofs are element-local: plain sums over ranks
     AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
     read_back(ctx, sc, SC_COUNT, h);
     double rr = h[SC_RR];
@@ -626,7 +808,9 @@ static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect)
     while (!ok && it < S->desc.max_iterations) {
         ++it;
         AB_LAUNCH(ctx, k_diag_apply_dot, red_grid(ctx, n), 256, 0, n, diag, p, q, ctx->d_partials, ctx->d_tickets, sc + SC_PQ);
+        allreduce_dev(ctx, sc + SC_PQ, 1);
         AB_LAUNCH(ctx, k_cg_step, red_grid(ctx, n), 256, 0, n, S->damp, sc, diag, p, q, x->d.p, r, z, ctx->d_partials, ctx->d_tickets, S->out2.p);
+        allreduce_dev(ctx, S->out2.p, 2);
         AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
         AB_LAUNCH(ctx, k_cg_p, ew_grid(ctx, n), 256, 0, n, sc, z, p);
         read_back(ctx, sc, SC_COUNT, h);
@@ -883,14 +1067,36 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }
-int ab_context_init_comm(ab_context*, int, int nranks, const void*) {
+int ab_context_init_comm(ab_context* ctx, int rank, int nranks, const void* nccl_unique_id) {
     AB_TRY
-    AB_REQUIRE(nranks == 1, AB_ERR_UNSUPPORTED, "multi-GPU communicator not built in this revision");
+    AB_REQUIRE(ctx && nranks >= 1 && rank >= 0 && rank < nranks, AB_ERR_ARG, "bad rank / nranks");
+    if (nranks == 1) return AB_OK;
+    AB_REQUIRE(nccl_unique_id, AB_ERR_ARG, "nccl_unique_id is NULL");
+    auto c = std::make_shared<Comm>();
+    c->rank = rank; c->nranks = nranks;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    AB_CUDA(cudaSetDevice(ctx->device));
+    AB_NCCL(NcclApi::get().CommInitRank(&c->comm, nranks, id, rank));
+    ctx->comm = c;
     AB_CATCH
 }
-int ab_nccl_unique_id(void*) {
+int ab_nccl_unique_id(void* out128) {
     AB_TRY
-    AB_REQUIRE(false, AB_ERR_UNSUPPORTED, "multi-GPU communicator not built in this revision");
+    AB_REQUIRE(out128, AB_ERR_ARG, "NULL argument");
+    ncclUniqueId id;
+    AB_NCCL(NcclApi::get().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    AB_CATCH
+}
+int ab_context_allreduce_host(ab_context* ctx, double* v, int n, int max_op) {
+    AB_TRY
+    if (ctx->comm && ctx->comm->nranks > 1) {
+        AB_REQUIRE(n <= Context::kResultSlots, AB_ERR_ARG, "too many values");
+        AB_CUDA(cudaMemcpyAsync(ctx->d_results, v, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->comm->allreduce(ctx->d_results, n, max_op != 0, ctx->stream);
+        read_back(ctx, ctx->d_results, n, v);
+    }
     AB_CATCH
 }
 
@@ -948,6 +1154,31 @@ int ab_domain_refine(ab_domain* dom, int num_refs) {
     }
     AB_CATCH
 }
+int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets, const int32_t* idx,
+                            const unsigned char* owned) {
+    AB_TRY
+    AB_REQUIRE(dom && !dom->finalized, AB_ERR_STATE, "interfaces must be set before the first ApproximationSpace");
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    if (dom->host_iface.size() < dom->mesh.levels.size()) dom->host_iface.resize(dom->mesh.levels.size());
+    Domain::HostIface& H = dom->host_iface[level];
+    H.neigh.assign(neigh_ranks, neigh_ranks + nneigh);
+    H.offset.assign(offsets, offsets + nneigh + 1);
+    H.idx.assign(idx, idx + (nneigh ? offsets[nneigh] : 0));
+    const int nv = dom->mesh.levels[level].nv;
+    H.owned.assign(owned, owned + nv);
+    for (int v : H.idx) AB_REQUIRE(v >= 0 && v < nv, AB_ERR_ARG, "interface vertex index out of range");
+    AB_CATCH
+}
+int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l0_gid, const int32_t* vsub0_global) {
+    AB_TRY
+    AB_REQUIRE(dom && !dom->finalized, AB_ERR_STATE, "must be set before the first ApproximationSpace");
+    const int nv0 = dom->mesh.levels[0].nv;
+    dom->nv0_global = nv0_global;
+    dom->l0_gid.assign(l0_gid, l0_gid + nv0);
+    dom->vsub0_global.assign(vsub0_global, vsub0_global + nv0_global);
+    for (int g : dom->l0_gid) AB_REQUIRE(g >= 0 && g < nv0_global, AB_ERR_ARG, "global vertex id out of range");
+    AB_CATCH
+}
 int ab_domain_num_levels(ab_domain* dom, int* out) {
     AB_TRY
     *out = (int)dom->mesh.levels.size();
@@ -987,6 +1218,32 @@ int ab_domain_get_level(ab_domain* dom, int level, double* xyz, int32_t* elems, 
     if (vsub) memcpy(vsub, L.vsub.data(), L.vsub.size() * sizeof(int32_t));
     if (parent_a && !L.pa.empty()) memcpy(parent_a, L.pa.data(), L.pa.size() * sizeof(int32_t));
     if (parent_b && !L.pb.empty()) memcpy(parent_b, L.pb.data(), L.pb.size() * sizeof(int32_t));
+    AB_CATCH
+}
+int ab_domain_special_info(ab_domain* dom, int level, int* n_sp_edges, int* n_sp_faces, int* nsubsets) {
+    AB_TRY
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    const HostLevel& L = dom->mesh.levels[level];
+    if (n_sp_edges) *n_sp_edges = (int)L.sp_edges_sub.size();
+    if (n_sp_faces) *n_sp_faces = (int)L.sp_faces_sub.size();
+    if (nsubsets) *nsubsets = (int)dom->mesh.subset_names.size();
+    AB_CATCH
+}
+int ab_domain_get_special(ab_domain* dom, int level, int32_t* sp_edges, int32_t* sp_edges_sub, int32_t* sp_faces, int32_t* sp_faces_sub, int32_t* esub) {
+    AB_TRY
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    const HostLevel& L = dom->mesh.levels[level];
+    if (sp_edges && !L.sp_edges.empty()) memcpy(sp_edges, L.sp_edges.data(), L.sp_edges.size() * sizeof(int32_t));
+    if (sp_edges_sub && !L.sp_edges_sub.empty()) memcpy(sp_edges_sub, L.sp_edges_sub.data(), L.sp_edges_sub.size() * sizeof(int32_t));
+    if (sp_faces && !L.sp_faces.empty()) memcpy(sp_faces, L.sp_faces.data(), L.sp_faces.size() * sizeof(int32_t));
+    if (sp_faces_sub && !L.sp_faces_sub.empty()) memcpy(sp_faces_sub, L.sp_faces_sub.data(), L.sp_faces_sub.size() * sizeof(int32_t));
+    if (esub) memcpy(esub, L.esub.data(), L.esub.size() * sizeof(int32_t));
+    AB_CATCH
+}
+int ab_domain_subset_name(ab_domain* dom, int index, char* buf, int buflen) {
+    AB_TRY
+    AB_REQUIRE(index >= 0 && index < (int)dom->mesh.subset_names.size() && buf && buflen > 0, AB_ERR_ARG, "subset index out of range");
+    snprintf(buf, buflen, "%s", dom->mesh.subset_names[index].c_str());
     AB_CATCH
 }
 int ab_domain_subset_index(ab_domain* dom, const char* name, int* out) {
@@ -1089,7 +1346,17 @@ int ab_vector_storage(ab_vector* v, int* out) {
 }
 int ab_vector_change_storage(ab_vector* v, int storage) {
     AB_TRY
-    // single-GPU: additive, consistent and unique representations coincide; only the flag changes.
+    // single GPU: additive, consistent and unique representations coincide; only the flag changes.
+    // multi-GPU (P1): additive -> consistent is the interface sum; consistent -> additive/unique keeps the owner's copy.
+    Domain* dom = v->sp->dom;
+    if (dom->distributed() && v->sp->kind == AB_SPACE_P1 && storage != v->storage) {
+        AB_REQUIRE(v->sp->ncomp == dom->dim(), AB_ERR_UNSUPPORTED, "storage conversion: P1 spaces with ncomp != dim");
+        const int top = dom->top();
+        if ((v->storage & AB_PST_ADDITIVE) && (storage & AB_PST_CONSISTENT)) exchange_sum(dom, top, v->d.p, v->sp->ncomp);
+        else if ((v->storage & AB_PST_CONSISTENT) && !(storage & AB_PST_CONSISTENT))
+            AB_LAUNCH(dom->ctx, k_zero_not_owned, ew_grid(dom->ctx, v->n()), 256, 0, v->n(), v->sp->ncomp, dom->iface[top].owned.p, v->d.p);
+        v->touch();
+    }
     v->storage = storage;
     AB_CATCH
 }
@@ -1114,10 +1381,41 @@ int ab_vec_scale_add2(ab_vector* dst, double a, ab_vector* x, double b, ab_vecto
 int ab_vec_prod_multi(int n, ab_vector* const* xs, ab_vector* y, double* out) {
     AB_TRY
     AB_REQUIRE(n >= 1 && n <= 4, AB_ERR_ARG, "ab_vec_prod_multi: n must be 1..4");
-    Context* ctx = y->sp->dom->ctx;
+    Domain* dom = y->sp->dom;
+    Context* ctx = dom->ctx;
     const double* p[4];
     for (int i = 0; i < n; ++i) { AB_REQUIRE(xs[i]->n() == y->n(), AB_ERR_ARG, "VecProd: size mismatch"); p[i] = xs[i]->d.p; }
-    dev_dots(ctx, y->n(), n, p, y->d.p, ctx->d_results);
+    if (!dom->distributed() || y->sp->kind == AB_SPACE_P0) {
+        dev_dots(ctx, y->n(), n, p, y->d.p, ctx->d_results);
+    } else {
+        // <additive, consistent> is the plain local sum (3d_admm.lua:991-992); <consistent, consistent> counts every
+        // shared vertex once (owner mask); <additive, additive> first makes a consistent copy of y
+        const int top = dom->top(), D = y->sp->ncomp;
+        const bool y_add = (y->storage & AB_PST_ADDITIVE) != 0;
+        const double* ycons = nullptr;
+        DevBuf<double> tmp;
+        for (int i = 0; i < n; ++i) {
+            const bool x_add = (xs[i]->storage & AB_PST_ADDITIVE) != 0;
+            if (x_add != y_add) {
+                const double* one[1] = {p[i]};
+                dev_dots(ctx, y->n(), 1, one, y->d.p, ctx->d_results + i);
+            } else if (!x_add) {
+                AB_LAUNCH(ctx, (k_dot_owned<1>), red_grid(ctx, y->n()), 256, 0, y->n(), D, dom->iface[top].owned.p, p[i], p[i], y->d.p, ctx->d_partials,
+                          ctx->d_tickets, ctx->d_results + i);
+            } else {
+                if (!ycons) {
+                    tmp.alloc((size_t)y->n());
+                    dev_copy(ctx, y->n(), y->d.p, tmp.p);
+                    exchange_sum(dom, top, tmp.p, D);
+                    ycons = tmp.p;
+                }
+                const double* one[1] = {p[i]};
+                dev_dots(ctx, y->n(), 1, one, ycons, ctx->d_results + i);
+            }
+        }
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));   // tmp is released below
+    }
+    allreduce_dev(ctx, ctx->d_results, n);
     read_back(ctx, ctx->d_results, n, out);
     AB_CATCH
 }
@@ -1139,17 +1437,26 @@ int ab_l2norm_all(ab_vector* v, double* out) {
     const int dim = dom->dim();
     const int g = red_grid(ctx, L.ne);
     int nc;
+    DevBuf<double> tmp;
     if (v->sp->kind == AB_SPACE_P1) {
         AB_REQUIRE(v->sp->ncomp == dim, AB_ERR_UNSUPPORTED, "L2Norm: P1 spaces with ncomp != dim are not supported");
         nc = dim;
-        if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p1<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
-        else AB_LAUNCH(ctx, (k_l2norm_p1<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+        const double* vp = v->d.p;
+        if (dom->distributed() && (v->storage & AB_PST_ADDITIVE)) {   // the FE function is the consistent representation
+            tmp.alloc((size_t)v->n());
+            dev_copy(ctx, v->n(), v->d.p, tmp.p);
+            exchange_sum(dom, dom->top(), tmp.p, dim);
+            vp = tmp.p;
+        }
+        if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p1<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, vp, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+        else AB_LAUNCH(ctx, (k_l2norm_p1<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, vp, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     } else {
         AB_REQUIRE(v->sp->ncomp == dim * dim, AB_ERR_UNSUPPORTED, "L2Norm: P0 spaces with ncomp != dim*dim are not supported");
         nc = dim * dim;
         if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p0<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
         else AB_LAUNCH(ctx, (k_l2norm_p0<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     }
+    allreduce_dev(ctx, ctx->d_results, nc);
     read_back(ctx, ctx->d_results, nc, out);
     for (int i = 0; i < nc; ++i) out[i] = std::sqrt(out[i]);
     AB_CATCH
@@ -1358,7 +1665,8 @@ static int solver_apply_impl(ab_solver* s, ab_vector* x, ab_vector* b, int* conv
     AB_TRY
     AB_REQUIRE(s->A, AB_ERR_STATE, "solver:apply before solver:init");
     AB_REQUIRE(x->n() == s->sp->ndofs && b->n() == s->sp->ndofs, AB_ERR_ARG, "solver:apply: vector size mismatch");
-    const bool ok = s->type == 1 ? bicgstab_apply(s, x, b, ret_def) : cg_jacobi_apply(s, x, b, ret_def);
+    const bool ok = s->type == 1 ? (s->sp->dom->distributed() ? bicgstab_apply_dist(s, x, b, ret_def) : bicgstab_apply(s, x, b, ret_def))
+                                 : cg_jacobi_apply(s, x, b, ret_def);
     x->storage = AB_PST_CONSISTENT;
     if (converged) *converged = ok ? 1 : 0;
     AB_CHECK_LAUNCH(s->sp->dom->ctx);
@@ -1428,6 +1736,7 @@ static int max_norm_impl(ab_vector* u, double* out, bool spectral) {
         AB_REQUIRE(!spectral, AB_ERR_UNSUPPORTED, "MaxSpectralNorm exists for 2D only (2d_admm.lua:901)");
         AB_LAUNCH(ctx, (k_max_grad_norm<3, 0>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     }
+    allreduce_dev(ctx, ctx->d_results, 1, true);
     read_back(ctx, ctx->d_results, 1, out);
     AB_CATCH
 }
@@ -1443,6 +1752,7 @@ static int vol_bary_impl(ab_vector* u, double* out4) {
     const int g = red_grid(ctx, L.ne);
     if (dom->dim() == 2) AB_LAUNCH(ctx, (k_volume_barycenter<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     else AB_LAUNCH(ctx, (k_volume_barycenter<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
+    allreduce_dev(ctx, ctx->d_results, dom->dim() + 1);
     read_back(ctx, ctx->d_results, dom->dim() + 1, out4);
     AB_CATCH
 }

@@ -1,0 +1,130 @@
+"""Host-side domain decomposition for the multi-GPU path (one process per GPU).
+
+Replaces, for the hot path, UG4's ParMETIS partitioning + hierarchical distribution (3d_admm.lua:124-186):
+the level-0 elements are split by recursive coordinate bisection, every rank keeps the sub-grid of its own
+elements and refines it locally (children inherit the parent's rank, `clusteredSiblings`, 3d_admm.lua:147), so
+each rank owns a complete nested hierarchy of its subdomain.  Vertices shared between ranks are found per
+level by exact coordinate matching of candidate lists (both sides run the same refinement arithmetic, so
+shared vertices have bit-identical coordinates); the matched lists are sorted lexicographically, which gives
+both sides the same canonical order without any further negotiation.
+
+Pure NumPy + a tiny `gather` callable (torch.distributed.all_gather_object in production, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def rcb_partition(centroids: np.ndarray, nparts: int) -> np.ndarray:
+    """Recursive coordinate bisection along the longest extent; parts are proportional for any nparts >= 1."""
+    part = np.zeros(len(centroids), np.int32)
+
+    def rec(idx, first, count):
+        if count == 1 or len(idx) == 0:
+            part[idx] = first
+            return
+        left = count // 2
+        ext = centroids[idx].max(axis=0) - centroids[idx].min(axis=0)
+        ax = int(np.argmax(ext))
+        order = idx[np.lexsort((idx, centroids[idx, ax]))]          # ties broken by element id: deterministic
+        k = (len(idx) * left) // count
+        rec(order[:k], first, left)
+        rec(order[k:], first + left, count - left)
+
+    rec(np.arange(len(centroids)), 0, nparts)
+    return part
+
+
+def vertex_rank_masks(elems: np.ndarray, part: np.ndarray, nv: int) -> np.ndarray:
+    """uint64 bitmask per vertex: bit q set <=> some element of rank q contains the vertex (nparts <= 64)."""
+    mask = np.zeros(nv, np.uint64)
+    bits = (np.uint64(1) << part.astype(np.uint64))
+    for a in range(elems.shape[1]):
+        np.bitwise_or.at(mask, elems[:, a], bits)
+    return mask
+
+
+_LOCAL_EDGES = {2: [(0, 1), (1, 2), (0, 2)], 3: [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]}
+_LOCAL_FACES = [(0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)]
+
+
+def _rows_in(rows, table, nv):
+    """boolean mask: which rows (sorted tuples) occur in table (sorted tuples)."""
+    if len(rows) == 0:
+        return np.zeros(0, bool)
+    def key(a):
+        k = a[:, 0].astype(np.int64)
+        for c in range(1, a.shape[1]):
+            k = k * nv + a[:, c]
+        return k
+    return np.isin(key(rows), key(table))
+
+
+def extract_submesh(g: dict, part: np.ndarray, rank: int) -> dict:
+    """Sub-grid of the elements owned by `rank` (local vertex numbering keeps the global order).
+    `g`: dim, xyz, elems, vsub, esub, sp_edges(+_sub), sp_faces(+_sub) of the global level-0 grid."""
+    dim = int(g["dim"])
+    mine = np.flatnonzero(part == rank)
+    elems_g = g["elems"][mine]
+    l2g = np.unique(elems_g)
+    g2l = -np.ones(len(g["xyz"]), np.int64)
+    g2l[l2g] = np.arange(len(l2g))
+    elems = g2l[elems_g].astype(np.int32)
+    nv = len(g["xyz"])
+    # boundary-subset edges / faces that are edges / faces of a local element
+    le = np.concatenate([np.sort(np.stack([elems_g[:, i], elems_g[:, j]], 1), axis=1) for i, j in _LOCAL_EDGES[dim]])
+    se, ses = g["sp_edges"], g["sp_edges_sub"]
+    keep = _rows_in(se, le, nv)
+    sp_edges, sp_edges_sub = g2l[se[keep]].astype(np.int32), ses[keep].astype(np.int32)
+    if dim == 3 and len(g["sp_faces"]):
+        lf = np.concatenate([np.sort(np.stack([elems_g[:, i], elems_g[:, j], elems_g[:, k]], 1), axis=1) for i, j, k in _LOCAL_FACES])
+        sf, sfs = g["sp_faces"], g["sp_faces_sub"]
+        keepf = _rows_in(sf, lf, nv)
+        sp_faces, sp_faces_sub = g2l[sf[keepf]].astype(np.int32), sfs[keepf].astype(np.int32)
+    else:
+        sp_faces, sp_faces_sub = np.zeros((0, 3), np.int32), np.zeros(0, np.int32)
+    return dict(dim=dim, xyz=np.ascontiguousarray(g["xyz"][l2g]), elems=np.ascontiguousarray(elems), vsub=g["vsub"][l2g].astype(np.int32),
+                esub=g["esub"][mine].astype(np.int32), sp_edges=np.ascontiguousarray(sp_edges).reshape(-1, 2), sp_edges_sub=sp_edges_sub,
+                sp_faces=np.ascontiguousarray(sp_faces).reshape(-1, 3), sp_faces_sub=sp_faces_sub, l2g=l2g.astype(np.int32))
+
+
+def refine_masks(mask_coarse: np.ndarray, parent_a: np.ndarray, parent_b: np.ndarray) -> np.ndarray:
+    """Candidate sharing masks of the next level: copies keep theirs, a midpoint can only be shared with ranks that
+    share both parents (a superset of the truth; the coordinate matching removes the false positives)."""
+    return np.concatenate([mask_coarse, mask_coarse[parent_a] & mask_coarse[parent_b]])
+
+
+def _void_rows(x):
+    x = np.ascontiguousarray(x)
+    return x.view([("", x.dtype)] * x.shape[1]).ravel()
+
+
+def match_level(xyz: np.ndarray, mask: np.ndarray, rank: int, nranks: int, gather):
+    """Interfaces of one level. `gather(obj)` returns the list of every rank's obj (all_gather_object).
+    Returns (neigh, offsets, idx, owned)."""
+    cand = {}
+    for q in range(nranks):
+        if q == rank:
+            continue
+        c = np.flatnonzero(mask & (np.uint64(1) << np.uint64(q)))
+        if len(c):
+            cand[q] = c
+    everyone = gather({q: xyz[c] for q, c in cand.items()})
+    neigh, offsets, idx = [], [0], []
+    owned = np.ones(len(xyz), np.uint8)
+    for q in sorted(cand):
+        theirs = everyone[q].get(rank)
+        if theirs is None or len(theirs) == 0:
+            continue
+        mine = xyz[cand[q]]
+        _, ia, _ = np.intersect1d(_void_rows(mine), _void_rows(theirs), return_indices=True)   # sorted by coordinates
+        if len(ia) == 0:
+            continue
+        loc = cand[q][ia].astype(np.int32)
+        neigh.append(q)
+        idx.append(loc)
+        offsets.append(offsets[-1] + len(loc))
+        if q < rank:
+            owned[loc] = 0
+    idx = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32)
+    return np.array(neigh, np.int32), np.array(offsets, np.int32), idx, owned

@@ -77,16 +77,35 @@ class Domain(_Handle):
         call("ab_domain_level_info", self.h, level, *[C.byref(x) for x in v])
         return dict(dim=v[0].value, nv=v[1].value, ne=v[2].value, nedges=v[3].value, nv_coarse=v[4].value)
 
-    def get_level(self, level):
+    def get_level(self, level, elems=True):
         i = self.level_info(level)
         d, nv, ne, nvc = i["dim"], i["nv"], i["ne"], i["nv_coarse"]
         xyz = np.empty((nv, d))
-        elems = np.empty((ne, d + 1), np.int32)
+        el = np.empty((ne, d + 1), np.int32) if elems else None
         vsub = np.empty(nv, np.int32)
         pa = np.empty(max(nv - nvc, 0) if level > 0 else 0, np.int32)
         pb = np.empty_like(pa)
-        call("ab_domain_get_level", self.h, level, _dp(xyz), _ip(elems), _ip(vsub), _ip(pa) if len(pa) else None, _ip(pb) if len(pb) else None)
-        return dict(xyz=xyz, elems=elems, vsub=vsub, parent_a=pa, parent_b=pb, nv_coarse=nvc)
+        call("ab_domain_get_level", self.h, level, _dp(xyz), _ip(el) if elems else None, _ip(vsub), _ip(pa) if len(pa) else None,
+             _ip(pb) if len(pb) else None)
+        return dict(xyz=xyz, elems=el, vsub=vsub, parent_a=pa, parent_b=pb, nv_coarse=nvc)
+
+    def get_grid_dict(self, level=0):
+        """Level arrays in the layout of the .npz fixtures (used to re-create a partition of a loaded grid)."""
+        lv = self.get_level(level)
+        nse, nsf, nsub = C.c_int(), C.c_int(), C.c_int()
+        call("ab_domain_special_info", self.h, level, C.byref(nse), C.byref(nsf), C.byref(nsub))
+        se, ses = np.empty((nse.value, 2), np.int32), np.empty(nse.value, np.int32)
+        sf, sfs = np.empty((nsf.value, 3), np.int32), np.empty(nsf.value, np.int32)
+        esub = np.empty(len(lv["elems"]), np.int32)
+        call("ab_domain_get_special", self.h, level, _ip(se) if nse.value else None, _ip(ses) if nse.value else None,
+             _ip(sf) if nsf.value else None, _ip(sfs) if nsf.value else None, _ip(esub))
+        names = []
+        for i in range(nsub.value):
+            buf = C.create_string_buffer(256)
+            call("ab_domain_subset_name", self.h, i, buf, 256)
+            names.append(buf.value.decode())
+        return dict(dim=self.level_info(level)["dim"], xyz=lv["xyz"], elems=lv["elems"], vsub=lv["vsub"], esub=esub, sp_edges=se,
+                    sp_edges_sub=ses, sp_faces=sf, sp_faces_sub=sfs, subset_names=names)
 
     def subset_index(self, name):
         out = C.c_int()
@@ -487,12 +506,35 @@ class Backend:
     """The Lua global namespace of a ugshell session, GPU edition."""
     name = "b200"
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, distributed=False):
+        """distributed=True: one process per GPU; torch.distributed must be initialised (any backend -- it is used only
+        for the host-side bootstrap: the NCCL id and the interface matching); the data path uses the library's own
+        NCCL communicator on `stream`."""
         self.lib = _lib.load()
         self.ctx = C.c_void_p()
         if stream is None:
             stream = 0
         call("ab_context_create", int(device), C.c_void_p(stream), C.byref(self.ctx))
+        self.rank, self.nranks, self._gather = 0, 1, None
+        if distributed:
+            import torch.distributed as dist
+            self.rank, self.nranks = dist.get_rank(), dist.get_world_size()
+            if self.nranks > 1:
+                if self.nranks > 64:
+                    raise AdmmB200Error("at most 64 ranks (one node: 8)")
+                uid = (C.c_ubyte * 128)()
+                if self.rank == 0:
+                    call("ab_nccl_unique_id", uid)
+                box = [bytes(uid)]
+                dist.broadcast_object_list(box, src=0)
+                uid = (C.c_ubyte * 128).from_buffer_copy(box[0])
+                call("ab_context_init_comm", self.ctx, self.rank, self.nranks, uid)
+
+                def gather(obj):
+                    out = [None] * self.nranks
+                    dist.all_gather_object(out, obj)
+                    return out
+                self._gather = gather
         self.dim = None
         self.util = _Namespace()
         self.util.refinement = _Namespace()
@@ -532,32 +574,75 @@ class Backend:
 
     def LoadDomain(self, dom, grid_name):
         """LoadDomain(dom, gridName)  3d_admm.lua:109. `.ugx` is parsed natively; `.npz` is the converted
-        fixture format of tools/convert_ugx.py (same content, travels to machines without the reference tree)."""
-        if grid_name.endswith(".npz"):
-            z = np.load(grid_name)
-            names = [str(s) for s in z["subset_names"]]
-            arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
-            xyz = np.ascontiguousarray(z["xyz"], np.float64)
-            elems = np.ascontiguousarray(z["elems"], np.int32)
-            vsub = np.ascontiguousarray(z["vsub"], np.int32)
-            esub = np.ascontiguousarray(z["esub"], np.int32)
-            se = np.ascontiguousarray(z["sp_edges"], np.int32)
-            ses = np.ascontiguousarray(z["sp_edges_sub"], np.int32)
-            sf = np.ascontiguousarray(z["sp_faces"], np.int32)
-            sfs = np.ascontiguousarray(z["sp_faces_sub"], np.int32)
-            call("ab_domain_create", self.ctx, int(z["dim"]), xyz.shape[0], _dp(xyz), elems.shape[0], _ip(elems), len(names), arr,
-                 _ip(vsub), _ip(esub), len(ses), _ip(se) if len(ses) else None, _ip(ses) if len(ses) else None,
-                 len(sfs), _ip(sf) if len(sfs) else None, _ip(sfs) if len(sfs) else None, C.byref(dom.h))
-            dom.subset_names = names
+        fixture format of tools/convert_ugx.py (same content, travels to machines without the reference tree).
+        Multi-GPU: the grid is partitioned here (level-0 elements, RCB) and this rank keeps its own sub-grid."""
+        if self.nranks > 1:
+            g = self._read_global_grid(grid_name)
+            from . import partition as P
+            cent = g["xyz"][g["elems"]].mean(axis=1)
+            part = P.rcb_partition(cent, self.nranks)
+            sub = P.extract_submesh(g, part, self.rank)
+            if len(sub["elems"]) == 0:
+                raise AdmmB200Error("rank %d received no elements" % self.rank)
+            self._create_from_dict(dom, dict(sub, subset_names=g["subset_names"]))
+            dom._dist = dict(l2g=sub["l2g"], mask0=P.vertex_rank_masks(g["elems"], part, len(g["xyz"]))[sub["l2g"]],
+                             vsub_global=np.ascontiguousarray(g["vsub"], np.int32), nv0_global=len(g["xyz"]), part=part)
+        elif grid_name.endswith(".npz"):
+            self._create_from_dict(dom, self._read_global_grid(grid_name))
         else:
             call("ab_domain_load_ugx", self.ctx, grid_name.encode(), C.byref(dom.h))
         dom._loaded()
-        if self.dim is not None and dom.dim != self.dim:
+        if self.dim is None:
+            self.dim = dom.dim
+        if dom.dim != self.dim:
             raise AdmmB200Error("grid dimension %d does not match InitUG(%d)" % (dom.dim, self.dim))
 
+    def _read_global_grid(self, grid_name):
+        if grid_name.endswith(".npz"):
+            z = np.load(grid_name)
+            g = {k: z[k] for k in ("xyz", "elems", "vsub", "esub", "sp_edges", "sp_edges_sub", "sp_faces", "sp_faces_sub")}
+            g["dim"] = int(z["dim"])
+            g["subset_names"] = [str(x) for x in z["subset_names"]]
+            return g
+        tmp = Domain(self)                                   # host-only parse of the .ugx
+        call("ab_domain_load_ugx", None, grid_name.encode(), C.byref(tmp.h))
+        return tmp.get_grid_dict(0)
+
+    def _create_from_dict(self, dom, g):
+        names = list(g["subset_names"])
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        xyz = np.ascontiguousarray(g["xyz"], np.float64)
+        elems = np.ascontiguousarray(g["elems"], np.int32)
+        vsub = np.ascontiguousarray(g["vsub"], np.int32)
+        esub = np.ascontiguousarray(g["esub"], np.int32)
+        se = np.ascontiguousarray(g["sp_edges"], np.int32)
+        ses = np.ascontiguousarray(g["sp_edges_sub"], np.int32)
+        sf = np.ascontiguousarray(g["sp_faces"], np.int32)
+        sfs = np.ascontiguousarray(g["sp_faces_sub"], np.int32)
+        call("ab_domain_create", self.ctx, int(g["dim"]), xyz.shape[0], _dp(xyz), elems.shape[0], _ip(elems), len(names), arr,
+             _ip(vsub), _ip(esub), len(ses), _ip(se) if len(ses) else None, _ip(ses) if len(ses) else None,
+             len(sfs), _ip(sf) if len(sfs) else None, _ip(sfs) if len(sfs) else None, C.byref(dom.h))
+        dom.subset_names = names
+
     def _create_regular_hierarchy(self, dom, num_refs, verbose=False, balancer_desc=None):
-        """util.refinement.CreateRegularHierarchy(dom, numRefs, false, balancerDesc)  3d_admm.lua:186"""
+        """util.refinement.CreateRegularHierarchy(dom, numRefs, false, balancerDesc)  3d_admm.lua:186.
+        Multi-GPU: every rank refines its own sub-grid; the shared-vertex interfaces of all levels are then matched."""
         call("ab_domain_refine", dom.h, int(num_refs))
+        if self.nranks > 1:
+            from . import partition as P
+            info = dom._dist
+            mask = info["mask0"]
+            dom._iface = []
+            for level in range(dom.num_levels()):
+                lv = dom.get_level(level, elems=False)
+                if level > 0:
+                    mask = P.refine_masks(mask, lv["parent_a"], lv["parent_b"])
+                neigh, offsets, idx, owned = P.match_level(lv["xyz"], mask, self.rank, self.nranks, self._gather)
+                call("ab_domain_set_interface", dom.h, level, len(neigh), _ip(neigh) if len(neigh) else None, _ip(offsets),
+                     _ip(idx) if len(idx) else None, owned.ctypes.data_as(C.POINTER(C.c_ubyte)))
+                dom._iface.append(dict(neigh=neigh, offsets=offsets, idx=idx, owned=owned))
+            l2g = np.ascontiguousarray(info["l2g"], np.int32)
+            call("ab_domain_set_global_coarse", dom.h, int(info["nv0_global"]), _ip(l2g), _ip(info["vsub_global"]))
 
     # -- spaces / functions -------------------------------------------------------------------
     def ApproximationSpace(self, dom):

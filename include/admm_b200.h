@@ -53,6 +53,8 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value);
  * `nccl_unique_id` is the 128-byte ncclUniqueId created on rank 0 and distributed by the host program.     */
 int ab_context_init_comm(ab_context* ctx, int rank, int nranks, const void* nccl_unique_id);
 int ab_nccl_unique_id(void* out128);
+/* sum (max_op = 0) or max (max_op != 0) of n <= 64 host doubles over all ranks (host-side scalars of the driver) */
+int ab_context_allreduce_host(ab_context* ctx, double* v, int n, int max_op);
 
 /* ---- Domain / grid hierarchy ---------------------------------------------------------------------------- */
 /* LoadDomain(dom, gridName)  3d_admm.lua:108-109 */
@@ -66,6 +68,13 @@ int ab_domain_create(ab_context* ctx, int dim, int nv, const double* xyz, int ne
 int ab_domain_destroy(ab_domain* dom);
 /* util.refinement.CreateRegularHierarchy(dom, numRefs, false, balancerDesc)  3d_admm.lua:186 */
 int ab_domain_refine(ab_domain* dom, int num_refs);
+/* Multi-GPU (replaces the ParMETIS/pcl distribution of 3d_admm.lua:124-186): this rank's domain is its element
+ * partition of the level-0 grid; after refinement the host program supplies, per level, the vertices shared with
+ * each neighbour rank (same canonical order on both sides) and the owner mask, plus the global level-0 numbering
+ * for the replicated coarse solve.  Must be called before the first ApproximationSpace.                        */
+int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets,
+                            const int32_t* idx, const unsigned char* owned);
+int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l0_gid, const int32_t* vsub0_global);
 int ab_domain_num_levels(ab_domain* dom, int* out);
 /* dom:domain_info() 3d_admm.lua:112,189 -- sizes of one level */
 int ab_domain_level_info(ab_domain* dom, int level, int* dim, int* nv, int* ne, int* nedges, int* nv_coarse);
@@ -73,6 +82,11 @@ int ab_domain_level_info(ab_domain* dom, int level, int* dim, int* nv, int* ne, 
 int ab_domain_get_level(ab_domain* dom, int level, double* xyz, int32_t* elems, int32_t* vsub,
                         int32_t* parent_a, int32_t* parent_b);
 int ab_domain_subset_index(ab_domain* dom, const char* name, int* out);
+int ab_domain_subset_name(ab_domain* dom, int index, char* buf, int buflen);
+/* boundary-subset ("special") edges / faces and element subsets of a level (needed to re-create a partition of a loaded grid) */
+int ab_domain_special_info(ab_domain* dom, int level, int* n_sp_edges, int* n_sp_faces, int* nsubsets);
+int ab_domain_get_special(ab_domain* dom, int level, int32_t* sp_edges, int32_t* sp_edges_sub, int32_t* sp_faces, int32_t* sp_faces_sub,
+                          int32_t* esub);
 /* TransformDomainByDisplacement(u, "u1,u2,u3")  3d_admm.lua:1333,1352 : vertex coordinates += u (all levels) */
 int ab_transform_domain_by_displacement(ab_domain* dom, ab_vector* u);
 

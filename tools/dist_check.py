@@ -1,0 +1,57 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the domain-decomposed solve / ADMM iteration
+must reproduce the single-GPU result (matched by vertex coordinates)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from admm_optim_b200 import ug4
+from admm_optim_b200.driver import ObstacleOptim
+
+refs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+dim = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+grid = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "grids", "box_3D_elongated.npz" if dim == 3 else "refined.npz")
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+ug = ug4.Backend(device=local, distributed=True)
+p = ObstacleOptim(ug, dim, numRefs=refs, grid=grid, admmSteps=2).setup()
+for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
+    s.desc.abs_tol = 1e-13
+J = p.synthetic_sensitivity(0.5)
+p.set_sensitivity(J)
+t0 = time.time()
+tr = p.run_admm()
+ug.synchronize()
+dt = time.time() - t0
+assert not p.p_solver_failure
+u_loc = p.u.to_numpy().reshape(-1, dim)
+X_loc = p.dom.get_level(refs, elems=False)["xyz"]
+owned = p.dom._iface[refs]["owned"].astype(bool)
+out = [None] * world
+dist.all_gather_object(out, (X_loc[owned], u_loc[owned], [{k: r[k] for k in ("u_diff", "lambda_inc", "max_norm", "Lambda")} for r in tr],
+                            [[n["its"] for n in r["newton"]] for r in tr]))
+if rank == 0:
+    X = np.concatenate([o[0] for o in out]); U = np.concatenate([o[1] for o in out])
+    ug1 = ug4.Backend(device=local)
+    q = ObstacleOptim(ug1, dim, numRefs=refs, grid=grid, admmSteps=2).setup()
+    for s in [q.SmallProblemRHS_Solver, q.LargeProblem_Solver] + q.B_Solver:
+        s.desc.abs_tol = 1e-13
+    q.set_sensitivity(q.synthetic_sensitivity(0.5))
+    t0 = time.time(); tq = q.run_admm(); ug1.synchronize(); dt1 = time.time() - t0
+    Xg = q.dom.get_level(refs, elems=False)["xyz"]; Ug = q.u.to_numpy().reshape(-1, dim)
+    assert len(X) == len(Xg), (len(X), len(Xg))
+    def order(a):
+        return np.lexsort(tuple(a[:, c] for c in reversed(range(dim))))
+    oa, ob = order(X), order(Xg)
+    assert np.array_equal(X[oa], Xg[ob])
+    rel = np.linalg.norm(U[oa] - Ug[ob]) / np.linalg.norm(Ug)
+    print("ranks %d  numRefs %d: rel L2 diff of u vs single GPU = %.3e ; time dist %.3fs single %.3fs" % (world, refs, rel, dt, dt1))
+    for a, b in zip(out[0][2], tq):
+        for k in ("u_diff", "lambda_inc", "max_norm"):
+            print("   %-11s dist %.14e single %.14e rel %.2e" % (k, a[k], b[k], abs(a[k] - b[k]) / max(abs(b[k]), 1e-300)))
+    print("   its dist  ", out[0][3][0][:2])
+    print("   its single", [n["its"] for n in tq[0]["newton"]][:2])
+    assert rel < 1e-9
+    print("DIST CHECK OK")
+dist.barrier()
+dist.destroy_process_group()
