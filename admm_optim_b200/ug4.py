@@ -542,6 +542,18 @@ class Backend:
         self.util.solver = _Namespace()
         self.util.solver.CreateSolver = lambda desc: BiCGStabGMG(self, desc)
 
+    @classmethod
+    def host_only(cls, rank=0, nranks=1, gather=None):
+        """Context-free instance for the host-side entry points (grid loading, refinement, partitioning): no GPU needed,
+        ApproximationSpaces cannot be created on its domains."""
+        ug = cls.__new__(cls)
+        ug.lib = _lib.load()
+        ug.ctx, ug.dim, ug.rank, ug.nranks, ug._gather = C.c_void_p(), None, rank, nranks, gather
+        ug.util = _Namespace()
+        ug.util.refinement = _Namespace()
+        ug.util.refinement.CreateRegularHierarchy = ug._create_regular_hierarchy
+        return ug
+
     def __del__(self):
         try:
             if self.ctx:

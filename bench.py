@@ -75,6 +75,20 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def global_counts(refs):
+    """(block rows, blocks) of every level of the GLOBAL hierarchy: host-only refinement through the C ABI (no GPU work)."""
+    from admm_optim_b200 import ug4
+    ug = ug4.Backend.host_only()
+    dom = ug4.Domain(ug)
+    ug.LoadDomain(dom, GRID3D)
+    ug4.call("ab_domain_refine", dom.h, refs)
+    out = []
+    for l in range(refs + 1):
+        i = dom.level_info(l)
+        out.append((i["nv"], i["nv"] + 2 * i["nedges"]))
+    return out
+
+
 def spmv_bytes(dim, nb, nnzb):
     """B_spmv = nnzb*(8 d^2 + 4) + nb*(4 + 16 d)."""
     return nnzb * (8 * dim * dim + 4) + nb * (4 + 16 * dim)
@@ -169,7 +183,7 @@ def run_b200(args):
     from admm_optim_b200.driver import ObstacleOptim
 
     stream = torch.cuda.Stream()
-    ug = ug4.Backend(device=local, stream=stream.cuda_stream)
+    ug = ug4.Backend(device=local, stream=stream.cuda_stream, distributed=world > 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def barrier():
@@ -177,12 +191,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # multi-GPU (this revision): the path shards by domain decomposition; until the halo layer lands each
-    # rank runs the whole problem as an independent replica and the aggregate is reported as weak scaling.
+    # multi-GPU: the SAME global problem is domain-decomposed over the ranks (strong scaling): level-0 elements are
+    # partitioned (RCB), every rank refines its sub-grid, interface sums + all-reduces run on NCCL
     prob = ObstacleOptim(ug, 3, numRefs=args.refs, grid=GRID3D).setup()
-    ndofs = prob.DeformationSpace_ApproxSpace.num_dofs()
+    ndofs_local = prob.DeformationSpace_ApproxSpace.num_dofs()
     J_host = torch.from_numpy(prob.synthetic_sensitivity(0.5)).pin_memory()
-    u_host = torch.empty(ndofs, dtype=torch.float64).pin_memory()
+    u_host = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
+    ndofs = global_counts(args.refs)[-1][0] * 3 if world > 1 else ndofs_local
 
     def timed_leg(e2e):
         prob.set_sensitivity(J_host.numpy())
@@ -191,6 +206,7 @@ def run_b200(args):
             assert prob.admm_iteration() is not None
         newton, its = 0, 0
         total_ms = 0.0
+        h2d = d2h = 0
         launches0 = ug.launch_count()
         barrier()
         for _ in range(args.steps):
@@ -201,9 +217,11 @@ def run_b200(args):
             e0.record(stream)
             if e2e:
                 prob.set_sensitivity(J_host.numpy())             # H2D from pinned memory
+                h2d = ndofs_local * 8
             rec = prob.admm_iteration()
             if e2e:
                 prob.u.to_numpy(u_host.numpy())                  # D2H of the step's result
+                d2h = ndofs_local * 8 + 8 * 16
             e1.record(stream)
             e1.synchronize()
             assert rec is not None, "ADMM iteration failed"
@@ -212,81 +230,95 @@ def run_b200(args):
             its += sum(n["its"]["rhs"] + n["its"]["large"] + sum(n["its"]["B"]) for n in rec["newton"])
         barrier()
         launches = ug.launch_count() - launches0
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, newton, its, rec
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t[0] = tm[0]
+        return float(t[0].item()), launches, newton, its, rec, int(t[1].item()), int(t[2].item())
 
     clocks = ClockSampler(local)
     clocks.start()
-    ms_dev, launches, newton, its, rec = timed_leg(False)
-    ms_e2e, _, _, _, _ = timed_leg(True)
+    ms_dev, launches, newton, its, rec, _, _ = timed_leg(False)
+    ms_e2e, _, _, _, _, h2d_bytes, d2h_bytes = timed_leg(True)
     clk = clocks.stop()
 
     # ---- roofline leg: SpMV / V-cycle on a level larger than L2 ---------------------------------
     roof, extra = None, {}
-    if rank == 0 and args.roofline_refs > 0:
+    if args.roofline_refs > 0:
         big = ObstacleOptim(ug, 3, numRefs=args.roofline_refs, grid=GRID3D).setup()
         DD = big.DeformationEquation_DomainDisc
         DD.assemble_jacobian(big.A_u_Hessian, big.u)
-        _, nb, nnzb = big.A_u_Hessian.info()
-        n = nb * 3
-        x = np.random.default_rng(1).standard_normal(n)
+        levels = global_counts(args.roofline_refs) if world > 1 else None
+        _, nb_loc, nnzb_loc = big.A_u_Hessian.info()
+        nb, nnzb = (levels[-1] if world > 1 else (nb_loc, nnzb_loc))
+        x = np.random.default_rng(1 + rank).standard_normal(nb_loc * 3)
         big.sigma.from_numpy(x)
         DD.adjust_solution(big.sigma)
-        for _ in range(3):
-            big.A_u_Hessian.apply(big.Lu, big.sigma)
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(reps):
-            big.A_u_Hessian.apply(big.Lu, big.sigma)
-        e1.record(stream)
-        e1.synchronize()
-        t_spmv = e0.elapsed_time(e1) / reps * 1e-3
+
+        def timeit(fn, reps):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e-3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        t_spmv = timeit(lambda: big.A_u_Hessian.apply(big.Lu, big.sigma), 20)
         bytes_spmv = spmv_bytes(3, nb, nnzb)
         peak, peak_src = measured_peak()
         ach = bytes_spmv / t_spmv / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": None,
                 "kernel": "k_bsr_spmv_tma<3,0,0,3> (y = A x, BSR 3x3 fp64, TMA-staged tiles)", "peak_source": peak_src,
-                "bytes_per_launch": bytes_spmv, "us_per_launch": t_spmv * 1e6,
-                "workload": "box_3D_elongated numRefs=%d: %d block rows, %d blocks (matrix %.2f GB > L2)" % (args.roofline_refs, nb, nnzb, nnzb * 76 / 1e9)}
+                "bytes_per_launch": bytes_spmv // world, "us_per_launch": t_spmv * 1e6,
+                "workload": "box_3D_elongated numRefs=%d: %d block rows, %d blocks (matrix %.2f GB > L2)%s" %
+                            (args.roofline_refs, nb, nnzb, nnzb * 76 / 1e9, " over %d GPUs; per-GPU figures" % world if world > 1 else "")}
         s = big.SmallProblemRHS_Solver
         s.init(big.A_u_Hessian, big.sigma)
-        levels = [s.level_info(l) for l in range(args.roofline_refs + 1)]
-        for _ in range(2):
-            s.vcycle(big.delta_u, big.sigma)
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(10):
-            s.vcycle(big.delta_u, big.sigma)
-        e1.record(stream)
-        e1.synchronize()
-        t_v = e0.elapsed_time(e1) / 10 * 1e-3
+        if levels is None:
+            levels = [s.level_info(l) for l in range(args.roofline_refs + 1)]
+        t_v = timeit(lambda: s.vcycle(big.delta_u, big.sigma), 10)
         bv = vcycle_bytes(3, levels)
-        extra = {"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / peak,
-                 "vcycle_bytes": bv, "roofline_levels": levels}
+        # one full solve on the big level (GMG-preconditioned BiCGStab to the script tolerance)
+        big.Lu.from_numpy(x, 2)
+        DD.adjust_solution(big.Lu)
+        big.sigma.set(0.0)
+        barrier()
+        t0 = time.perf_counter()
+        ok = s.apply(big.sigma, big.Lu)
+        ug.synchronize()
+        t_solve = time.perf_counter() - t0
+        extra = {"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / (peak * world),
+                 "vcycle_bytes": bv, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(), "solve_converged": bool(ok)}
         del big
 
     if rank != 0:
         return
-    value = world * args.steps / (ms_dev * 1e-3)
-    e2e_v = world * args.steps / (ms_e2e * 1e-3)
+    value = args.steps / (ms_dev * 1e-3)
+    e2e_v = args.steps / (ms_e2e * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, ndofs),
-                       "numRefs": args.refs, "dofs": ndofs, "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                       "numRefs": args.refs, "dofs": ndofs,
+                       "parallelism": ("domain decomposition x%d (RCB of the level-0 grid, NCCL interface sums + all-reduces)" % world) if world > 1 else "1 GPU",
                        "l2": "L2 flushed (256 MB write) between timed iterations; working set itself is L2-sized",
                        "smoother": "Chebyshev(3)-Jacobi (stated equivalent of the reference's sequential GS, DESIGN.md)",
                        "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
-            "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": ndofs * 8, "d2h_bytes_per_step": ndofs * 8 + 8 * 16,
+            "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk}
     if roof:
         line["roofline"] = roof
         line.update(extra)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(args.refs)
     print(json.dumps(line))
 

@@ -29,15 +29,10 @@ def test_library_exports_every_declared_symbol():
 
 def _host_domain(path_or_npz, refs):
     from admm_optim_b200 import ug4
-
-    class _UG:      # host-only: no context
-        dim = None
-        ctx = None
-    ug = ug4.Backend.__new__(ug4.Backend)
-    ug.ctx, ug.dim = C.c_void_p(), None
+    ug = ug4.Backend.host_only()
     dom = ug4.Domain(ug)
-    ug4.Backend.LoadDomain(ug, dom, path_or_npz)
-    ug4.call("ab_domain_refine", dom.h, refs)
+    ug.LoadDomain(dom, path_or_npz)
+    ug.util.refinement.CreateRegularHierarchy(dom, refs, False, None)
     return dom
 
 
@@ -154,3 +149,37 @@ def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
     line = json.loads(outs[0])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert outs[1] == ""
+
+
+@pytest.mark.parametrize("grid,refs,counts", [(GRID3D, 2, [338, 2124, 14910]), (GRID2D, 2, [160, 596, 2296])])
+def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts):
+    """Host side of the multi-GPU path on 2 gloo ranks: every global vertex is owned exactly once on every level,
+    both sides of an interface list the same coordinates in the same order."""
+    import json
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_host_worker.py"), grid, str(refs)],
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0, err[-2000:]
+        outs.append(out)
+    res = json.loads(outs[0].strip().splitlines()[-1])
+    for level in range(refs + 1):
+        assert sum(r[level]["owned"] for r in res) == counts[level]
+        a, b = res[0][level]["shared"].get("1"), res[1][level]["shared"].get("0")
+        assert a is not None and a == b and len(a) > 0
+        assert res[0][level]["nv"] + res[1][level]["nv"] - len(a) == counts[level]
+
+
+def test_rcb_partition_is_balanced_and_deterministic():
+    from admm_optim_b200 import partition as P
+    z = np.load(GRID3D)
+    cent = z["xyz"][z["elems"]].mean(axis=1)
+    for n in (2, 3, 4, 8):
+        part = P.rcb_partition(cent, n)
+        cnt = np.bincount(part, minlength=n)
+        assert cnt.min() >= len(cent) // n - 1 and cnt.max() <= len(cent) // n + n
+        assert np.array_equal(part, P.rcb_partition(cent, n))
+        sub = P.extract_submesh({k: z[k] for k in z.files}, part, 0)
+        assert sub["elems"].max() == len(sub["l2g"]) - 1 and (np.diff(sub["l2g"]) > 0).all()
