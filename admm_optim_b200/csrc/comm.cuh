@@ -62,7 +62,72 @@ struct Interface {
     DevBuf<unsigned char> owned;      // per local vertex: 1 when this rank is the lowest rank sharing it
     DevBuf<double> send, recv, save;  // packed buffers (total * maxcomp), smoother scratch (niv * 2 * D)
     int total = 0, niv = 0;
+    // peer-to-peer path (NVLink, CUDA IPC): neighbours write straight into this rank's window
+    DevBuf<int> d_offset, d_neigh;                 // device copies of offset / neigh
+    DevBuf<unsigned long long> d_peer_dst;          // per neighbour: address (in this process) of my slot in the neighbour's window, parity 0
+    DevBuf<unsigned long long> d_peer_stride;       // per neighbour: byte distance between the neighbour's two parity buffers
+    DevBuf<unsigned long long> d_peer_flag;         // per neighbour: address of the neighbour's flag word for this rank
+    double* win_recv = nullptr;                     // my two parity buffers inside the window (total*D doubles each)
+    unsigned long long* win_flags = nullptr;        // my flag words (one per rank) for this level
+    unsigned long long epoch = 0;
 };
+
+// Fused interface sum over NVLink peer memory: every rank stores its additive interface values directly into its
+// neighbours' receive windows, publishes a per-level epoch flag (system-scope release), waits for the neighbours'
+// flags and accumulates what they wrote -- pack, transfer, synchronisation and unpack in ONE launch, no NCCL call.
+// Double-buffered by epoch parity (a neighbour can be at most one exchange ahead).  `done` counts finished blocks
+// so that the flags are published once all of this rank's stores are out.  A bounded spin turns a lost peer into an
+// error flag instead of a hang.
+__global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, int nneigh, unsigned long long epoch, unsigned long long done_target,
+                                                            const int* __restrict__ idx, const int* __restrict__ offset,
+                                                            const int* __restrict__ neigh, const unsigned long long* __restrict__ peer_dst,
+                                                            const unsigned long long* __restrict__ peer_stride,
+                                                            const unsigned long long* __restrict__ peer_flag, double* my_recv,
+                                                            unsigned long long* my_flags, unsigned long long* done, int* err, double* v) {
+    const int parity = (int)(epoch & 1ull);
+    const int n_ent = total * D;
+    // 1. put: my additive values go straight into the neighbours' windows
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
+        const int k = t / D, c = t - k * D;
+        int n = 0;
+        while (n + 1 < nneigh && k >= offset[n + 1]) ++n;
+        double* dst = reinterpret_cast<double*>(peer_dst[n] + (unsigned long long)parity * peer_stride[n]) + (size_t)(k - offset[n]) * D + c;
+        *dst = v[(int64_t)idx[k] * D + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // grid-wide: every block has read v and issued its stores before anybody accumulates into v (a vertex shared with
+    // several neighbours is sent by one block and accumulated by another).  `done` is a monotonic counter (never reset).
+    if (threadIdx.x == 0) {
+        const unsigned long long old = atomicAdd(done, 1ull);
+        if (old + 1 == done_target) {                       // last block of this launch: publish the epoch to the neighbours
+            __threadfence_system();
+            for (int n = 0; n < nneigh; ++n) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_flag[n]);
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            }
+        }
+        long long spins = 0;
+        while (*(volatile unsigned long long*)done < done_target)
+            if (++spins > 400000000ll) { *err = 2; break; }
+        // 2. wait for every neighbour's flag of this epoch
+        for (int n = 0; n < nneigh; ++n) {
+            spins = 0;
+            unsigned long long f;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(my_flags + neigh[n]) : "memory");
+                if (++spins > 400000000ll) { *err = 1; break; }
+            } while (f < epoch);
+        }
+    }
+    __syncthreads();
+    // 3. accumulate what the neighbours wrote
+    const double* buf = my_recv + (size_t)parity * n_ent;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
+        const int k = t / D, c = t - k * D;
+        atomicAdd(v + (int64_t)idx[k] * D + c, __ldcg(buf + t));
+    }
+}
 
 __global__ void k_iface_pack(int total, int D, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total * D; t += gridDim.x * blockDim.x) {

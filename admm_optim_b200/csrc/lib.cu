@@ -65,6 +65,15 @@ struct Domain {
     std::vector<Interface> iface;
     int nv0_global = 0;
     std::vector<int> l0_gid, vsub0_global;
+    // P2P window (CUDA IPC): [flags: nlevels*nranks u64][level 0: 2 parity buffers][level 1: ...]
+    unsigned char* window = nullptr;
+    size_t window_bytes = 0;
+    std::vector<size_t> win_level_base;
+    std::vector<void*> peer_windows;        // opened IPC mappings, by rank
+    bool p2p_connected = false;
+    DevBuf<unsigned long long> p2p_done;
+    unsigned long long p2p_done_total = 0;
+    DevBuf<int> p2p_err;
     bool distributed() const { return ctx && ctx->comm && ctx->comm->nranks > 1; }
     int dim() const { return mesh.dim; }
     int top() const { return (int)mesh.levels.size() - 1; }
@@ -151,6 +160,14 @@ static void exchange_sum(Domain* dom, int level, double* v, int D) {
     Context* ctx = dom->ctx;
     Interface& I = dom->iface[level];
     if (I.total == 0) return;
+    if (dom->p2p_connected) {   // one fused kernel over NVLink peer memory
+        I.epoch++;
+        const int g = std::max(1, std::min(grid_for((int64_t)I.total * D, 256, 64), ctx->num_sms));
+        dom->p2p_done_total += (unsigned long long)g;
+        AB_LAUNCH(ctx, k_iface_exchange_p2p, g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, dom->p2p_done_total, I.idx.p, I.d_offset.p, I.d_neigh.p,
+                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, v);
+        return;
+    }
     NcclApi& nc = NcclApi::get();
     AB_LAUNCH(ctx, k_iface_pack, grid_for((int64_t)I.total * D, 256, ctx->num_sms * 4), 256, 0, I.total, D, I.idx.p, v, I.send.p);
     AB_NCCL(nc.GroupStart());
@@ -1177,6 +1194,81 @@ int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l
     dom->l0_gid.assign(l0_gid, l0_gid + nv0);
     dom->vsub0_global.assign(vsub0_global, vsub0_global + nv0_global);
     for (int g : dom->l0_gid) AB_REQUIRE(g >= 0 && g < nv0_global, AB_ERR_ARG, "global vertex id out of range");
+    AB_CATCH
+}
+int ab_domain_p2p_export(ab_domain* dom, void* handle64, int64_t* level_base /* nlevels */, int32_t* totals /* nlevels */) {
+    AB_TRY
+    AB_REQUIRE(dom->finalized && dom->distributed(), AB_ERR_STATE, "p2p window needs a finalised multi-GPU domain");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const int nl = (int)dom->iface.size(), nr = dom->ctx->comm->nranks, D = dom->dim();
+    if (!dom->window) {
+        size_t off = (size_t)nl * nr * sizeof(unsigned long long);
+        off = (off + 255) & ~(size_t)255;
+        dom->win_level_base.resize(nl);
+        for (int l = 0; l < nl; ++l) {
+            dom->win_level_base[l] = off;
+            off += ((size_t)2 * dom->iface[l].total * D * sizeof(double) + 255) & ~(size_t)255;
+        }
+        dom->window_bytes = std::max<size_t>(off, 256);
+        AB_CUDA(cudaMalloc((void**)&dom->window, dom->window_bytes));      // a plain allocation: exported whole through CUDA IPC
+        AB_CUDA(cudaMemset(dom->window, 0, dom->window_bytes));
+        dom->p2p_done.alloc(1); dom->p2p_done.zero(dom->ctx->stream);
+        dom->p2p_err.alloc(1); dom->p2p_err.zero(dom->ctx->stream);
+        AB_CUDA(cudaStreamSynchronize(dom->ctx->stream));
+    }
+    cudaIpcMemHandle_t h;
+    AB_CUDA(cudaIpcGetMemHandle(&h, dom->window));
+    memcpy(handle64, &h, 64);
+    for (int l = 0; l < nl; ++l) { level_base[l] = (int64_t)dom->win_level_base[l]; totals[l] = dom->iface[l].total; }
+    AB_CATCH
+}
+// handles: nranks x 64 bytes; per level l and neighbour slot k (concatenated over levels in neighbour order):
+// remote_dst[.] = byte offset inside the neighbour's window of this rank's slot (parity 0), remote_stride[.] = the neighbour's
+// parity stride in bytes
+int ab_domain_p2p_connect(ab_domain* dom, const void* handles, const int64_t* remote_dst, const int64_t* remote_stride) {
+    AB_TRY
+    AB_REQUIRE(dom->window && !dom->p2p_connected, AB_ERR_STATE, "ab_domain_p2p_export first");
+    Context* ctx = dom->ctx;
+    const int nl = (int)dom->iface.size(), nr = ctx->comm->nranks, me = ctx->comm->rank, D = dom->dim();
+    dom->peer_windows.assign(nr, nullptr);
+    std::vector<char> used(nr, 0);
+    for (int l = 0; l < nl; ++l) for (int q : dom->iface[l].neigh) used[q] = 1;
+    for (int q = 0; q < nr; ++q) {
+        if (!used[q] || q == me) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)q * 64, 64);
+        AB_CUDA(cudaIpcOpenMemHandle(&dom->peer_windows[q], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    size_t pos = 0;
+    for (int l = 0; l < nl; ++l) {
+        Interface& I = dom->iface[l];
+        const size_t nn = I.neigh.size();
+        std::vector<unsigned long long> dst(nn), stride(nn), flag(nn);
+        for (size_t k = 0; k < nn; ++k, ++pos) {
+            const int q = I.neigh[k];
+            unsigned char* base = (unsigned char*)dom->peer_windows[q];
+            dst[k] = (unsigned long long)(uintptr_t)(base + remote_dst[pos]);
+            stride[k] = (unsigned long long)remote_stride[pos];
+            flag[k] = (unsigned long long)(uintptr_t)(base + ((size_t)l * nr + me) * sizeof(unsigned long long));
+        }
+        if (nn) {
+            I.d_peer_dst.upload(dst, ctx->stream); I.d_peer_stride.upload(stride, ctx->stream); I.d_peer_flag.upload(flag, ctx->stream);
+            I.d_offset.upload(I.offset, ctx->stream); I.d_neigh.upload(I.neigh, ctx->stream);
+        }
+        I.win_recv = (double*)(dom->window + dom->win_level_base[l]);
+        I.win_flags = (unsigned long long*)dom->window + (size_t)l * nr;
+        (void)D;
+    }
+    dom->p2p_connected = true;
+    AB_CATCH
+}
+int ab_domain_p2p_status(ab_domain* dom, int* connected, int* error) {
+    AB_TRY
+    if (connected) *connected = dom->p2p_connected ? 1 : 0;
+    if (error) {
+        *error = 0;
+        if (dom->p2p_err.p) { AB_CUDA(cudaStreamSynchronize(dom->ctx->stream)); AB_CUDA(cudaMemcpy(error, dom->p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost)); }
+    }
     AB_CATCH
 }
 int ab_domain_num_levels(ab_domain* dom, int* out) {

@@ -152,6 +152,9 @@ class ApproximationSpace(_Handle):
     def _ensure(self):
         if not self.h:
             call("ab_space_create", self.dom.h, self.kind, len(self.names), C.byref(self.h))
+            if self.ug.nranks > 1 and not getattr(self.dom, "_p2p_done", False):
+                self.dom._p2p_done = True
+                self.ug._connect_p2p(self.dom)
 
     def init_levels(self):
         self._ensure()
@@ -655,6 +658,34 @@ class Backend:
                 dom._iface.append(dict(neigh=neigh, offsets=offsets, idx=idx, owned=owned))
             l2g = np.ascontiguousarray(info["l2g"], np.int32)
             call("ab_domain_set_global_coarse", dom.h, int(info["nv0_global"]), _ip(l2g), _ip(info["vsub_global"]))
+
+    def _connect_p2p(self, dom):
+        """Wire the NVLink peer-to-peer interface sums (collective over all ranks): exchange the CUDA IPC handles and the
+        window layouts, then tell every rank where its slots live in its neighbours' windows.  ADMM_B200_P2P=0 keeps NCCL."""
+        if os.environ.get("ADMM_B200_P2P", "1") == "0":
+            return
+        nl = dom.num_levels()
+        handle = (C.c_ubyte * 64)()
+        base = (C.c_int64 * nl)()
+        totals = (C.c_int32 * nl)()
+        call("ab_domain_p2p_export", dom.h, handle, base, totals)
+        d = dom.dim
+        mine = dict(handle=bytes(handle), base=list(base), totals=list(totals),
+                    neigh=[list(map(int, I["neigh"])) for I in dom._iface], offsets=[list(map(int, I["offsets"])) for I in dom._iface])
+        everyone = self._gather(mine)
+        handles = b"".join(e["handle"] for e in everyone)
+        rdst, rstride = [], []
+        for l in range(nl):
+            for q in mine["neigh"][l]:
+                e = everyone[q]
+                k = e["neigh"][l].index(self.rank)
+                rdst.append(e["base"][l] + e["offsets"][l][k] * d * 8)
+                rstride.append(e["totals"][l] * d * 8)
+        n = max(len(rdst), 1)
+        a_dst = (C.c_int64 * n)(*rdst) if rdst else (C.c_int64 * 1)()
+        a_str = (C.c_int64 * n)(*rstride) if rstride else (C.c_int64 * 1)()
+        call("ab_domain_p2p_connect", dom.h, handles, a_dst, a_str)
+        self._gather(0)                                   # everyone connected before the first exchange
 
     # -- spaces / functions -------------------------------------------------------------------
     def ApproximationSpace(self, dom):

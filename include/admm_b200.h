@@ -75,6 +75,12 @@ int ab_domain_refine(ab_domain* dom, int num_refs);
 int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets,
                             const int32_t* idx, const unsigned char* owned);
 int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l0_gid, const int32_t* vsub0_global);
+/* NVLink peer-to-peer interface sums (CUDA IPC; optional -- without it the exchanges use ncclSend/ncclRecv):
+ * export this rank's receive window after the first ApproximationSpace exists, gather all handles / layouts on the
+ * host, then connect.  remote_dst / remote_stride: one entry per (level, neighbour) in level-major, neighbour order. */
+int ab_domain_p2p_export(ab_domain* dom, void* handle64, int64_t* level_base, int32_t* totals);
+int ab_domain_p2p_connect(ab_domain* dom, const void* handles, const int64_t* remote_dst, const int64_t* remote_stride);
+int ab_domain_p2p_status(ab_domain* dom, int* connected, int* error);
 int ab_domain_num_levels(ab_domain* dom, int* out);
 /* dom:domain_info() 3d_admm.lua:112,189 -- sizes of one level */
 int ab_domain_level_info(ab_domain* dom, int level, int* dim, int* nv, int* ne, int* nedges, int* nv_coarse);

@@ -28,9 +28,22 @@ from .mesh_np import Mesh, p1_pattern
 # ------------------------------------------------------------------------------------------
 
 
+_GEOM_CACHE = {}
+
+
 def geometry(mesh: Mesh):
     """P1 gradients G (ne,d+1,d), element measure vol (ne,) (|det J|/d!  -- refined.ugx has 134
-    clockwise triangles), centroid xbar (ne,d)."""
+    clockwise triangles), centroid xbar (ne,d).  Cached per coordinate array content."""
+    key = (id(mesh), mesh.xyz.ctypes.data, hash(mesh.xyz[:: max(1, mesh.nv // 64)].tobytes()), float(mesh.xyz.sum()))
+    hit = _GEOM_CACHE.get(id(mesh))
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    out = _geometry(mesh)
+    _GEOM_CACHE[id(mesh)] = (key, out)
+    return out
+
+
+def _geometry(mesh: Mesh):
     d = mesh.dim
     X = mesh.xyz[mesh.elems]                         # (ne,d+1,d)
     J = np.transpose(X[:, 1:, :] - X[:, :1, :], (0, 2, 1))   # columns = edge vectors
@@ -292,6 +305,69 @@ def barycenter_defect(mesh, u):
 # ------------------------------------------------------------------------------------------
 # multigrid + Krylov (obstacle_optim_3d_util.lua:9-43)
 # ------------------------------------------------------------------------------------------
+import ctypes as _C
+import os as _os
+
+_CLIB = None
+
+
+def c_kernels():
+    """oracle/liboracle_c.so (oracle_kernels.c): forward Gauss-Seidel sweep + CSR SpMV; None when not built."""
+    global _CLIB
+    if _CLIB is None:
+        path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "liboracle_c.so")
+        if not _os.path.exists(path):
+            _CLIB = False
+        else:
+            lib = _C.CDLL(path)
+            ip, dp = _C.POINTER(_C.c_int), _C.POINTER(_C.c_double)
+            lib.oracle_gs_forward.argtypes = [_C.c_int, ip, ip, dp, dp, dp, _C.c_int, dp]
+            lib.oracle_gs_forward.restype = None
+            lib.oracle_spmv.argtypes = [_C.c_int, ip, ip, dp, dp, dp, _C.c_int]
+            lib.oracle_spmv.restype = None
+            lib.oracle_max_threads.restype = _C.c_int
+            _CLIB = lib
+    return _CLIB or None
+
+
+class CsrC:
+    """CSR matrix with C SpMV / GS (falls back to SciPy when the C library is not built)."""
+
+    def __init__(self, A, threads=1):
+        A = A.tocsr()
+        A.sort_indices()
+        self.A, self.n, self.threads = A, A.shape[0], threads
+        self.ip = np.ascontiguousarray(A.indptr, np.int32)
+        self.idx = np.ascontiguousarray(A.indices, np.int32)
+        self.a = np.ascontiguousarray(A.data, np.float64)
+        self.lib = c_kernels()
+        self._xold = np.empty(self.n)
+        self._LD = None
+
+    def _p(self, arr, t):
+        return arr.ctypes.data_as(_C.POINTER(t))
+
+    def matvec(self, x):
+        if self.lib is None:
+            return self.A @ x
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty(self.n)
+        self.lib.oracle_spmv(self.n, self._p(self.ip, _C.c_int), self._p(self.idx, _C.c_int), self._p(self.a, _C.c_double),
+                             self._p(x, _C.c_double), self._p(y, _C.c_double), self.threads)
+        return y
+
+    def gs_sweep(self, x, b, blocks=1):
+        """one forward sweep, in place on a copy; blocks > 1 = block-Jacobi across `blocks` row blocks"""
+        if self.lib is None:
+            if self._LD is None:
+                self._LD = sp.tril(self.A, 0, format="csr")
+            return x + spla.spsolve_triangular(self._LD, b - self.A @ x, lower=True)
+        x = np.array(x, dtype=np.float64, copy=True)
+        b = np.ascontiguousarray(b, np.float64)
+        self.lib.oracle_gs_forward(self.n, self._p(self.ip, _C.c_int), self._p(self.idx, _C.c_int), self._p(self.a, _C.c_double),
+                                   self._p(b, _C.c_double), self._p(x, _C.c_double), blocks, self._p(self._xold, _C.c_double))
+        return x
+
 
 
 def prolongation(fine: Mesh, d: int):
@@ -318,9 +394,9 @@ class GMG:
               'jac'  damped point Jacobi, omega = 0.66
     The product (CUDA) path implements 'cheb' and 'jac'; 'gs' is kept for side-by-side iteration counts."""
 
-    def __init__(self, levels, A_top, dmasks, smoother="cheb", nu1=3, nu2=3, cheb_ratio=4.0, omega=0.66):
+    def __init__(self, levels, A_top, dmasks, smoother="cheb", nu1=3, nu2=3, cheb_ratio=4.0, omega=0.66, threads=1):
         d = levels[0].dim
-        self.smoother, self.nu1, self.nu2, self.omega = smoother, nu1, nu2, omega
+        self.smoother, self.nu1, self.nu2, self.omega, self.threads = smoother, nu1, nu2, omega, threads
         self.A = [None] * len(levels)
         self.P = [None] * len(levels)
         self.keep = [(~m).astype(float) for m in dmasks]
@@ -334,20 +410,18 @@ class GMG:
         self.dinv = [1.0 / A.diagonal() for A in self.A]
         self.lmax = [gershgorin_lmax(A) for A in self.A]
         self.cheb_ratio = cheb_ratio
-        if smoother == "gs":
-            self.LD = [sp.tril(A, 0, format="csr") for A in self.A]
+        self.C = [CsrC(A, threads) for A in self.A]
 
     # -- smoothers -------------------------------------------------------------------------
     def _smooth(self, l, x, b, nu, zero_guess):
-        A = self.A[l]
+        A = self.C[l]
         if self.smoother == "gs":
             for _ in range(nu):
-                r = b - A @ x
-                x = x + spla.spsolve_triangular(self.LD[l], r, lower=True)
+                x = A.gs_sweep(x, b, self.threads)
             return x
         if self.smoother == "jac":
             for it in range(nu):
-                r = b if (zero_guess and it == 0) else b - A @ x
+                r = b if (zero_guess and it == 0) else b - A.matvec(x)
                 x = x + self.omega * self.dinv[l] * r
             return x
         # Chebyshev (Saad, Alg. 12.1) preconditioned by point Jacobi
@@ -356,12 +430,12 @@ class GMG:
         theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
         sigma1 = theta / delta
         rho = 1.0 / sigma1
-        r = b if zero_guess else b - A @ x
+        r = b if zero_guess else b - A.matvec(x)
         dvec = self.dinv[l] * r / theta
         x = x + dvec
         for _ in range(nu - 1):
             rho_new = 1.0 / (2.0 * sigma1 - rho)
-            r = b - A @ x
+            r = b - A.matvec(x)
             dvec = rho_new * rho * dvec + (2.0 * rho_new / delta) * (self.dinv[l] * r)
             x = x + dvec
             rho = rho_new
@@ -371,7 +445,7 @@ class GMG:
         if l == 0:
             return self.lu.solve(b)
         x = self._smooth(l, np.zeros_like(b), b, self.nu1, True)
-        r = b - self.A[l] @ x
+        r = b - self.C[l].matvec(x)
         bc = self.keep[l - 1] * (self.P[l].T @ r)
         x = x + self.P[l] @ self.vcycle(l - 1, bc)
         return self._smooth(l, x, b, self.nu2, False)

@@ -288,7 +288,7 @@ class BiCGStabGMG:
         if key not in cache:
             cache.clear()
             cache[key] = F.GMG(dom.levels, A.mat, dmasks, smoother=self.ug.smoother, nu1=pre.get("preSmooth", 3),
-                               nu2=pre.get("postSmooth", 3), cheb_ratio=self.ug.cheb_ratio)
+                               nu2=pre.get("postSmooth", 3), cheb_ratio=self.ug.cheb_ratio, threads=self.ug.threads)
         self.gmg = cache[key]
         return True
 
@@ -325,9 +325,9 @@ class Backend:
     'gs' (lexicographic Gauss-Seidel, what the reference asks for -- iteration counts side by side)."""
     name = "oracle"
 
-    def __init__(self, smoother="cheb", cheb_ratio=6.0):
+    def __init__(self, smoother="cheb", cheb_ratio=6.0, threads=1):
         self.dim = None
-        self.smoother, self.cheb_ratio = smoother, cheb_ratio
+        self.smoother, self.cheb_ratio, self.threads = smoother, cheb_ratio, threads
         self._gmg_cache = {}
         self._asm_cache = {}
         self.util = _NS()
