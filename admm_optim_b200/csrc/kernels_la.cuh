@@ -770,6 +770,66 @@ __global__ void __launch_bounds__(256) k_gauss_jordan(int n, double* __restrict_
         grid.sync();
     }
 }
+// Blocked Gauss-Jordan without row exchanges (the free-dof coarse operator is symmetric and, for the moderate
+// multipliers of the ADMM loop, positive definite): K pivot columns per grid-wide barrier.  Every block reduces the
+// K x 2n pivot panel redundantly in shared memory (the K x K diagonal block becomes the identity), then applies the
+// rank-K update to the rows it owns.  A pivot that is tiny relative to the largest pivot seen raises *fail = 2 and
+// the host falls back to the partially pivoted k_gauss_jordan.  On exit M = [I | A^-1].
+template <int K>
+__global__ void __launch_bounds__(256) k_gauss_jordan_blocked(int n, double* __restrict__ M, int* __restrict__ pivrow, int* __restrict__ fail) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double panel[];                   // K x 2n
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    const int ld = 2 * n;
+    double maxpiv = 0.0;
+    if (tid == 0) s_bad = 0;
+    for (int i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) pivrow[i] = i;
+    for (int k0 = 0; k0 < n; k0 += K) {
+        const int kk = min(K, n - k0);
+        for (int j = 0; j < kk; ++j)
+            for (int c = k0 + tid; c < ld; c += blockDim.x) panel[j * ld + c] = M[(int64_t)(k0 + j) * ld + c];
+        grid.sync();                                    // every block holds the panel before its owner overwrites it
+        for (int j = 0; j < kk; ++j) {
+            const double piv = panel[j * ld + k0 + j];
+            const double ap = fabs(piv);
+            if (!(ap > 1e-10 * maxpiv) || !(ap > 0.0)) { if (tid == 0) s_bad = 1; }
+            maxpiv = fmax(maxpiv, ap);
+            const double inv = 1.0 / piv;
+            __syncthreads();
+            for (int c = k0 + tid; c < ld; c += blockDim.x) panel[j * ld + c] *= inv;
+            __syncthreads();
+            for (int j2 = 0; j2 < kk; ++j2) {
+                if (j2 == j) continue;
+                const double f = panel[j2 * ld + k0 + j];
+                __syncthreads();
+                if (f != 0.0)
+                    for (int c = k0 + tid; c < ld; c += blockDim.x) panel[j2 * ld + c] -= f * panel[j * ld + c];
+                __syncthreads();
+            }
+        }
+        for (int i = blockIdx.x; i < n; i += gridDim.x) {
+            double* row = M + (int64_t)i * ld;
+            if (i >= k0 && i < k0 + kk) {
+                for (int c = k0 + tid; c < ld; c += blockDim.x) row[c] = panel[(i - k0) * ld + c];
+                continue;
+            }
+            double cf[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) cf[j] = j < kk ? row[k0 + j] : 0.0;
+            __syncthreads();
+            for (int c = k0 + tid; c < ld; c += blockDim.x) {
+                double v = row[c];
+#pragma unroll
+                for (int j = 0; j < K; ++j) v -= cf[j] * panel[j * ld + c];
+                row[c] = (c < k0 + kk) ? 0.0 : v;
+            }
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && tid == 0 && s_bad) *fail = 2;
+}
+
 // Ainv[k][c] = M[pivrow[k]][n+c] / M[pivrow[k]][k]
 __global__ void k_extract_inverse(int n, const double* __restrict__ M, const int* __restrict__ pivrow, double* __restrict__ Ainv) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)n * n; t += (int64_t)gridDim.x * blockDim.x) {

@@ -390,6 +390,7 @@ struct Gmg {
     int n_free = 0, n0 = 0;
     DevBuf<double> Ainv, Mwork;
     DevBuf<int> free2dof, dof2free, pivrow, fail;
+    bool force_pivoting = false;      // set when the unpivoted blocked elimination met a tiny pivot
     DevBuf<int> dof2gfree;            // multi-GPU: local level-0 dof -> global free-dof index (-1: Dirichlet)
     DevBuf<double> bg, xg;            // global coarse vectors (replicated solve)
     void setup(const std::shared_ptr<MatrixData>& A);
@@ -482,7 +483,15 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
             int* fail = G.fail.p;
             void* args[] = {&nn, &M, &piv, &fail};
             int grid = std::min(ctx->num_sms, n);
-            AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
+            constexpr int KB = 8;
+            const size_t panel_bytes = (size_t)KB * 2 * n * sizeof(double);
+            if (!G.force_pivoting && panel_bytes <= 200 * 1024) {      // blocked, unpivoted (fast path; checked in Gmg::setup)
+                static bool attr = false;
+                if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_blocked<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_blocked<KB>, dim3(grid), dim3(256), args, panel_bytes, ctx->stream));
+            } else {
+                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
+            }
             ctx->launches++;
             AB_LAUNCH(ctx, k_extract_inverse, grid_for((int64_t)n * n, 256, ctx->num_sms * 8), 256, 0, n, G.Mwork.p, G.pivrow.p, G.Ainv.p);
         }
@@ -557,6 +566,12 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     int hfail = 0;
     AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hfail == 2 && !force_pivoting) {          // tiny pivot without row exchanges: redo everything with partial pivoting
+        force_pivoting = true;
+        if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
+        AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
 }
 
