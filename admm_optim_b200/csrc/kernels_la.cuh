@@ -796,17 +796,18 @@ __global__ void __launch_bounds__(256) k_gauss_jordan_blocked(int n, double* __r
             if (!(ap > 1e-10 * maxpiv) || !(ap > 0.0)) { if (tid == 0) s_bad = 1; }
             maxpiv = fmax(maxpiv, ap);
             const double inv = 1.0 / piv;
-            __syncthreads();
-            for (int c = k0 + tid; c < ld; c += blockDim.x) panel[j * ld + c] *= inv;
-            __syncthreads();
-            for (int j2 = 0; j2 < kk; ++j2) {
-                if (j2 == j) continue;
-                const double f = panel[j2 * ld + k0 + j];
-                __syncthreads();
-                if (f != 0.0)
-                    for (int c = k0 + tid; c < ld; c += blockDim.x) panel[j2 * ld + c] -= f * panel[j * ld + c];
-                __syncthreads();
+            double f[K];
+#pragma unroll
+            for (int j2 = 0; j2 < K; ++j2) f[j2] = (j2 < kk && j2 != j) ? panel[j2 * ld + k0 + j] : 0.0;
+            __syncthreads();                             // pivot column read by everybody before it is overwritten
+            for (int c = k0 + tid; c < ld; c += blockDim.x) {
+                const double pj = panel[j * ld + c] * inv;
+                panel[j * ld + c] = pj;
+#pragma unroll
+                for (int j2 = 0; j2 < K; ++j2)
+                    if (j2 < kk && j2 != j) panel[j2 * ld + c] -= f[j2] * pj;
             }
+            __syncthreads();
         }
         for (int i = blockIdx.x; i < n; i += gridDim.x) {
             double* row = M + (int64_t)i * ld;

@@ -76,16 +76,19 @@ class ClockSampler:
 
 
 def global_counts(refs):
-    """(block rows, blocks) of every level of the GLOBAL hierarchy: host-only refinement through the C ABI (no GPU work)."""
-    from admm_optim_b200 import ug4
-    ug = ug4.Backend.host_only()
-    dom = ug4.Domain(ug)
-    ug.LoadDomain(dom, GRID3D)
-    ug4.call("ab_domain_refine", dom.h, refs)
-    out = []
-    for l in range(refs + 1):
-        i = dom.level_info(l)
-        out.append((i["nv"], i["nv"] + 2 * i["nedges"]))
+    """(block rows, blocks) = (V, V + 2E) of every level of the GLOBAL hierarchy from the regular-refinement recurrences
+    V' = V+E, E' = 2E+3F+T, F' = 4F+8T, T' = 8T seeded with the level-0 entity counts of the grid."""
+    import numpy as np
+    z = np.load(GRID3D)
+    el = z["elems"]
+    V, T = len(z["xyz"]), len(el)
+    edges = np.unique(np.sort(np.concatenate([el[:, [i, j]] for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))]), axis=1), axis=0)
+    faces = np.unique(np.sort(np.concatenate([el[:, list(f)] for f in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))]), axis=1), axis=0)
+    E, F = len(edges), len(faces)
+    out = [(V, V + 2 * E)]
+    for _ in range(refs):
+        V, E, F, T = V + E, 2 * E + 3 * F + T, 4 * F + 8 * T, 8 * T
+        out.append((V, V + 2 * E))
     return out
 
 
