@@ -103,41 +103,6 @@ __global__ void k_bicg_half_x(int64_t n, const double* __restrict__ sc, const do
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += alpha * ph[i];
 }
 
-// ---- distributed BiCGStab: residual-type vectors are kept in additive (_a) and consistent (_c) form ------
-// s = r - alpha v for both representations; reduce <s_c, s_a> (local part)
-__global__ void __launch_bounds__(256) k_bicg2_s(int64_t n, double* __restrict__ sc, const double* __restrict__ ra, const double* __restrict__ rc,
-                                                 const double* __restrict__ va, const double* __restrict__ vc, double* __restrict__ sa,
-                                                 double* __restrict__ scv, double* partials, unsigned int* ticket) {
-    const double alpha = sc[SC_RHO] / sc[SC_RV];
-    double acc[1] = {0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double a = ra[i] - alpha * va[i], c = rc[i] - alpha * vc[i];
-        sa[i] = a;
-        scv[i] = c;
-        acc[0] += a * c;
-    }
-    grid_reduce<1, 0>(acc, partials, ticket, sc + SC_SS);
-}
-// x += alpha ph + omega sh; r = s - omega t (both representations); reduce <r_c,r_a>, <rh,r_a> (local parts)
-__global__ void __launch_bounds__(256) k_bicg2_xr(int64_t n, double* __restrict__ sc, const double* __restrict__ ph, const double* __restrict__ sh,
-                                                  const double* __restrict__ sa, const double* __restrict__ scv, const double* __restrict__ ta,
-                                                  const double* __restrict__ tc, const double* __restrict__ rh, double* __restrict__ x,
-                                                  double* __restrict__ ra, double* __restrict__ rc, double* partials, unsigned int* ticket,
-                                                  double* out2) {
-    const double alpha = sc[SC_RHO] / sc[SC_RV];
-    const double tt = sc[SC_TT];
-    const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
-    double acc[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        x[i] += alpha * ph[i] + omega * sh[i];
-        const double a = sa[i] - omega * ta[i], c = scv[i] - omega * tc[i];
-        ra[i] = a;
-        rc[i] = c;
-        acc[0] += a * c;
-        acc[1] += rh[i] * a;
-    }
-    grid_reduce<2, 0>(acc, partials, ticket, out2);
-}
 // point-Jacobi data, distributed: additive diagonal and additive absolute row sums (made consistent by an interface sum)
 template <int D>
 __global__ void k_diag_rowabs(int nb, const int* __restrict__ rowptr, const int* __restrict__ diagpos, const double* __restrict__ vals,

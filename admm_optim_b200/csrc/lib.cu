@@ -660,7 +660,7 @@ struct Solver {
     std::shared_ptr<MatrixData> A;
     std::shared_ptr<Gmg> gmg;
     DevBuf<double> r, rh, p, v, s, t, ph, sh, sc, out2;
-    DevBuf<double> rc, vc, scons, tc;   // multi-GPU: consistent twins of the residual-type vectors
+    DevBuf<double> rc;                  // multi-GPU: scratch for the unique (owner-only) form of the preconditioner input
     int last_steps = 0;
     double last_defect = 0;
     void ensure_vectors();
@@ -671,7 +671,7 @@ void Solver::ensure_vectors() {
     if (sc.n == 0) { sc.alloc(SC_COUNT + 3); out2.alloc(2); }
     if (type == 1 && r.n == 0) {
         r.alloc(n); rh.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); t.alloc(n); ph.alloc(n); sh.alloc(n);
-        if (sp->dom->distributed()) { rc.alloc(n); vc.alloc(n); scons.alloc(n); tc.alloc(n); }
+        if (sp->dom->distributed()) rc.alloc(n);
     }
     if (type == 2 && r.n == 0) { r.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); }
 }
@@ -750,9 +750,23 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     return ok;
 }
 
-// Multi-GPU BiCGStab: matrices and residual-type vectors are additive, iterates and preconditioned directions
-// consistent (the storage-type discipline UG4 exposes to the scripts, 3d_admm.lua:978-982).  Residual-type vectors
-// are carried in both forms so that every dot product is <consistent, additive>; one interface sum per SpMV.
+// Multi-GPU BiCGStab.  The matrix is additive, so every SpMV result is made consistent by one interface sum; the
+// Krylov vectors (r, p, v, s, t) are then all CONSISTENT and every inner product is taken over the owned copies only
+// (owner mask) -- mathematically the global dot product, and free of the large cancelling per-rank parts an additive
+// residual carries at shared vertices (<consistent, additive> stagnates at ~1e-8 once copies differ in the last bit,
+// which they do as soon as three ranks share a vertex).  The preconditioner input is the unique (owner-only) form,
+// a valid additive representation.  2 interface sums + 3 all-reduces per iteration.
+static void dot_owned(Domain* dom, int64_t n, const double* x0, const double* x1, const double* y, int nx, double* out) {
+    Context* ctx = dom->ctx;
+    const unsigned char* owned = dom->iface[dom->top()].owned.p;
+    if (nx == 1) AB_LAUNCH(ctx, (k_dot_owned<1>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x0, y, ctx->d_partials, ctx->d_tickets, out);
+    else AB_LAUNCH(ctx, (k_dot_owned<2>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x1, y, ctx->d_partials, ctx->d_tickets, out);
+    allreduce_dev(ctx, out, nx);
+}
+static void to_unique(Domain* dom, int64_t n, const double* src, double* dst) {
+    dev_copy(dom->ctx, n, src, dst);
+    AB_LAUNCH(dom->ctx, k_zero_not_owned, ew_grid(dom->ctx, n), 256, 0, n, dom->dim(), dom->iface[dom->top()].owned.p, dst);
+}
 static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_defect) {
     Domain* dom = S->sp->dom;
     Context* ctx = dom->ctx;
@@ -761,18 +775,16 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
     const int64_t n = S->sp->ndofs;
     const double* Av = S->A->vals.p;
     double* sc = S->sc.p;
+    double* uniq = S->rc.p;                                                     // scratch: unique form of the preconditioner input
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
-    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);                       // r_a = b_a - A x_c
-    dev_copy(ctx, n, S->r.p, S->rc.p);
-    exchange_sum(dom, top, S->rc.p, dim);                                       // r_c
-    dev_copy(ctx, n, S->rc.p, S->rh.p);
+    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);                       // r = b_additive - A x  (additive)
+    exchange_sum(dom, top, S->r.p, dim);                                        // -> consistent
+    dev_copy(ctx, n, S->r.p, S->rh.p);
     {
         const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        const double* xs[1] = {S->rc.p};
-        dev_dots(ctx, n, 1, xs, S->r.p, sc + SC_RR);
-        allreduce_dev(ctx, sc + SC_RR, 1);
+        dot_owned(dom, n, S->r.p, nullptr, S->r.p, 1, sc + SC_RR);
         AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     dev_fill(ctx, S->p.p, n, 0.0);
@@ -787,24 +799,20 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
     while (!ok && it < S->desc.max_iterations) {
         ++it;
         AB_LAUNCH(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
-        S->gmg->apply(S->p.p, S->ph.p);
-        spmv(ctx, dim, Lt, Av, 0, 1, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, S->rh.p, sc + SC_RV);
-        allreduce_dev(ctx, sc + SC_RV, 1);
-        dev_copy(ctx, n, S->v.p, S->vc.p);
-        exchange_sum(dom, top, S->vc.p, dim);
-        AB_LAUNCH(ctx, k_bicg2_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->rc.p, S->v.p, S->vc.p, S->s.p, S->scons.p, ctx->d_partials, ctx->d_tickets);
-        S->gmg->apply(S->s.p, S->sh.p);
-        spmv(ctx, dim, Lt, Av, 0, 1, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, S->scons.p, sc + SC_TS);
-        dev_copy(ctx, n, S->t.p, S->tc.p);
-        exchange_sum(dom, top, S->tc.p, dim);
-        {
-            const double* xs[1] = {S->tc.p};
-            dev_dots(ctx, n, 1, xs, S->t.p, sc + SC_TT);
-        }
-        allreduce_dev(ctx, sc + SC_TS, 2);
-        AB_LAUNCH(ctx, k_bicg2_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->scons.p, S->t.p, S->tc.p, S->rh.p, x->d.p, S->r.p,
-                  S->rc.p, ctx->d_partials, ctx->d_tickets, S->out2.p);
-        allreduce_dev(ctx, S->out2.p, 2);
+        to_unique(dom, n, S->p.p, uniq);
+        S->gmg->apply(uniq, S->ph.p);
+        spmv(ctx, dim, Lt, Av, 0, 0, S->ph.p, nullptr, S->v.p);
+        exchange_sum(dom, top, S->v.p, dim);
+        dot_owned(dom, n, S->rh.p, nullptr, S->v.p, 1, sc + SC_RV);
+        AB_LAUNCH(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
+        to_unique(dom, n, S->s.p, uniq);
+        S->gmg->apply(uniq, S->sh.p);
+        spmv(ctx, dim, Lt, Av, 0, 0, S->sh.p, nullptr, S->t.p);
+        exchange_sum(dom, top, S->t.p, dim);
+        dot_owned(dom, n, S->s.p, S->t.p, S->t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
+        AB_LAUNCH(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
+                  ctx->d_tickets, S->out2.p);                                    // local sums overwritten below
+        dot_owned(dom, n, S->r.p, S->rh.p, S->r.p, 2, S->out2.p);               // <r,r>, <rh,r>
         AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
         read_back(ctx, sc, SC_COUNT, h);
         rr = h[SC_RR];
@@ -816,7 +824,7 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
     x->touch();
     S->last_steps = it;
     S->last_defect = std::sqrt(std::max(rr, 0.0));
-    if (return_defect) { dev_copy(ctx, n, S->r.p, b->d.p); b->storage = AB_PST_ADDITIVE; b->touch(); }
+    if (return_defect) { to_unique(dom, n, S->r.p, b->d.p); b->storage = AB_PST_ADDITIVE; b->touch(); }   // unique = additive form of the defect
     return ok;
 }
 

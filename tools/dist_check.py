@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 ug = ug4.Backend(device=local, distributed=True)
-p = ObstacleOptim(ug, dim, numRefs=refs, grid=grid, admmSteps=2).setup()
+p = ObstacleOptim(ug, dim, numRefs=refs, grid=grid, admmSteps=2, verbose=(rank == 0 and os.environ.get("DIST_VERBOSE") == "1")).setup()
 for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
     s.desc.abs_tol = 1e-13
 J = p.synthetic_sensitivity(0.5)
