@@ -75,17 +75,48 @@ struct Interface {
 // Fused interface sum over NVLink peer memory: every rank stores its additive interface values directly into its
 // neighbours' receive windows, publishes a per-level epoch flag (system-scope release), waits for the neighbours'
 // flags and accumulates what they wrote -- pack, transfer, synchronisation and unpack in ONE launch, no NCCL call.
-// Double-buffered by epoch parity (a neighbour can be at most one exchange ahead).  `done` counts finished blocks
-// so that the flags are published once all of this rank's stores are out.  A bounded spin turns a lost peer into an
-// error flag instead of a hang.
-__global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, int nneigh, unsigned long long epoch, unsigned long long done_target,
+// Double-buffered by epoch parity (a neighbour can be at most one exchange ahead).  Intra-grid ordering uses one
+// monotonic counter (never reset; the host passes the value it must reach).  A bounded spin turns a lost peer into
+// an error flag instead of a hang.
+//   SMOOTH = false: v <- v + sum over neighbours           (additive -> consistent)
+//   SMOOTH = true : the Chebyshev/Jacobi interface fix-up fused around the sum (Gmg::smooth): the locally updated
+//                   d_out = c1 d_in + c2 D^-1 r_local is reduced to its additive increment, summed, and d_out, x_out
+//                   are rebuilt at the shared vertices:  d_out = c1 d_in + total,  x_out = x_in + d_out.
+__device__ __forceinline__ void p2p_grid_barrier(unsigned long long* counter, unsigned long long target, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        long long spins = 0;
+        while (*(volatile unsigned long long*)counter < target)
+            if (++spins > 400000000ll) { *err = 2; break; }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool SMOOTH>
+__global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, int nneigh, unsigned long long epoch, unsigned long long cnt_base,
                                                             const int* __restrict__ idx, const int* __restrict__ offset,
                                                             const int* __restrict__ neigh, const unsigned long long* __restrict__ peer_dst,
                                                             const unsigned long long* __restrict__ peer_stride,
                                                             const unsigned long long* __restrict__ peer_flag, double* my_recv,
-                                                            unsigned long long* my_flags, unsigned long long* done, int* err, double* v) {
+                                                            unsigned long long* my_flags, unsigned long long* counter, int* err, double* v,
+                                                            int niv, const int* __restrict__ iv, double c1, const double* din,
+                                                            const double* xin, double* xout) {
     const int parity = (int)(epoch & 1ull);
     const int n_ent = total * D;
+    const unsigned long long g = gridDim.x;
+    unsigned long long stage = cnt_base;
+    if (SMOOTH) {
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < niv * D; t += gridDim.x * blockDim.x) {
+            const int k = t / D, c = t - k * D;
+            const int64_t i = (int64_t)iv[k] * D + c;
+            v[i] = v[i] - (c1 != 0.0 ? c1 * din[i] : 0.0);            // additive increment c2 D^-1 r_local
+        }
+        stage += g;
+        p2p_grid_barrier(counter, stage, err);
+    }
     // 1. put: my additive values go straight into the neighbours' windows
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
         const int k = t / D, c = t - k * D;
@@ -97,10 +128,11 @@ __global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, in
     __threadfence_system();
     __syncthreads();
     // grid-wide: every block has read v and issued its stores before anybody accumulates into v (a vertex shared with
-    // several neighbours is sent by one block and accumulated by another).  `done` is a monotonic counter (never reset).
+    // several neighbours is sent by one block and accumulated by another); the last block publishes the epoch
+    stage += g;
     if (threadIdx.x == 0) {
-        const unsigned long long old = atomicAdd(done, 1ull);
-        if (old + 1 == done_target) {                       // last block of this launch: publish the epoch to the neighbours
+        const unsigned long long old = atomicAdd(counter, 1ull);
+        if (old + 1 == stage) {
             __threadfence_system();
             for (int n = 0; n < nneigh; ++n) {
                 unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_flag[n]);
@@ -108,7 +140,7 @@ __global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, in
             }
         }
         long long spins = 0;
-        while (*(volatile unsigned long long*)done < done_target)
+        while (*(volatile unsigned long long*)counter < stage)
             if (++spins > 400000000ll) { *err = 2; break; }
         // 2. wait for every neighbour's flag of this epoch
         for (int n = 0; n < nneigh; ++n) {
@@ -126,6 +158,17 @@ __global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, in
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
         const int k = t / D, c = t - k * D;
         atomicAdd(v + (int64_t)idx[k] * D + c, __ldcg(buf + t));
+    }
+    if (SMOOTH) {
+        stage += g;
+        p2p_grid_barrier(counter, stage, err);
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < niv * D; t += gridDim.x * blockDim.x) {
+            const int k = t / D, c = t - k * D;
+            const int64_t i = (int64_t)iv[k] * D + c;
+            const double dn = (c1 != 0.0 ? c1 * din[i] : 0.0) + v[i];
+            v[i] = dn;
+            xout[i] = (xin ? xin[i] : 0.0) + dn;
+        }
     }
 }
 

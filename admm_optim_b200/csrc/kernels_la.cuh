@@ -169,7 +169,7 @@ template <int D, int LPR, int MODE, int DOTS, int BATCH = D * D, int MINB = 3>
 __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                                   const double* __restrict__ vals, const double* __restrict__ x,
                                                   const double* __restrict__ b, double* __restrict__ y,
-                                                  const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
+                                                  const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
                                                   const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
     constexpr int DD = D * D;
     const int lane = threadIdx.x & 31;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
             } else {
                 const double res = b[i] - av;
                 const double dn = (c1 != 0.0 ? c1 * dvec[i] : 0.0) + c2 * dinv[i] * res;   // c1 == 0: dvec may be uninitialised
-                dvec[i] = dn;
+                dout[i] = dn;
                 y[i] = x[i] + dn;
             }
         }
@@ -276,7 +276,7 @@ template <int D, int MODE, int DOTS, int U>
 __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
                                                        const double* __restrict__ vals, const double* __restrict__ x,
                                                        const double* __restrict__ b, double* __restrict__ y,
-                                                       const double* __restrict__ dinv, double* __restrict__ dvec, double c1, double c2,
+                                                       const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
                                                        const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
     constexpr int DD = D * D;
     constexpr int BPS = 32 / DD;                        // blocks per step
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
             } else {
                 const double res = b[i] - v;
                 const double dn = (c1 != 0.0 ? c1 * dvec[i] : 0.0) + c2 * dinv[i] * res;
-                dvec[i] = dn;
+                dout[i] = dn;
                 y[i] = x[i] + dn;
             }
         }
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
                                                                  const int* __restrict__ colidx, const double* __restrict__ vals,
                                                                  const double* __restrict__ x, const double* __restrict__ b,
                                                                  double* __restrict__ y, const double* __restrict__ dinv,
-                                                                 double* __restrict__ dvec, double c1, double c2, const double* __restrict__ w,
+                                                                 const double* dvec, double* dout, double c1, double c2, const double* __restrict__ w,
                                                                  double* partials, unsigned int* ticket, double* red) {
     using T = SpmvTma<D>;
     constexpr int DD = T::DD, BPS = 32 / DD, NS = T::NSTAGE, NW = T::NT / 32 - 1;
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
                         const double dold = c1 != 0.0 ? reinterpret_cast<const double*>(sa + 2 * T::AUX_B + meta[8])[li] : 0.0;
                         const double xi = reinterpret_cast<const double*>(sa + 3 * T::AUX_B + meta[9])[li];
                         const double dn = c1 * dold + c2 * di * res;
-                        dvec[gi] = dn;
+                        dout[gi] = dn;
                         y[gi] = xi + dn;
                     }
                 }

@@ -163,9 +163,11 @@ static void exchange_sum(Domain* dom, int level, double* v, int D) {
     if (dom->p2p_connected) {   // one fused kernel over NVLink peer memory
         I.epoch++;
         const int g = std::max(1, std::min(grid_for((int64_t)I.total * D, 256, 64), ctx->num_sms));
+        const unsigned long long base = dom->p2p_done_total;
         dom->p2p_done_total += (unsigned long long)g;
-        AB_LAUNCH(ctx, k_iface_exchange_p2p, g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, dom->p2p_done_total, I.idx.p, I.d_offset.p, I.d_neigh.p,
-                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, v);
+        AB_LAUNCH(ctx, (k_iface_exchange_p2p<false>), g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, base, I.idx.p, I.d_offset.p, I.d_neigh.p,
+                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, v, 0,
+                  (const int*)nullptr, 0.0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr);
         return;
     }
     NcclApi& nc = NcclApi::get();
@@ -178,6 +180,18 @@ static void exchange_sum(Domain* dom, int level, double* v, int D) {
     }
     AB_NCCL(nc.GroupEnd());
     AB_LAUNCH(ctx, k_iface_unpack_add, grid_for((int64_t)I.total * D, 256, ctx->num_sms * 4), 256, 0, I.total, D, I.idx.p, I.recv.p, v);
+}
+// smoother interface fix-up fused around the peer-to-peer sum (needs the P2P window): see k_iface_exchange_p2p<true>
+static void smooth_exchange_p2p(Domain* dom, int level, int D, double c1, const double* din, double* dout, const double* xin, double* xout) {
+    Context* ctx = dom->ctx;
+    Interface& I = dom->iface[level];
+    I.epoch++;
+    const int g = std::max(1, std::min(grid_for((int64_t)I.total * D, 256, 64), ctx->num_sms));
+    const unsigned long long base = dom->p2p_done_total;
+    dom->p2p_done_total += 3ull * (unsigned long long)g;
+    AB_LAUNCH(ctx, (k_iface_exchange_p2p<true>), g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, base, I.idx.p, I.d_offset.p, I.d_neigh.p,
+              I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, dout, I.niv, I.iv.p, c1,
+              din, xin, xout);
 }
 // global sum / max of device scalars (no-op on one GPU)
 static void allreduce_dev(Context* ctx, double* d, int n, bool max_op = false) {
@@ -300,13 +314,13 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
 template <int D, int BATCH, int MINB>
 static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                        const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
     constexpr int LPR = D == 3 ? 16 : 8;
     const int64_t groups_per_block = 256 / LPR;
     const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * MINB * ctx->spmv_waves);
     const int g = std::min(std::max(grid, 1), (int)Context::kMaxBlocks);
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -317,14 +331,14 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
 }
 template <int D, int U>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                            const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+                            const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
     using T = SpmvTma<D>;
     const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
     do {                                                                                                                              \
         static bool attr = false;                                                                                                     \
         if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, MODE, DOTS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B)); attr = true; } \
-        AB_LAUNCH(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red); \
+        AB_LAUNCH(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red); \
     } while (0)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
@@ -336,11 +350,11 @@ static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals,
 }
 template <int D, int U>
 static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                             const double* dinv, double* dvec, double c1, double c2, const double* w, double* red) {
+                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
     const int64_t want = ((int64_t)L.nv + 7) / 8;        // 8 warps (rows) per CTA
     const int g = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    AB_LAUNCH(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -350,22 +364,24 @@ static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals
 #undef AB_SPMV
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                 const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr) {
+                 const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr,
+                 double* dout = nullptr) {
+    if (!dout) dout = dvec;
     // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path,
     // 2 = first-generation sub-warp row groups (kept for the comparisons in profiles/)
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
-            if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
             return;
         case 2:
-            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
             return;
         default:
-            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
-            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, c1, c2, w, red);
+            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
             return;
     }
 }
@@ -376,7 +392,7 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
 struct GmgLevel {
     DevBuf<double> vals_own;          // Galerkin operator (levels below top)
     const double* vals = nullptr;
-    DevBuf<double> dinv, x, b, r, d, x2;
+    DevBuf<double> dinv, x, b, r, d, x2, d2;   // d2: second increment buffer (multi-GPU P2P smoother ping-pong)
     double lmax = 0;
     std::vector<std::pair<double, double>> coef_pre, coef_post;   // (c1,c2) per smoothing step
     const unsigned char* mask = nullptr;
@@ -509,7 +525,7 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
             const int64_t n = (int64_t)dom->dev[l].nv * dim;
             GmgLevel& g = L[l];
             if (l < top) { g.x.alloc(n); g.b.alloc(n); }
-            if (l > 0) { g.r.alloc(n); g.d.alloc(n); g.x2.alloc(n); g.dinv.alloc(n); }
+            if (l > 0) { g.r.alloc(n); g.d.alloc(n); g.x2.alloc(n); g.dinv.alloc(n); if (dom->distributed()) g.d2.alloc(n); }
         }
         // free-dof numbering of level 0
         const HostLevel& H0 = dom->mesh.levels[0];
@@ -587,10 +603,15 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     const bool dist = dom->distributed() && dom->iface[l].niv > 0;
     Interface* I = dist ? &dom->iface[l] : nullptr;
     const int D = dom->dim();
+    const bool p2p = dist && dom->p2p_connected;
+    double* dbuf[2] = {g.d.p, p2p ? g.d2.p : g.d.p};     // P2P path ping-pongs d so that d_old survives the fused step
+    int dcur = 0;
     if (zero_guess) {
         cur = ((nu - 1) % 2 == 0) ? 0 : 1;
-        AB_LAUNCH(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, g.d.p, bufs[cur]);
-        if (dist) {   // d = c2 D^-1 b is additive at the interfaces: sum it, then x = d there
+        AB_LAUNCH(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur]);
+        if (p2p) {          // d = c2 D^-1 b is additive at the interfaces: sum it, x = d there -- one fused launch
+            smooth_exchange_p2p(dom, l, D, 0.0, nullptr, dbuf[dcur], nullptr, bufs[cur]);
+        } else if (dist) {
             AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, (const double*)nullptr, (const double*)nullptr, I->save.p);
             exchange_sum(dom, l, g.d.p, D);
             AB_LAUNCH(ctx, k_iface_fix, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, 0.0, I->save.p, g.d.p, bufs[cur]);
@@ -603,12 +624,19 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     for (; k < nu; ++k) {
         // multi-GPU: the local step yields d_new = c1 d_old + c2 D^-1 r_local at shared vertices; the increment
         // c2 D^-1 r_local is additive -> sum it over the interfaces and rebuild d, x there (comm.cuh)
-        if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
-        spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, coef[k].first, coef[k].second);
-        if (dist) {
-            AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first, I->save.p, g.d.p);
-            exchange_sum(dom, l, g.d.p, D);
-            AB_LAUNCH(ctx, k_iface_fix, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, coef[k].first, I->save.p, g.d.p, bufs[1 - cur]);
+        const double c1 = coef[k].first, c2 = coef[k].second;
+        if (p2p) {
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, dbuf[dcur], c1, c2, nullptr, nullptr, dbuf[1 - dcur]);
+            smooth_exchange_p2p(dom, l, D, c1, dbuf[dcur], dbuf[1 - dcur], bufs[cur], bufs[1 - cur]);
+            dcur = 1 - dcur;
+        } else {
+            if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1 != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2);
+            if (dist) {
+                AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1, I->save.p, g.d.p);
+                exchange_sum(dom, l, g.d.p, D);
+                AB_LAUNCH(ctx, k_iface_fix, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1, I->save.p, g.d.p, bufs[1 - cur]);
+            }
         }
         cur = 1 - cur;
     }
