@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(256) k_diag_gershgorin(int nb, const int* __re
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, const int* __restrict__ pb,
-                              const double* __restrict__ xc, double* __restrict__ xf) {
+                              const double* __restrict__ xc, const double* xin, double* xout) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvf * D; t += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
         double add;
@@ -566,23 +566,45 @@ __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, cons
             const int k = v - nvc;
             add = 0.5 * (xc[(int64_t)pa[k] * D + c] + xc[(int64_t)pb[k] * D + c]);
         }
-        xf[t] += add;
+        xout[t] = xin[t] + add;
     }
 }
 
-// rc = mask * P^T rf : gather over the coarse vertex graph, `mid` gives the fine midpoint of every coarse edge
+// rc = mask * P^T rf : gather over the coarse vertex graph, `mid` gives the fine midpoint of every coarse edge.
+// Half-warp per coarse vertex: the lanes take the row's entries (one midpoint each), gather the D components and
+// shuffle-reduce -- two dependent loads per vertex instead of a serial walk over its ~15 neighbours.
 template <int D>
-__global__ void k_restrict(int nvc, const int* __restrict__ rowptr, const int* __restrict__ mid, const int* __restrict__ diagpos,
-                           const unsigned char* __restrict__ dirmask, const double* __restrict__ rf, double* __restrict__ rc) {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvc * D; t += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
-        const int s = rowptr[v], e = rowptr[v + 1], dp = diagpos[v];
-        double half = 0.0;
-        for (int k = s; k < e; ++k)
-            if (k != dp) half += rf[(int64_t)mid[k] * D + c];
-        double val = rf[t] + 0.5 * half;
-        if (dirmask && ((dirmask[v] >> c) & 1)) val = 0.0;
-        rc[t] = val;
+__global__ void __launch_bounds__(256) k_restrict(int nvc, const int* __restrict__ rowptr, const int* __restrict__ mid, const int* __restrict__ diagpos,
+                                                  const unsigned char* __restrict__ dirmask, const double* __restrict__ rf, double* __restrict__ rc) {
+    const int hl = threadIdx.x & 15;
+    const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    const int64_t rounds = (nvc + nhw - 1) / nhw;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t v = hw + it * nhw;
+        const bool on = v < nvc;
+        const int s = on ? rowptr[v] : 0, e = on ? rowptr[v + 1] : 0, dp = on ? diagpos[v] : -1;
+        double acc[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = 0.0;
+        for (int k = s + hl; k < e; k += 16) {
+            if (k == dp) continue;
+            const int64_t m = (int64_t)mid[k] * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] += rf[m + c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (on && hl < D) {
+            double h = acc[0];
+#pragma unroll
+            for (int c = 1; c < D; ++c) h = (hl == c) ? acc[c] : h;
+            double val = rf[v * D + hl] + 0.5 * h;
+            if (dirmask && ((dirmask[v] >> hl) & 1)) val = 0.0;
+            rc[v * D + hl] = val;
+        }
     }
 }
 
@@ -804,15 +826,21 @@ __global__ void k_extract_inverse(int n, const double* __restrict__ M, const int
         Ainv[t] = M[(int64_t)p * 2 * n + n + c] / M[(int64_t)p * 2 * n + k];
     }
 }
-// x0 = scatter(Ainv * gather(b0)) ; Dirichlet dofs: x = b (identity rows).  One warp per free row.
+// x0 = scatter(Ainv * gather(b0)) ; Dirichlet dofs: x = b (identity rows).  The compact right-hand side is staged in
+// shared memory once per block, then one warp per free row streams its row of the inverse with independent loads.
 __global__ void __launch_bounds__(256) k_coarse_solve(int n, int ndof, const double* __restrict__ Ainv, const int* __restrict__ free2dof,
                                                       const int* __restrict__ dof2free, const double* __restrict__ b, double* __restrict__ x) {
+    extern __shared__ double sb[];
+    for (int c = threadIdx.x; c < n; c += blockDim.x) sb[c] = b[free2dof[c]];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp; i < n; i += nwarps) {
+        const double* row = Ainv + i * n;
         double acc = 0.0;
-        for (int c = lane; c < n; c += 32) acc += Ainv[i * n + c] * b[free2dof[c]];
+#pragma unroll 8
+        for (int c = lane; c < n; c += 32) acc += row[c] * sb[c];
         acc = warp_sum(acc);
         if (lane == 0) x[free2dof[i]] = acc;
     }

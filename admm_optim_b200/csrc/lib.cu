@@ -649,7 +649,7 @@ void Gmg::vcycle(int l, const double* b, double* x) {
         const int n = n_free;
         const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
         if (!dom->distributed()) {
-            AB_LAUNCH(ctx, k_coarse_solve, grid, 256, 0, n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+            AB_LAUNCH(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
         } else {   // replicated solve of the global level-0 system (the reference keeps level 0 on one process, 3d_admm.lua:158-161)
             AB_CUDA(cudaMemsetAsync(bg.p, 0, (size_t)n * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, k_coarse_gather, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, b, bg.p);
@@ -666,14 +666,14 @@ void Gmg::vcycle(int l, const double* b, double* x) {
     const int64_t n = (int64_t)Ld.nv * dim, nc = (int64_t)Lc.nv * dim;
     smooth(l, b, x, desc.pre_smooth, true, g.coef_pre);
     spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p);
-    if (dim == 2) AB_LAUNCH(ctx, (k_restrict<2>), ew_grid(ctx, nc), 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
-    else AB_LAUNCH(ctx, (k_restrict<3>), ew_grid(ctx, nc), 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    const int rg = grid_for((int64_t)Lc.nv * 16, 256, ctx->num_sms * 8);
+    if (dim == 2) AB_LAUNCH(ctx, (k_restrict<2>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    else AB_LAUNCH(ctx, (k_restrict<3>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
     vcycle(l - 1, gc.b.p, gc.x.p);
-    // x (+)= P xc ; written to x2 when the post-smoother runs an odd number of steps so that it ends in x
+    // x_out = x + P xc ; written to x2 when the post-smoother runs an odd number of steps so that it ends in x
     double* target = (desc.post_smooth % 2 == 1) ? g.x2.p : x;
-    if (target != x) dev_copy(ctx, n, x, target);
-    if (dim == 2) AB_LAUNCH(ctx, (k_prolong_add<2>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, target);
-    else AB_LAUNCH(ctx, (k_prolong_add<3>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, target);
+    if (dim == 2) AB_LAUNCH(ctx, (k_prolong_add<2>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
+    else AB_LAUNCH(ctx, (k_prolong_add<3>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
     smooth(l, b, x, desc.post_smooth, false, g.coef_post);
 }
 

@@ -107,6 +107,12 @@ class Domain(_Handle):
         return dict(dim=self.level_info(level)["dim"], xyz=lv["xyz"], elems=lv["elems"], vsub=lv["vsub"], esub=esub, sp_edges=se,
                     sp_edges_sub=ses, sp_faces=sf, sp_faces_sub=sfs, subset_names=names)
 
+    def p2p_status(self):
+        """{connected, error}: error != 0 means a bounded spin of the peer-to-peer exchange expired (a peer was lost)."""
+        c, e = C.c_int(), C.c_int()
+        call("ab_domain_p2p_status", self.h, C.byref(c), C.byref(e))
+        return dict(connected=bool(c.value), error=e.value)
+
     def subset_index(self, name):
         out = C.c_int()
         call("ab_domain_subset_index", self.h, name.encode(), C.byref(out))

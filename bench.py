@@ -27,6 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GRID3D = os.path.join(ROOT, "grids", "box_3D_elongated.npz")
 METRIC = "3D ADMM outer iters/s at fixed DoFs"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_bsr_spmv_tma<3,0,0,3> from the committed `ncu --set full`
+# capture (profiles/r01_spmv_tma_raw.csv, numRefs=4, one GPU); other sizes were not captured -> null
+NCU_TRAFFIC_BYTES = {4: 1059398000 + 24325888}
 
 
 def measured_peak():
@@ -287,7 +290,8 @@ def run_b200(args):
         bytes_spmv = spmv_bytes(3, nb, nnzb)
         peak, peak_src = measured_peak()
         ach = bytes_spmv / t_spmv / 1e9
-        roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak, "traffic": None,
+        roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak,
+                "traffic": NCU_TRAFFIC_BYTES.get(args.roofline_refs) if world == 1 else None,
                 "kernel": "k_bsr_spmv_tma<3,0,0,3> (y = A x, BSR 3x3 fp64, TMA-staged tiles)", "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmv // world, "us_per_launch": t_spmv * 1e6,
                 "workload": "box_3D_elongated numRefs=%d: %d block rows, %d blocks (matrix %.2f GB > L2)%s" %
@@ -311,6 +315,9 @@ def run_b200(args):
                  "vcycle_bytes": bv, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(), "solve_converged": bool(ok)}
         del big
 
+    if world > 1:
+        st = prob.dom.p2p_status()
+        assert st["error"] == 0, "peer-to-peer interface exchange timed out (error %d)" % st["error"]
     if rank != 0:
         return
     value = args.steps / (ms_dev * 1e-3)
@@ -341,7 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--refs", type=int, default=2, help="numRefs of the ADMM workload (3d_admm.lua:46 default 2)")
-    ap.add_argument("--roofline-refs", type=int, default=4, help="refinement level of the SpMV / V-cycle roofline leg (0 = skip)")
+    ap.add_argument("--roofline-refs", type=int, default=5, help="refinement level of the SpMV / V-cycle / solve roofline leg (0 = skip); 5 = 20.3 M DoFs, 7.6 GB matrix")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

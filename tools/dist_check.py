@@ -24,6 +24,7 @@ tr = p.run_admm()
 ug.synchronize()
 dt = time.time() - t0
 assert not p.p_solver_failure
+assert p.dom.p2p_status()["error"] == 0
 u_loc = p.u.to_numpy().reshape(-1, dim)
 X_loc = p.dom.get_level(refs, elems=False)["xyz"]
 owned = p.dom._iface[refs]["owned"].astype(bool)
