@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(256) k_gauss_jordan(int n, double* __restrict_
 // rank-K update to the rows it owns.  A pivot that is tiny relative to the largest pivot seen raises *fail = 2 and
 // the host falls back to the partially pivoted k_gauss_jordan.  On exit M = [I | A^-1].
 template <int K>
-__global__ void __launch_bounds__(256) k_gauss_jordan_blocked(int n, double* __restrict__ M, int* __restrict__ pivrow, int* __restrict__ fail) {
+__global__ void __launch_bounds__(1024) k_gauss_jordan_blocked(int n, double* __restrict__ M, int* __restrict__ pivrow, int* __restrict__ fail) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double panel[];                   // K x 2n
     __shared__ int s_bad;

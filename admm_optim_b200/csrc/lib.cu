@@ -504,7 +504,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
             if (!G.force_pivoting && panel_bytes <= 200 * 1024) {      // blocked, unpivoted (fast path; checked in Gmg::setup)
                 static bool attr = false;
                 if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_blocked<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_blocked<KB>, dim3(grid), dim3(256), args, panel_bytes, ctx->stream));
+                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_blocked<KB>, dim3(grid), dim3(1024), args, panel_bytes, ctx->stream));
             } else {
                 AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
             }
