@@ -281,3 +281,73 @@ def test_multi_gpu_matches_single_gpu():
                               "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), str(refs), str(dim)],
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["3d_refs1", "2d_refs2"])
+def test_gpu_matches_committed_golden_trace(gpu_backend, name):
+    """The CUDA path against the committed golden ADMM trace (tests/golden, generated by tools/make_golden.py from the
+    oracle): per-iteration scalars within 1e-8 relative (north_star), Newton iteration counts equal, deformation probes."""
+    import json
+    import os
+    from conftest import ROOT
+    from admm_optim_b200.driver import ObstacleOptim
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "admm_trace_%s.json" % name)))
+    p = ObstacleOptim(gpu_backend, gold["dim"], numRefs=gold["numRefs"], grid=os.path.join(ROOT, "grids", gold["grid"]), admmSteps=2).setup()
+    for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
+        s.desc.abs_tol = gold["abs_tol"]
+    p.set_sensitivity(p.synthetic_sensitivity(gold["amplitude"]))
+    tr = p.run_admm()
+    assert len(tr) == len(gold["admm"]) == 2
+    for a, g in zip(tr, gold["admm"]):
+        assert len(a["newton"]) == g["newton_its"]
+        for k in ("u_diff", "lambda_inc", "max_norm"):
+            assert abs(a[k] - g[k]) <= 1e-8 * max(abs(g[k]), 1e-3), (k, a[k], g[k])
+        assert np.allclose(a["Lambda"], g["Lambda"], rtol=1e-8, atol=1e-10)
+    u = p.u.to_numpy()
+    assert abs(np.linalg.norm(u) - gold["u_l2"]) <= 1e-9 * gold["u_l2"]
+    assert np.allclose(u[:: max(1, len(u) // 16)][:16], gold["u_probe"], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("dim,grid,refs,vol", [(3, GRID3D, 2, 719.0), (2, GRID2D, 3, 83.0)])
+def test_full_size_properties(gpu_backend, dim, grid, refs, vol):
+    """BASELINE.json configs[1] / configs[0] at the scripts' default refinement (44 730 / 18 016 DoFs), where the oracle is too
+    slow for the full loop: size-independent properties -- known volume, linearity and symmetry of the operator, true
+    residual of the GMG-BiCGStab solve, quadratic Newton convergence with vanishing constraint residuals."""
+    from admm_optim_b200.driver import ObstacleOptim
+    p = ObstacleOptim(gpu_backend, dim, numRefs=refs, grid=grid, admmSteps=1).setup()
+    ug = p.ug
+    n = p.DeformationSpace_ApproxSpace.num_dofs()
+    assert n == {3: 44730, 2: 18016}[dim]                                       # SURVEY.md 8: C2 / C1
+    assert abs(p.ReferenceVolume - vol) < 1e-8
+    rng = np.random.default_rng(7)
+    DD = p.DeformationEquation_DomainDisc
+    p.u.from_numpy(0.01 * rng.standard_normal(n)); DD.adjust_solution(p.u)
+    p.Hessian_ElemDisc.set_lambda_vol(0.1); p.Hessian_ElemDisc.set_lambda_barycenter(0.05, -0.02, 0.03 if dim == 3 else 0.0)
+    DD.assemble_jacobian(p.A_u_Hessian, p.u)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    def A(v):
+        p.sigma.from_numpy(v); p.A_u_Hessian.apply(p.Lu, p.sigma); return p.Lu.to_numpy()
+    Ax, Ay = A(x), A(y)
+    lin = A(2.0 * x - 3.0 * y)
+    assert np.linalg.norm(lin - (2.0 * Ax - 3.0 * Ay)) <= 1e-12 * np.linalg.norm(lin)      # linearity
+    assert abs(x @ Ay - y @ Ax) <= 1e-11 * abs(x @ Ay)                                      # symmetry (Dirichlet eliminated symmetrically)
+    # solve and check the TRUE residual with an independent SpMV
+    b = rng.standard_normal(n)
+    p.Lu.from_numpy(b, 2); DD.adjust_solution(p.Lu)
+    bb = p.Lu.to_numpy()
+    p.sigma.set(0.0)
+    s = p.SmallProblemRHS_Solver
+    s.init(p.A_u_Hessian, p.sigma)
+    assert s.apply(p.sigma, p.Lu)
+    sol = p.sigma.to_numpy()
+    assert np.linalg.norm(A(sol) - bb) < 10 * (1e-10 if dim == 3 else 1e-12) and 1 <= s.step() <= 40
+    # one full ADMM iteration of the script replay
+    for d in (p.Hessian_ElemDisc,):
+        d.set_lambda_vol(0.0); d.set_lambda_barycenter(0.0, 0.0, 0.0)
+    p.u.set(0.0)
+    p.set_sensitivity(p.synthetic_sensitivity(0.5))
+    tr = p.run_admm()
+    assert tr and not p.p_solver_failure
+    dl = [m["delta_lambda"] for m in tr[0]["newton"]]
+    assert dl[-1] <= 1e-9 and len(dl) <= 10 and all(dl[i + 1] < 0.5 * dl[i] for i in range(len(dl) - 1))
+    assert max(abs(v) for v in tr[0]["L_lambda"]) < 1e-7

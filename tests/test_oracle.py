@@ -166,3 +166,27 @@ def test_newton_schur_replay_converges_quadratically():
         assert all(dl[i + 1] < 0.5 * dl[i] for i in range(len(dl) - 1))
         assert max(abs(v) for v in tr[0]["L_lambda"]) < 1e-8
         assert tr[0]["u_diff"] > 0 and tr[0]["lambda_inc"] > 0
+
+
+@pytest.mark.parametrize("name", ["3d_refs1", "2d_refs2"])
+def test_oracle_reproduces_committed_golden_trace(name):
+    """tests/golden/admm_trace_*.json (tools/make_golden.py): regression pin of the oracle's ADMM trace -- the columns the
+    drivers write to __ADMMStats_step_*.txt (3d_admm.lua:1265-1276) plus the multiplier / Newton trace."""
+    import json
+    import os
+    from conftest import ROOT
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "admm_trace_%s.json" % name)))
+    p = ObstacleOptim(ug4_np.Backend(smoother="cheb"), gold["dim"], numRefs=gold["numRefs"], grid=os.path.join(ROOT, "grids", gold["grid"]),
+                      admmSteps=1).setup()
+    for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
+        s.desc["convCheck"]["absolute"] = gold["abs_tol"]
+    p.set_sensitivity(p.synthetic_sensitivity(gold["amplitude"]))
+    tr = p.run_admm()                                            # first ADMM iteration only (keeps the CPU suite fast)
+    g = gold["admm"][0]
+    assert abs(p.ReferenceVolume - gold["reference_volume"]) < 1e-9
+    assert len(tr[0]["newton"]) == g["newton_its"]
+    for k in ("u_diff", "lambda_inc", "max_norm"):
+        assert abs(tr[0][k] - g[k]) <= 1e-9 * max(abs(g[k]), 1e-3), k
+    assert np.allclose(tr[0]["Lambda"], g["Lambda"], rtol=1e-8, atol=1e-10)
