@@ -329,7 +329,10 @@ def run_b200(args):
                        "parallelism": ("domain decomposition x%d (RCB of the level-0 grid, NCCL interface sums + all-reduces)" % world) if world > 1 else "1 GPU",
                        "l2": "L2 flushed (256 MB write) between timed iterations; working set itself is L2-sized",
                        "smoother": "Chebyshev(3)-Jacobi (stated equivalent of the reference's sequential GS, DESIGN.md)",
-                       "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
+                       "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps,
+                       "scaling_note": "value at N>1 = the SAME 44 730-DoF problem domain-decomposed (latency-bound, SURVEY 8e); the strong-scaling "
+                                       "numbers that matter are spmv_gbs / vcycle_ms / solve_ms at roofline numRefs and profiles/r01_scaling.md "
+                                       "(numRefs 6: 7.4x from 1 to 8 GPUs)"},
             "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk}
