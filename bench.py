@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 GRID3D = os.path.join(ROOT, "grids", "box_3D_elongated.npz")
+GRID2D = os.path.join(ROOT, "grids", "refined.npz")
 METRIC = "3D ADMM outer iters/s at fixed DoFs"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_bsr_spmv_tma<3,0,0,3> from the committed `ncu --set full`
 # capture (profiles/r01_spmv_tma_raw.csv, numRefs=4, one GPU); other sizes were not captured -> null
@@ -78,16 +79,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def global_counts(refs):
+def global_counts(refs, dim=3):
     """(block rows, blocks) = (V, V + 2E) of every level of the GLOBAL hierarchy from the regular-refinement recurrences
-    V' = V+E, E' = 2E+3F+T, F' = 4F+8T, T' = 8T seeded with the level-0 entity counts of the grid."""
+    V' = V+E, E' = 2E+3F(+T), F' = 4F(+8T), T' = 8T seeded with the level-0 entity counts of the grid."""
     import numpy as np
-    z = np.load(GRID3D)
+    z = np.load(GRID3D if dim == 3 else GRID2D)
     el = z["elems"]
-    V, T = len(z["xyz"]), len(el)
-    edges = np.unique(np.sort(np.concatenate([el[:, [i, j]] for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))]), axis=1), axis=0)
-    faces = np.unique(np.sort(np.concatenate([el[:, list(f)] for f in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))]), axis=1), axis=0)
-    E, F = len(edges), len(faces)
+    V = len(z["xyz"])
+    if dim == 3:
+        T = len(el)
+        edges = np.unique(np.sort(np.concatenate([el[:, [i, j]] for i, j in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))]), axis=1), axis=0)
+        faces = np.unique(np.sort(np.concatenate([el[:, list(f)] for f in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3))]), axis=1), axis=0)
+        E, F = len(edges), len(faces)
+    else:
+        T, F = 0, len(el)
+        E = len(np.unique(np.sort(np.concatenate([el[:, [i, j]] for i, j in ((0, 1), (1, 2), (0, 2))]), axis=1), axis=0))
     out = [(V, V + 2 * E)]
     for _ in range(refs):
         V, E, F, T = V + E, 2 * E + 3 * F + T, 4 * F + 8 * T, 8 * T

@@ -351,3 +351,40 @@ def test_full_size_properties(gpu_backend, dim, grid, refs, vol):
     dl = [m["delta_lambda"] for m in tr[0]["newton"]]
     assert dl[-1] <= 1e-9 and len(dl) <= 10 and all(dl[i + 1] < 0.5 * dl[i] for i in range(len(dl) - 1))
     assert max(abs(v) for v in tr[0]["L_lambda"]) < 1e-7
+
+
+def test_operator_sharing_cache_is_transparent(gpu_backend, monkeypatch):
+    """The six operators of a Newton iteration share one assembly / one GMG setup through the signature cache
+    (DESIGN.md section 5); ADMM_B200_NO_CACHE=1 assembles and sets up each of them -- same iterates either way."""
+    from admm_optim_b200.driver import ObstacleOptim
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADMM_B200_NO_CACHE", flag)
+        p = ObstacleOptim(gpu_backend, 3, numRefs=1, grid=GRID3D, admmSteps=1).setup()
+        p.set_sensitivity(p.synthetic_sensitivity(0.5))
+        tr = p.run_admm()
+        assert tr and not p.p_solver_failure
+        outs.append((p.u.to_numpy(), tr[0]["u_diff"], [n["its"] for n in tr[0]["newton"]]))
+    assert _rel(outs[0][0], outs[1][0]) < 1e-12 and outs[0][2] == outs[1][2]
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_jacobi_smoother_option_matches_oracle(gpu_backend, monkeypatch, dim, grid, refs):
+    """ADMM_B200_SMOOTHER=jacobi (damped point Jacobi, 0.66) against the oracle's 'jac' smoother: same iteration count."""
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    monkeypatch.setenv("ADMM_B200_SMOOTHER", "jacobi")
+    g = ObstacleOptim(gpu_backend, dim, numRefs=refs, grid=grid).setup()
+    o = ObstacleOptim(ug4_np.Backend(smoother="jac"), dim, numRefs=refs, grid=grid).setup()
+    b = np.random.default_rng(11).standard_normal(o.u.v.size)
+    its, sols = [], []
+    for p in (g, o):
+        DD = p.DeformationEquation_DomainDisc
+        DD.assemble_jacobian(p.A_u_Hessian, p.u)
+        p.Lu.from_numpy(b, 2); DD.adjust_solution(p.Lu)
+        p.sigma.set(0.0)
+        s = p.SmallProblemRHS_Solver
+        s.init(p.A_u_Hessian, p.sigma)
+        assert s.apply(p.sigma, p.Lu)
+        its.append(s.step()); sols.append(p.sigma.to_numpy())
+    assert abs(its[0] - its[1]) <= 1 and _rel(sols[0], sols[1]) < 1e-7

@@ -13,6 +13,9 @@ from admm_optim_b200 import ug4
 from admm_optim_b200.driver import ObstacleOptim, linear_solver
 
 mode, refs = sys.argv[1], int(sys.argv[2])
+dim = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+GRID = bench.GRID3D if dim == 3 else bench.GRID2D
+CMP = ["u1", "u2", "u3"][:dim]
 world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 if world > 1:
@@ -31,16 +34,16 @@ def maxtime(t):
     return float(x.item())
 
 t0 = time.time()
-out = {"mode": mode, "numRefs": refs, "n_gpus": world}
+out = {"mode": mode, "numRefs": refs, "n_gpus": world, "dim": dim}
 if mode == "solver":
-    ug.InitUG(3, None)
-    dom = ug.Domain(); ug.LoadDomain(dom, bench.GRID3D)
+    ug.InitUG(dim, None)
+    dom = ug.Domain(); ug.LoadDomain(dom, GRID)
     ug.util.refinement.CreateRegularHierarchy(dom, refs, False, None)
-    DS = ug.ApproximationSpace(dom); DS.add_fct("u1,u2,u3", "Lagrange", 1); DS.init_levels(); DS.init_top_surface()
-    H = ug.DeformationEquation("u1,u2,u3", "outer")
+    DS = ug.ApproximationSpace(dom); DS.add_fct(",".join(CMP), "Lagrange", 1); DS.init_levels(); DS.init_top_surface()
+    H = ug.DeformationEquation(",".join(CMP), "outer")
     Dir = ug.DirichletBoundary()
     for sub in ("inlet", "wall", "outlet"):
-        for c in ("u1", "u2", "u3"): Dir.add(0, c, sub)
+        for c in CMP: Dir.add(0, c, sub)
     DD = ug.DomainDiscretization(DS); DD.add(H); DD.add(Dir)
     A = ug.AssembledLinearOperator(DD)
     x, b, y, u = (ug.GridFunction(DS) for _ in range(4))
@@ -56,24 +59,24 @@ if mode == "solver":
         for _ in range(reps): fn()
         e1.record(stream); e1.synchronize()
         return maxtime(e0.elapsed_time(e1) / reps)
-    levels = bench.global_counts(refs)
+    levels = bench.global_counts(refs, dim)
     nb, nnzb = levels[-1]
     peak, _ = bench.measured_peak()
     t_spmv = timeit(lambda: A.apply(y, x), 10)
-    out.update(dofs=nb * 3, nnzb=nnzb, spmv_ms=t_spmv, spmv_gbs=bench.spmv_bytes(3, nb, nnzb) / t_spmv / 1e6,
-               spmv_frac_per_gpu=bench.spmv_bytes(3, nb, nnzb) / t_spmv / 1e6 / peak / world)
-    s = linear_solver(ug, DD, DS, False, 3)
+    out.update(dofs=nb * dim, nnzb=nnzb, spmv_ms=t_spmv, spmv_gbs=bench.spmv_bytes(dim, nb, nnzb) / t_spmv / 1e6,
+               spmv_frac_per_gpu=bench.spmv_bytes(dim, nb, nnzb) / t_spmv / 1e6 / peak / world)
+    s = linear_solver(ug, DD, DS, False, dim)
     s.desc.verbose = 0
     te = time.time(); s.init(A, x); ug.synchronize(); out["gmg_init_ms"] = maxtime((time.time() - te) * 1e3)
     t_v = timeit(lambda: s.vcycle(y, x), 5)
-    bv = bench.vcycle_bytes(3, levels)
+    bv = bench.vcycle_bytes(dim, levels)
     out.update(vcycle_ms=t_v, vcycle_gbs=bv / t_v / 1e6, vcycle_frac=bv / t_v / 1e6 / peak / world)
     b.from_numpy(np.random.default_rng(7 + rank).standard_normal(n_loc), 2); DD.adjust_solution(b)
     y.set(0.0)
     barrier(); ts = time.perf_counter(); ok = s.apply(y, b); ug.synchronize()
     out.update(solve_ms=maxtime((time.perf_counter() - ts) * 1e3), solve_its=s.step(), solve_ok=bool(ok), solve_defect=s.defect())
 else:
-    p = ObstacleOptim(ug, 3, numRefs=refs, grid=bench.GRID3D, admmSteps=1).setup()
+    p = ObstacleOptim(ug, dim, numRefs=refs, grid=GRID, admmSteps=1).setup()
     out["setup_s"] = maxtime(time.time() - t0)
     p.set_sensitivity(p.synthetic_sensitivity(0.5))
     p.begin_step()
@@ -82,7 +85,7 @@ else:
     ug.synchronize()
     out["admm_iteration_s"] = maxtime(time.perf_counter() - ts)
     assert rec is not None and not p.p_solver_failure
-    out.update(dofs=bench.global_counts(refs)[-1][0] * 3, newton_its=len(rec["newton"]), delta_lambda=[n["delta_lambda"] for n in rec["newton"]],
+    out.update(dofs=bench.global_counts(refs, dim)[-1][0] * dim, newton_its=len(rec["newton"]), delta_lambda=[n["delta_lambda"] for n in rec["newton"]],
                bicgstab_its=[n["its"] for n in rec["newton"]], L_lambda=rec["L_lambda"], Lambda=[float(v) for v in rec["Lambda"]],
                u_diff=rec["u_diff"], lambda_inc=rec["lambda_inc"], reference_volume=p.ReferenceVolume)
     if world > 1:
