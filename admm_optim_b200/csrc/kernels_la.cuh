@@ -446,11 +446,14 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
         }
     } else {
         // ---------------- consumers ----------------
-        // half-warp per block row, lane <-> (block slot, column c) of the block: one x gather and D value loads
-        // (column c of the DxD block, from shared memory) feed D independent accumulators -- no idle work per entry,
-        // no index division; two rows per warp share every instruction.
-        constexpr int BPH = 16 / D;                     // blocks per step of a half-warp (5 for 3x3, 8 for 2x2)
-        const int hl = lane & 15, half = lane >> 4;
+        // HL lanes per block row (half-warp for 3x3 blocks, quarter-warp for 2x2 where rows are ~250 bytes), lane <->
+        // (block slot, column c) of the block: one x gather and D value loads (column c of the DxD block, from shared
+        // memory) feed D independent accumulators -- no idle work per entry, no index division; the 32/HL rows of a warp
+        // share every instruction.
+        constexpr int HL = D == 3 ? 16 : 8;            // lanes per row
+        constexpr int RPW = 32 / HL;                    // rows per warp
+        constexpr int BPH = HL / D;                     // blocks per step of a row group (5 for 3x3, 4 for 2x2)
+        const int hl = lane % HL, half = lane / HL;
         const int lb = hl / D, c = hl - lb * D;
         const bool lane_on = lb < BPH;
         for (int i = 0; i < n_my; ++i) {
@@ -463,12 +466,13 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
             const int* sc = reinterpret_cast<const int*>(sb + T::VALS_B + meta[4]);
             const int* sr = reinterpret_cast<const int*>(sb + T::VALS_B + T::COLS_B + meta[5]);
             const unsigned char* sa = sb + T::VALS_B + T::COLS_B + T::ROWS_B;
-            for (int task = warp; 2 * task < nr; task += NW) {
-                const int lr = 2 * task + half;
+            for (int task = warp; RPW * task < nr; task += NW) {
+                const int lr = RPW * task + half;
                 const bool row_on = lr < nr;
                 const int s = row_on ? sr[lr] - b0 : 0, e = row_on ? sr[lr + 1] - b0 : 0;
-                const int len_other = __shfl_xor_sync(0xffffffffu, e - s, 16);
-                const int len = max(e - s, len_other);                     // warp-uniform trip count
+                int len = e - s;                                           // warp-uniform trip count = longest row of the warp
+#pragma unroll
+                for (int o = 16; o >= HL; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
                 double acc[D];
 #pragma unroll
                 for (int r = 0; r < D; ++r) acc[r] = 0.0;
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
 #pragma unroll
-                    for (int o = 8; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+                    for (int o = HL / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
                 }
                 if (row_on && hl < D) {
                     double v = acc[0];

@@ -372,7 +372,7 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
-            if (dim == 2) spmv_tma_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
             else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
             return;
         case 2:
