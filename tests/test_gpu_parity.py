@@ -365,7 +365,8 @@ def test_operator_sharing_cache_is_transparent(gpu_backend, monkeypatch):
         tr = p.run_admm()
         assert tr and not p.p_solver_failure
         outs.append((p.u.to_numpy(), tr[0]["u_diff"], [n["its"] for n in tr[0]["newton"]]))
-    assert _rel(outs[0][0], outs[1][0]) < 1e-12 and outs[0][2] == outs[1][2]
+    # separately assembled matrices differ in the last bits (atomic summation order) and the solves stop at 1e-10
+    assert _rel(outs[0][0], outs[1][0]) < 1e-9 and outs[0][2] == outs[1][2]
 
 
 @pytest.mark.parametrize("dim,grid,refs", CASES)
