@@ -38,6 +38,10 @@ struct Context {
     int64_t launches = 0;
     int spmv_variant = 0;   // ADMM_B200_SPMV_VARIANT
     int spmv_waves = 8;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
+    bool use_graph = true;  // ADMM_B200_GRAPH: replay the BiCGStab iteration as a CUDA graph (single GPU)
+    bool own_stream = false;
+    bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
+    int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
     unsigned int* d_tickets = nullptr;
@@ -123,6 +127,33 @@ struct DevBuf {
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
         (ctx)->launches++;                                              \
     } while (0)
+
+// Programmatic dependent launch (PDL): the kernels of the V-cycle / BiCGStab chain are a few microseconds each, so the
+// launch latency between two dependent kernels is a large share of the chain.  Launched with the programmatic-stream-
+// serialization attribute (a programmatic edge when captured into a graph), kernel N+1 is scheduled while kernel N still
+// runs; every such kernel calls pdl_prologue() before its first global-memory access: it releases ITS dependents, then
+// blocks until the preceding grid has completed and its writes are visible (griddepcontrol.wait).
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(Context* ctx, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->use_pdl ? 1 : 0;
+    AB_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    ctx->launches++;
+}
+#define AB_LAUNCH_PDL(ctx, kernel, grid, block, smem, ...) ab::launch_pdl((ctx), kernel, (grid), (block), (smem), __VA_ARGS__)
+
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 inline int grid_for(int64_t n, int block, int max_blocks) {
     int64_t g = (n + block - 1) / block;

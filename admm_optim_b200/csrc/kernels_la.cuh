@@ -52,6 +52,7 @@ enum { SC_RHO = 0, SC_RHO_OLD, SC_ALPHA, SC_OMEGA, SC_RV, SC_TS, SC_TT, SC_RR, S
 // p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega)   [BiCGStab]
 __global__ void k_bicg_update_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
                                 double* __restrict__ p) {
+    pdl_prologue();
     const double beta = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
     const double omega = sc[SC_OMEGA];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -60,6 +61,7 @@ __global__ void k_bicg_update_p(int64_t n, const double* __restrict__ sc, const 
 // alpha = rho / <rh,v>;  s = r - alpha v;  reduce |s|^2
 __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
                                                 double* __restrict__ s, double* partials, unsigned int* ticket) {
+    pdl_prologue();
     const double alpha = sc[SC_RHO] / sc[SC_RV];
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ 
 __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* __restrict__ sc, const double* __restrict__ ph, const double* __restrict__ sh,
                                                  const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ rh,
                                                  double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2) {
+    pdl_prologue();
     const double alpha = sc[SC_RHO] / sc[SC_RV];
     const double tt = sc[SC_TT];
     const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* __restrict__
 }
 // bookkeeping between iterations: rho_old = rho; alpha, omega stored; rho = <rh,r>
 __global__ void k_bicg_roll(double* sc, const double* out2) {
+    pdl_prologue();
     const double alpha = sc[SC_RHO] / sc[SC_RV];
     const double tt = sc[SC_TT];
     const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
@@ -170,7 +174,9 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
                                                   const double* __restrict__ vals, const double* __restrict__ x,
                                                   const double* __restrict__ b, double* __restrict__ y,
                                                   const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
-                                                  const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
+                                                  const double* __restrict__ w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
+    pdl_prologue();
+    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
     constexpr int DD = D * D;
     const int lane = threadIdx.x & 31;
     const int gl = lane % LPR;                          // lane within group
@@ -277,7 +283,9 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
                                                        const double* __restrict__ vals, const double* __restrict__ x,
                                                        const double* __restrict__ b, double* __restrict__ y,
                                                        const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
-                                                       const double* __restrict__ w, double* partials, unsigned int* ticket, double* red) {
+                                                       const double* __restrict__ w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
+    pdl_prologue();
+    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
     constexpr int DD = D * D;
     constexpr int BPS = 32 / DD;                        // blocks per step
     const int lane = threadIdx.x & 31;
@@ -381,7 +389,9 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
                                                                  const double* __restrict__ x, const double* __restrict__ b,
                                                                  double* __restrict__ y, const double* __restrict__ dinv,
                                                                  const double* dvec, double* dout, double c1, double c2, const double* __restrict__ w,
-                                                                 double* partials, unsigned int* ticket, double* red) {
+                                                                 double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
+    pdl_prologue();
+    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
     using T = SpmvTma<D>;
     constexpr int DD = T::DD, BPS = 32 / DD, NS = T::NSTAGE, NW = T::NT / 32 - 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -526,7 +536,9 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
 
 // first Chebyshev/Jacobi step from a zero initial guess: d = c2*dinv*b ; x = d   (no matrix pass)
 __global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* __restrict__ b,
-                               double* __restrict__ d, double* __restrict__ x) {
+                               double* __restrict__ d, double* __restrict__ x, const double* __restrict__ cf) {
+    pdl_prologue();
+    if (cf) c2 = cf[1];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double dn = c2 * dinv[i] * b[i];
         d[i] = dn;
@@ -562,6 +574,7 @@ __global__ void __launch_bounds__(256) k_diag_gershgorin(int nb, const int* __re
 template <int D>
 __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, const int* __restrict__ pb,
                               const double* __restrict__ xc, const double* xin, double* xout) {
+    pdl_prologue();
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvf * D; t += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
         double add;
@@ -580,6 +593,7 @@ __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, cons
 template <int D>
 __global__ void __launch_bounds__(256) k_restrict(int nvc, const int* __restrict__ rowptr, const int* __restrict__ mid, const int* __restrict__ diagpos,
                                                   const unsigned char* __restrict__ dirmask, const double* __restrict__ rf, double* __restrict__ rc) {
+    pdl_prologue();
     const int hl = threadIdx.x & 15;
     const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
     const int64_t rounds = (nvc + nhw - 1) / nhw;
@@ -682,7 +696,7 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
 // scatter the BSR level-0 matrix into the augmented dense system [A_ff | I]  (n x 2n, row-major)
 template <int D>
 __global__ void k_bsr_to_dense(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
-                               const int* __restrict__ dof2free, int n, double* __restrict__ M) {
+                               const int* __restrict__ dof2free, int ld, double* __restrict__ M) {
     constexpr int DD = D * D;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)rowptr[nb] * DD; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t blk = t / DD;
@@ -694,7 +708,7 @@ __global__ void k_bsr_to_dense(int nb, const int* __restrict__ rowptr, const int
             if (rowptr[m] <= blk) lo = m; else hi = m - 1;
         }
         const int fi = dof2free[lo * D + r], fj = dof2free[colidx[blk] * D + c];
-        if (fi >= 0 && fj >= 0) M[(int64_t)fi * 2 * n + fj] = vals[t];
+        if (fi >= 0 && fj >= 0) M[(int64_t)fi * ld + fj] = vals[t];
     }
 }
 __global__ void k_dense_identity(int n, double* __restrict__ M) {
@@ -822,6 +836,123 @@ __global__ void __launch_bounds__(1024) k_gauss_jordan_blocked(int n, double* __
     if (blockIdx.x == 0 && tid == 0 && s_bad) *fail = 2;
 }
 
+// Fast path of the coarse inverse: in-place blocked Gauss-Jordan ("sweep") inversion with every row RESIDENT in shared
+// memory.  Row i lives in CTA i % gridDim.x for the whole kernel; per block step of K pivots only the K pivot rows travel
+// (published by their owners into a ping-pong global panel, read back by everybody after ONE grid barrier):
+//     Dinv = T[P,P]^-1                      (K x K, one warp, rows in registers, shuffle broadcasts)
+//     pivot rows   p: T[p,J] = Dinv[p,:] T[P,J],             T[p,P] = Dinv[p,:]
+//     other rows   i: w = T[i,P] Dinv ; T[i,J] -= w T[P,J] ; T[i,P] = -w
+// After ceil(n/K) steps T = A^-1.  No row exchanges (as k_gauss_jordan_blocked); a pivot tiny relative to the largest
+// one seen raises *fail = 2 and the host redoes the setup with the partially pivoted kernel.
+template <int K>
+__global__ void __launch_bounds__(640) k_gauss_jordan_resident(int n, const double* __restrict__ A, double* __restrict__ Ainv, double* panelbuf,
+                                                               int* __restrict__ fail) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm_gj[];
+    __shared__ int s_bad;
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int rmax = (n + G - 1) / G;
+    const int nrows = b < n ? (n - b + G - 1) / G : 0;     // rows b, b+G, b+2G, ...
+    double* rows = sm_gj;                                  // rmax x n
+    double* panel = rows + (size_t)rmax * n;               // K x n
+    double* Dinv = panel + (size_t)K * n;                  // K x K
+    double* w = Dinv + K * K;                              // rmax x K
+    if (tid == 0) s_bad = 0;
+    for (int r = 0; r < nrows; ++r)
+        for (int c = tid; c < n; c += nt) rows[(size_t)r * n + c] = A[(size_t)(b + r * G) * n + c];
+    __syncthreads();
+    // publish the pivot rows of step 0
+    for (int q = 0; q < min(K, n); ++q)
+        if (q % G == b) {
+            const int r = q / G;
+            for (int c = tid; c < n; c += nt) panelbuf[(size_t)q * n + c] = rows[(size_t)r * n + c];
+        }
+    grid.sync();
+    double maxpiv = 0.0;                                   // warp 0 only
+    int step = 0;
+    for (int k0 = 0; k0 < n; k0 += K, ++step) {
+        const int kk = min(K, n - k0);
+        const double* pb = panelbuf + (size_t)(step & 1) * K * n;
+        for (int idx = tid; idx < kk * n; idx += nt) panel[idx] = __ldcg(pb + idx);   // written by other CTAs: read through L2
+        __syncthreads();
+        if (tid < 32) {      // invert the K x K pivot block: lane l holds row l (identity padding beyond kk)
+            const int lane = tid;
+            double d[K];
+#pragma unroll
+            for (int q = 0; q < K; ++q) d[q] = (lane < kk && q < kk) ? panel[(size_t)lane * n + k0 + q] : (q == lane ? 1.0 : 0.0);
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                double pj[K];
+#pragma unroll
+                for (int q = 0; q < K; ++q) pj[q] = __shfl_sync(0xffffffffu, d[q], j);
+                const double piv = pj[j], ap = fabs(piv);
+                if (!(ap > 1e-10 * maxpiv) || !(ap > 0.0)) bad = true;
+                maxpiv = fmax(maxpiv, ap);
+                const double inv = 1.0 / piv;
+                if (lane == j) {
+#pragma unroll
+                    for (int q = 0; q < K; ++q) d[q] = (q == j) ? inv : pj[q] * inv;
+                } else {
+                    const double f = d[j] * inv;
+#pragma unroll
+                    for (int q = 0; q < K; ++q) d[q] = (q == j) ? -f : d[q] - f * pj[q];
+                }
+            }
+            if (lane < K) {
+#pragma unroll
+                for (int q = 0; q < K; ++q) Dinv[lane * K + q] = d[q];
+            }
+            if (bad && lane == 0) s_bad = 1;
+        }
+        __syncthreads();
+        // update coefficients per own row (negated pivot-block rows of Dinv for the pivot rows themselves)
+        for (int idx = tid; idx < nrows * K; idx += nt) {
+            const int r = idx / K, q = idx - r * K, i = b + r * G;
+            double wv = 0.0;
+            if (q < kk) {
+                if (i >= k0 && i < k0 + kk) wv = -Dinv[(i - k0) * K + q];
+                else
+                    for (int q2 = 0; q2 < kk; ++q2) wv += rows[(size_t)r * n + k0 + q2] * Dinv[q2 * K + q];
+            }
+            w[idx] = wv;
+        }
+        __syncthreads();
+        for (int c = tid; c < n; c += nt) {
+            const bool inP = c >= k0 && c < k0 + kk;
+            double pv[K];
+#pragma unroll
+            for (int q = 0; q < K; ++q) pv[q] = (!inP && q < kk) ? panel[(size_t)q * n + c] : 0.0;
+            for (int r = 0; r < nrows; ++r) {
+                const int i = b + r * G;
+                double* row = rows + (size_t)r * n;
+                if (inP) { row[c] = -w[r * K + (c - k0)]; continue; }
+                double v = (i >= k0 && i < k0 + kk) ? 0.0 : row[c];
+#pragma unroll
+                for (int q = 0; q < K; ++q) v -= w[r * K + q] * pv[q];
+                row[c] = v;
+            }
+        }
+        __syncthreads();
+        const int next = k0 + K;
+        if (next < n) {      // owners publish the pivot rows of the next step into the other half of the panel buffer
+            double* nb = panelbuf + (size_t)((step + 1) & 1) * K * n;
+            const int kn = min(K, n - next);
+            for (int q = 0; q < kn; ++q) {
+                const int i = next + q;
+                if (i % G == b) {
+                    const int r = i / G;
+                    for (int c = tid; c < n; c += nt) nb[(size_t)q * n + c] = rows[(size_t)r * n + c];
+                }
+            }
+            grid.sync();
+        }
+    }
+    for (int r = 0; r < nrows; ++r)
+        for (int c = tid; c < n; c += nt) Ainv[(size_t)(b + r * G) * n + c] = rows[(size_t)r * n + c];
+    if (tid == 0 && s_bad) *fail = 2;
+}
+
 // Ainv[k][c] = M[pivrow[k]][n+c] / M[pivrow[k]][k]
 __global__ void k_extract_inverse(int n, const double* __restrict__ M, const int* __restrict__ pivrow, double* __restrict__ Ainv) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)n * n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -834,6 +965,7 @@ __global__ void k_extract_inverse(int n, const double* __restrict__ M, const int
 // shared memory once per block, then one warp per free row streams its row of the inverse with independent loads.
 __global__ void __launch_bounds__(256) k_coarse_solve(int n, int ndof, const double* __restrict__ Ainv, const int* __restrict__ free2dof,
                                                       const int* __restrict__ dof2free, const double* __restrict__ b, double* __restrict__ x) {
+    pdl_prologue();
     extern __shared__ double sb[];
     for (int c = threadIdx.x; c < n; c += blockDim.x) sb[c] = b[free2dof[c]];
     __syncthreads();

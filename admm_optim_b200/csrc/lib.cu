@@ -59,6 +59,7 @@ struct Domain {
     uint64_t coords_version = 1;
     bool host_xyz_stale = false;
     std::vector<std::weak_ptr<MatrixData>> live;   // assembled matrices, for signature sharing
+    std::vector<std::shared_ptr<struct Gmg>> gmg_pool;   // hierarchies are recycled (buffers, BiCGStab workspace, iteration graph)
     // multi-GPU: shared-vertex interfaces per level (host staging until finalize) and the replicated level-0 numbering
     struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
     std::vector<HostIface> host_iface;
@@ -314,13 +315,13 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
 template <int D, int BATCH, int MINB>
 static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
+                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
     constexpr int LPR = D == 3 ? 16 : 8;
     const int64_t groups_per_block = 256 / LPR;
     const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * MINB * ctx->spmv_waves);
     const int g = std::min(std::max(grid, 1), (int)Context::kMaxBlocks);
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    AB_LAUNCH_PDL(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -331,14 +332,12 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
 }
 template <int D, int U>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                            const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
+                            const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
     using T = SpmvTma<D>;
     const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
     do {                                                                                                                              \
-        static bool attr = false;                                                                                                     \
-        if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, MODE, DOTS, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B)); attr = true; } \
-        AB_LAUNCH(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red); \
+        AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf); \
     } while (0)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
@@ -350,11 +349,11 @@ static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals,
 }
 template <int D, int U>
 static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red) {
+                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
     const int64_t want = ((int64_t)L.nv + 7) / 8;        // 8 warps (rows) per CTA
     const int g = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red)
+    AB_LAUNCH_PDL(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -363,25 +362,40 @@ static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals
     else AB_SPMV(2, 0);
 #undef AB_SPMV
 }
+// opt in to the large dynamic shared memory of every TMA SpMV instantiation once, up front (not lazily inside a launch
+// that may be under stream capture)
+template <int D, int U>
+static void spmv_prepare_dim() {
+    using T = SpmvTma<D>;
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 1, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 2, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 1, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 2, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+}
+static void spmv_prepare_kernels() {
+    spmv_prepare_dim<2, 2>();
+    spmv_prepare_dim<3, 3>();
+}
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr,
-                 double* dout = nullptr) {
+                 double* dout = nullptr, const double* cf = nullptr) {
     if (!dout) dout = dvec;
     // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path,
     // 2 = first-generation sub-warp row groups (kept for the comparisons in profiles/)
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
-            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
-            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
             return;
         case 2:
-            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
-            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
             return;
         default:
-            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
-            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red);
+            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
             return;
     }
 }
@@ -395,7 +409,21 @@ struct GmgLevel {
     DevBuf<double> dinv, x, b, r, d, x2, d2;   // d2: second increment buffer (multi-GPU P2P smoother ping-pong)
     double lmax = 0;
     std::vector<std::pair<double, double>> coef_pre, coef_post;   // (c1,c2) per smoothing step
+    const double *cf_pre = nullptr, *cf_post = nullptr;           // the same pairs in device memory (Gmg::coefs): launches stay graph-replayable
     const unsigned char* mask = nullptr;
+};
+
+// BiCGStab work vectors and scalars.  They live with the hierarchy, not with the solver object: the six solvers of one
+// Newton iteration share one hierarchy (operator sharing), so one BiCGStab iteration is captured
+// ONCE into an executable CUDA graph and replayed by all of them (x is copied in and out of the workspace).
+struct KrylovWs {
+    DevBuf<double> r, rh, p, v, s, t, ph, sh, x, sc, out2;
+    cudaGraphExec_t exec = nullptr;        // one full BiCGStab iteration (2 V-cycles, 2 SpMV, recurrences, D2H of the scalars)
+    std::vector<const void*> key;          // every pointer baked into the captured launches
+    int64_t nodes = 0;                     // kernel launches per replay
+    KrylovWs() = default;
+    KrylovWs(const KrylovWs&) = delete;
+    ~KrylovWs() { if (exec) cudaGraphExecDestroy(exec); }
 };
 
 struct Gmg {
@@ -404,14 +432,18 @@ struct Gmg {
     std::vector<GmgLevel> L;
     // coarse level: dense inverse on the free dofs
     int n_free = 0, n0 = 0;
-    DevBuf<double> Ainv, Mwork;
+    DevBuf<double> Ainv, Mwork, gjpanel;
     DevBuf<int> free2dof, dof2free, pivrow, fail;
     bool force_pivoting = false;      // set when the unpivoted blocked elimination met a tiny pivot
     DevBuf<int> dof2gfree;            // multi-GPU: local level-0 dof -> global free-dof index (-1: Dirichlet)
     DevBuf<double> bg, xg;            // global coarse vectors (replicated solve)
+    DevBuf<double> coefs;             // smoother coefficients, [level][pre|post][step][c1,c2]
+    int coef_stride = 0;              // doubles per (level, pre|post) slot
+    std::unique_ptr<KrylovWs> ws;     // single-GPU BiCGStab workspace + iteration graph
+    std::string pool_key;             // descriptor + Dirichlet set (Domain::gmg_pool)
     void setup(const std::shared_ptr<MatrixData>& A);
     void vcycle(int l, const double* b, double* x);
-    void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef);
+    void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf);
     void apply(const double* r, double* z) { vcycle((int)L.size() - 1, r, z); }
 };
 
@@ -450,7 +482,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
         const LevelDev& F = dom->dev[l];
         const LevelDev& C = dom->dev[l - 1];
         GmgLevel& gc = G.L[l - 1];
-        gc.vals_own.alloc((size_t)C.nnzb * DD);
+        if (gc.vals_own.n != (size_t)C.nnzb * DD) gc.vals_own.alloc((size_t)C.nnzb * DD);   // pointers stay put across setups (graph replay)
         gc.vals = gc.vals_own.p;
         const int warps = 8;
         const size_t smem = (size_t)warps * C.maxrow * (DD * sizeof(double) + sizeof(int));
@@ -486,30 +518,47 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
         const LevelDev& L0 = dom->dev[0];
         const int n = G.n_free;
         if (n > 0) {
-            AB_CUDA(cudaMemsetAsync(G.Mwork.p, 0, (size_t)n * 2 * n * sizeof(double), ctx->stream));
+            constexpr int KR = 16;                                 // pivots per barrier of the shared-memory-resident kernel
+            const int grid_r = std::min(ctx->num_sms, n);
+            const int rmax = (n + grid_r - 1) / grid_r;
+            const size_t smem_r = ((size_t)rmax * n + (size_t)KR * n + KR * KR + (size_t)rmax * KR) * sizeof(double);
+            const bool resident = !G.force_pivoting && ctx->coarse_variant == 0 && smem_r <= 200 * 1024;
+            const int ld = resident ? n : 2 * n;                   // resident: A (n x n) in, A^-1 straight into Ainv; otherwise [A | I]
+            AB_CUDA(cudaMemsetAsync(G.Mwork.p, 0, (size_t)n * ld * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, (k_bsr_to_dense<D>), grid_for(L0.nnzb * DD, 256, ctx->num_sms * 8), 256, 0, L0.nv, L0.rowptr.p, L0.colidx.p, G.L[0].vals,
-                      dom->distributed() ? G.dof2gfree.p : G.dof2free.p, n, G.Mwork.p);
+                      dom->distributed() ? G.dof2gfree.p : G.dof2free.p, ld, G.Mwork.p);
             // multi-GPU: the additive level-0 operators are summed into the replicated global coarse matrix
-            if (dom->distributed()) { AB_REQUIRE((int64_t)n * 2 * n < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "coarse matrix too large"); allreduce_dev(ctx, G.Mwork.p, n * 2 * n); }
-            AB_LAUNCH(ctx, k_dense_identity, grid_for(n, 256, 64), 256, 0, n, G.Mwork.p);
+            if (dom->distributed()) { AB_REQUIRE((int64_t)n * ld < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "coarse matrix too large"); allreduce_dev(ctx, G.Mwork.p, n * ld); }
             AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
             int nn = n;
             double* M = G.Mwork.p;
             int* piv = G.pivrow.p;
             int* fail = G.fail.p;
-            void* args[] = {&nn, &M, &piv, &fail};
-            int grid = std::min(ctx->num_sms, n);
-            constexpr int KB = 8;
-            const size_t panel_bytes = (size_t)KB * 2 * n * sizeof(double);
-            if (!G.force_pivoting && panel_bytes <= 200 * 1024) {      // blocked, unpivoted (fast path; checked in Gmg::setup)
+            if (resident) {
                 static bool attr = false;
-                if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_blocked<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_blocked<KB>, dim3(grid), dim3(1024), args, panel_bytes, ctx->stream));
+                if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_resident<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+                if (G.gjpanel.n < (size_t)2 * KR * n) G.gjpanel.alloc((size_t)2 * KR * n);
+                double* ainv = G.Ainv.p;
+                double* pbuf = G.gjpanel.p;
+                void* rargs[] = {&nn, &M, &ainv, &pbuf, &fail};
+                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_resident<KR>, dim3(grid_r), dim3(640), rargs, smem_r, ctx->stream));
+                ctx->launches++;
             } else {
-                AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
+                AB_LAUNCH(ctx, k_dense_identity, grid_for(n, 256, 64), 256, 0, n, G.Mwork.p);
+                void* args[] = {&nn, &M, &piv, &fail};
+                int grid = std::min(ctx->num_sms, n);
+                constexpr int KB = 8;
+                const size_t panel_bytes = (size_t)KB * 2 * n * sizeof(double);
+                if (!G.force_pivoting && panel_bytes <= 200 * 1024) {      // blocked, unpivoted, rows in global memory
+                    static bool attr = false;
+                    if (!attr) { AB_CUDA(cudaFuncSetAttribute(k_gauss_jordan_blocked<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+                    AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan_blocked<KB>, dim3(grid), dim3(1024), args, panel_bytes, ctx->stream));
+                } else {
+                    AB_CUDA(cudaLaunchCooperativeKernel((void*)k_gauss_jordan, dim3(grid), dim3(256), args, (size_t)n, ctx->stream));
+                }
+                ctx->launches++;
+                AB_LAUNCH(ctx, k_extract_inverse, grid_for((int64_t)n * n, 256, ctx->num_sms * 8), 256, 0, n, G.Mwork.p, G.pivrow.p, G.Ainv.p);
             }
-            ctx->launches++;
-            AB_LAUNCH(ctx, k_extract_inverse, grid_for((int64_t)n * n, 256, ctx->num_sms * 8), 256, 0, n, G.Mwork.p, G.pivrow.p, G.Ainv.p);
         }
     }
 }
@@ -565,6 +614,8 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
         if (n_free) { Ainv.alloc((size_t)n_free * n_free); Mwork.alloc((size_t)n_free * 2 * n_free); }
         pivrow.alloc(std::max(n_free, 1));
         fail.alloc(1);
+        coef_stride = 2 * std::max(1, std::max(desc.pre_smooth, desc.post_smooth));
+        coefs.alloc((size_t)(top + 1) * 2 * coef_stride);
     }
     for (int l = 0; l <= top; ++l) L[l].mask = A->dd ? A->dd->mask(l) : nullptr;
     L[top].vals = A->vals.p;
@@ -573,11 +624,19 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     if (top >= 1) {
         std::vector<double> lm(top + 1, 0.0);
         read_back(ctx, ctx->d_results + 1, top, lm.data() + 1);
+        std::vector<double> hc((size_t)(top + 1) * 2 * coef_stride, 0.0);
         for (int l = 1; l <= top; ++l) {
             L[l].lmax = lm[l];
             smoother_coefs(desc, lm[l], desc.pre_smooth, L[l].coef_pre);
             smoother_coefs(desc, lm[l], desc.post_smooth, L[l].coef_post);
+            double* hp = hc.data() + (size_t)l * 2 * coef_stride;
+            for (size_t k = 0; k < L[l].coef_pre.size(); ++k) { hp[2 * k] = L[l].coef_pre[k].first; hp[2 * k + 1] = L[l].coef_pre[k].second; }
+            for (size_t k = 0; k < L[l].coef_post.size(); ++k) { hp[coef_stride + 2 * k] = L[l].coef_post[k].first; hp[coef_stride + 2 * k + 1] = L[l].coef_post[k].second; }
+            L[l].cf_pre = coefs.p + (size_t)l * 2 * coef_stride;
+            L[l].cf_post = L[l].cf_pre + coef_stride;
         }
+        // pageable source: the call returns once the buffer is staged, so `hc` may go out of scope
+        AB_CUDA(cudaMemcpyAsync(coefs.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     int hfail = 0;
     AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -591,7 +650,7 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
 }
 
-void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef) {
+void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf) {
     if (nu <= 0) { if (zero_guess) dev_fill(dom->ctx, x, (int64_t)dom->dev[l].nv * dom->dim(), 0.0); return; }
     Context* ctx = dom->ctx;
     const LevelDev& Ld = dom->dev[l];
@@ -608,7 +667,7 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     int dcur = 0;
     if (zero_guess) {
         cur = ((nu - 1) % 2 == 0) ? 0 : 1;
-        AB_LAUNCH(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur]);
+        AB_LAUNCH_PDL(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur], cf);
         if (p2p) {          // d = c2 D^-1 b is additive at the interfaces: sum it, x = d there -- one fused launch
             smooth_exchange_p2p(dom, l, D, 0.0, nullptr, dbuf[dcur], nullptr, bufs[cur]);
         } else if (dist) {
@@ -631,7 +690,7 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
             dcur = 1 - dcur;
         } else {
             if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1 != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
-            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2, nullptr, nullptr, nullptr, cf ? cf + 2 * k : nullptr);
             if (dist) {
                 AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1, I->save.p, g.d.p);
                 exchange_sum(dom, l, g.d.p, D);
@@ -649,7 +708,7 @@ void Gmg::vcycle(int l, const double* b, double* x) {
         const int n = n_free;
         const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
         if (!dom->distributed()) {
-            AB_LAUNCH(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+            AB_LAUNCH_PDL(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
         } else {   // replicated solve of the global level-0 system (the reference keeps level 0 on one process, 3d_admm.lua:158-161)
             AB_CUDA(cudaMemsetAsync(bg.p, 0, (size_t)n * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, k_coarse_gather, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, b, bg.p);
@@ -664,17 +723,17 @@ void Gmg::vcycle(int l, const double* b, double* x) {
     GmgLevel& g = L[l];
     GmgLevel& gc = L[l - 1];
     const int64_t n = (int64_t)Ld.nv * dim, nc = (int64_t)Lc.nv * dim;
-    smooth(l, b, x, desc.pre_smooth, true, g.coef_pre);
+    smooth(l, b, x, desc.pre_smooth, true, g.coef_pre, g.cf_pre);
     spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p);
     const int rg = grid_for((int64_t)Lc.nv * 16, 256, ctx->num_sms * 8);
-    if (dim == 2) AB_LAUNCH(ctx, (k_restrict<2>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
-    else AB_LAUNCH(ctx, (k_restrict<3>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    if (dim == 2) AB_LAUNCH_PDL(ctx, (k_restrict<2>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
+    else AB_LAUNCH_PDL(ctx, (k_restrict<3>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
     vcycle(l - 1, gc.b.p, gc.x.p);
     // x_out = x + P xc ; written to x2 when the post-smoother runs an odd number of steps so that it ends in x
     double* target = (desc.post_smooth % 2 == 1) ? g.x2.p : x;
-    if (dim == 2) AB_LAUNCH(ctx, (k_prolong_add<2>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
-    else AB_LAUNCH(ctx, (k_prolong_add<3>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
-    smooth(l, b, x, desc.post_smooth, false, g.coef_post);
+    if (dim == 2) AB_LAUNCH_PDL(ctx, (k_prolong_add<2>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
+    else AB_LAUNCH_PDL(ctx, (k_prolong_add<3>), ew_grid(ctx, n), 256, 0, Lc.nv, Ld.nv, Ld.pa.p, Ld.pb.p, gc.x.p, (const double*)x, target);
+    smooth(l, b, x, desc.post_smooth, false, g.coef_post, g.cf_post);
 }
 
 // =============================================================================================
@@ -697,9 +756,9 @@ struct Solver {
 void Solver::ensure_vectors() {
     const int64_t n = sp->ndofs;
     if (sc.n == 0) { sc.alloc(SC_COUNT + 3); out2.alloc(2); }
-    if (type == 1 && r.n == 0) {
+    if (type == 1 && r.n == 0 && sp->dom->distributed()) {   // single GPU: the work vectors live in the shared hierarchy (KrylovWs)
         r.alloc(n); rh.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); t.alloc(n); ph.alloc(n); sh.alloc(n);
-        if (sp->dom->distributed()) rc.alloc(n);
+        rc.alloc(n);
     }
     if (type == 2 && r.n == 0) { r.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); }
 }
@@ -713,9 +772,27 @@ static void solver_init(Solver* S, Operator* A) {
         const std::string key = gmg_key(S->desc);
         auto it = A->data->gmg.find(key);
         if (it != A->data->gmg.end() && !env_flag("ADMM_B200_NO_CACHE")) { S->gmg = it->second; return; }
-        // reuse this solver's own hierarchy buffers when nobody else holds them
-        std::shared_ptr<Gmg> G = (S->gmg && S->gmg.use_count() == 1) ? S->gmg : std::make_shared<Gmg>();
-        G->dom = S->sp->dom;
+        // recycle an idle hierarchy of this domain (same descriptor and Dirichlet set): its level buffers, BiCGStab workspace
+        // and captured iteration graph keep their addresses, so in steady state nothing is reallocated or re-instantiated
+        std::string pool_key = key + "|";
+        if (A->data->dd) {
+            auto dir = A->data->dd->dir;
+            std::sort(dir.begin(), dir.end());
+            for (auto& e : dir) pool_key += std::to_string(e.first) + "." + std::to_string(e.second) + ",";
+        }
+        Domain* dom = S->sp->dom;
+        S->gmg.reset();
+        std::shared_ptr<Gmg> G;
+        for (auto& g : dom->gmg_pool)
+            if (g.use_count() == 1 && g->pool_key == pool_key) { G = g; break; }
+        if (!G) {
+            auto& pool = dom->gmg_pool;
+            if (pool.size() >= 8) pool.erase(std::remove_if(pool.begin(), pool.end(), [](const std::shared_ptr<Gmg>& g) { return g.use_count() == 1; }), pool.end());
+            G = std::make_shared<Gmg>();
+            G->pool_key = pool_key;
+            pool.push_back(G);
+        }
+        G->dom = dom;
         G->desc = S->desc;
         G->setup(A->data);
         A->data->gmg[key] = G;
@@ -725,6 +802,58 @@ static void solver_init(Solver* S, Operator* A) {
     }
 }
 
+// one full BiCGStab iteration on the workspace vectors; ends with the D2H copy of the scalars the ConvCheck reads
+static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    double* sc = W.sc.p;
+    AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p);
+    G->apply(W.p.p, W.ph.p);
+    spmv(ctx, dim, Lt, Av, 0, 1, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, W.rh.p, sc + SC_RV);
+    AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, ctx->d_partials, ctx->d_tickets);
+    G->apply(W.s.p, W.sh.p);
+    spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS);
+    AB_LAUNCH_PDL(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
+              ctx->d_tickets, W.out2.p);
+    AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, W.out2.p);
+    AB_CUDA(cudaMemcpyAsync(ctx->h_results, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+}
+
+// (re)capture the iteration when any pointer baked into its launches changed since the last capture
+static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    std::vector<const void*> key;
+    key.push_back(Av);
+    key.push_back(G->Ainv.p);
+    key.push_back(G->coefs.p);
+    key.push_back((const void*)(intptr_t)(G->n_free * 16 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
+    for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
+    if (W.exec && W.key == key) return;
+    TraceTimer tt(ctx->stream, "bicgstab: graph capture");
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = ctx->launches;
+    AB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    try {
+        bicg_iteration(ctx, dim, Lt, Av, G, W, n);
+    } catch (...) {
+        cudaStreamEndCapture(ctx->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        ctx->launches = l0;
+        throw;
+    }
+    AB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    W.nodes = ctx->launches - l0;
+    ctx->launches = l0;                      // capturing launches nothing
+    if (W.exec) {                            // same topology, new pointers: update in place (cheaper than instantiating)
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(W.exec, graph, &info) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphExecDestroy(W.exec);
+            W.exec = nullptr;
+        }
+    }
+    if (!W.exec) AB_CUDA(cudaGraphInstantiate(&W.exec, graph, 0));
+    AB_CUDA(cudaGraphDestroy(graph));
+    W.key = key;
+}
+
 static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) {
     Domain* dom = S->sp->dom;
     Context* ctx = dom->ctx;
@@ -732,49 +861,59 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     const LevelDev& Lt = dom->dev[dom->top()];
     const int64_t n = S->sp->ndofs;
     const double* Av = S->A->vals.p;
-    double* sc = S->sc.p;
+    Gmg* G = S->gmg.get();
+    if (!G->ws) G->ws = std::make_unique<KrylovWs>();
+    KrylovWs& W = *G->ws;
+    if (W.r.n != (size_t)n) {
+        W.r.alloc(n); W.rh.alloc(n); W.p.alloc(n); W.v.alloc(n); W.s.alloc(n); W.t.alloc(n); W.ph.alloc(n); W.sh.alloc(n); W.x.alloc(n);
+        W.sc.alloc(SC_COUNT + 3); W.out2.alloc(2);
+        W.key.clear();
+    }
+    double* sc = W.sc.p;
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
     // r = b - A x ; rh = r ; rho = <r,r>
-    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);
-    dev_copy(ctx, n, S->r.p, S->rh.p);
+    dev_copy(ctx, n, x->d.p, W.x.p);
+    spmv(ctx, dim, Lt, Av, 1, 0, W.x.p, b->d.p, W.r.p);
+    dev_copy(ctx, n, W.r.p, W.rh.p);
     {
         const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        const double* xs[1] = {S->r.p};
-        dev_dots(ctx, n, 1, xs, S->r.p, sc + SC_RR);
+        const double* xs[1] = {W.r.p};
+        dev_dots(ctx, n, 1, xs, W.r.p, sc + SC_RR);
         AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    dev_fill(ctx, S->p.p, n, 0.0);
-    dev_fill(ctx, S->v.p, n, 0.0);
+    dev_fill(ctx, W.p.p, n, 0.0);
+    dev_fill(ctx, W.v.p, n, 0.0);
     read_back(ctx, sc, SC_COUNT, h);
     const double rr0 = h[SC_RR];
     double rr = rr0;
     bool ok = rr < tol2;
     int it = 0;
     if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
+    const bool graph = ctx->use_graph && ctx->stream != nullptr;
+    if (graph && !ok && S->desc.max_iterations > 0) ensure_iteration_graph(ctx, dim, Lt, Av, G, W, n);
     while (!ok && it < S->desc.max_iterations) {
         ++it;
-        AB_LAUNCH(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
-        S->gmg->apply(S->p.p, S->ph.p);
-        spmv(ctx, dim, Lt, Av, 0, 1, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, S->rh.p, sc + SC_RV);
-        AB_LAUNCH(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);
-        S->gmg->apply(S->s.p, S->sh.p);
-        spmv(ctx, dim, Lt, Av, 0, 2, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, S->s.p, sc + SC_TS);
-        AB_LAUNCH(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
-                  ctx->d_tickets, S->out2.p);
-        AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
-        read_back(ctx, sc, SC_COUNT, h);
+        if (graph) {
+            AB_CUDA(cudaGraphLaunch(W.exec, ctx->stream));
+            ctx->launches += W.nodes;
+        } else {
+            bicg_iteration(ctx, dim, Lt, Av, G, W, n);
+        }
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < SC_COUNT; ++i) h[i] = ctx->h_results[i];
         rr = h[SC_RR];
         if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
         if (!(rr == rr) || std::isinf(rr)) break;                       // NaN/Inf: breakdown
         if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
         if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;               // breakdown
     }
+    if (it > 0) dev_copy(ctx, n, W.x.p, x->d.p);
     x->touch();
     S->last_steps = it;
     S->last_defect = std::sqrt(rr);
-    if (return_defect) { dev_copy(ctx, n, S->r.p, b->d.p); b->touch(); }
+    if (return_defect) { dev_copy(ctx, n, W.r.p, b->d.p); b->touch(); }
     return ok;
 }
 
@@ -826,22 +965,22 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
     if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
     while (!ok && it < S->desc.max_iterations) {
         ++it;
-        AB_LAUNCH(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
+        AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
         to_unique(dom, n, S->p.p, uniq);
         S->gmg->apply(uniq, S->ph.p);
         spmv(ctx, dim, Lt, Av, 0, 0, S->ph.p, nullptr, S->v.p);
         exchange_sum(dom, top, S->v.p, dim);
         dot_owned(dom, n, S->rh.p, nullptr, S->v.p, 1, sc + SC_RV);
-        AB_LAUNCH(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
+        AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
         to_unique(dom, n, S->s.p, uniq);
         S->gmg->apply(uniq, S->sh.p);
         spmv(ctx, dim, Lt, Av, 0, 0, S->sh.p, nullptr, S->t.p);
         exchange_sum(dom, top, S->t.p, dim);
         dot_owned(dom, n, S->s.p, S->t.p, S->t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
-        AB_LAUNCH(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
+        AB_LAUNCH_PDL(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
                   ctx->d_tickets, S->out2.p);                                    // local sums overwritten below
         dot_owned(dom, n, S->r.p, S->rh.p, S->r.p, 2, S->out2.p);               // <r,r>, <rh,r>
-        AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
+        AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
         read_back(ctx, sc, SC_COUNT, h);
         rr = h[SC_RR];
         if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
@@ -1096,6 +1235,14 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     auto* c = new ab_context();
     c->device = device;
     c->stream = (cudaStream_t)stream;
+    if (!c->stream) {   // the legacy default stream cannot be captured into a graph: use an own blocking stream (still ordered with it)
+        AB_CUDA(cudaStreamCreate(&c->stream));
+        c->own_stream = true;
+    }
+    if (const char* v = getenv("ADMM_B200_GRAPH")) c->use_graph = atoi(v) != 0;
+    if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
+    spmv_prepare_kernels();
     cudaDeviceProp prop;
     AB_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
@@ -1114,6 +1261,7 @@ int ab_context_destroy(ab_context* ctx) {
     if (!ctx) return AB_OK;
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_tickets); cudaFree(ctx->d_results); cudaFreeHost(ctx->h_results);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     AB_CATCH
 }
@@ -1132,6 +1280,9 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     const std::string k = key;
     if (k == "spmv_variant") ctx->spmv_variant = value;
     else if (k == "spmv_waves") ctx->spmv_waves = std::max(1, value);
+    else if (k == "graph") ctx->use_graph = value != 0;
+    else if (k == "coarse_variant") ctx->coarse_variant = value;
+    else if (k == "pdl") ctx->use_pdl = value != 0;
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }

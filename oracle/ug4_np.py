@@ -315,6 +315,11 @@ class BiCGStabGMG:
     def defect(self):
         return self.last_defect
 
+    def vcycle(self, z, r):
+        """z = one V-cycle applied to r (the preconditioner alone; mirrors ab_solver_vcycle of the CUDA library)."""
+        z.v[:] = self.gmg.apply(r.v)
+        z.storage = PST_CONSISTENT
+
 
 class _NS:
     pass

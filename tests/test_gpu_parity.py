@@ -245,6 +245,44 @@ def test_transform_domain_and_cache_invalidation(gpu_backend):
     vol = [p.ug.VolumeDefect(p.u_zeros, 0.0, "outer", p.ucmps, 4, False, 1, False) for p in (g, o)]
     assert abs(vol[0] - vol[1]) < 1e-10
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_coarse_inverse_variants_agree(gpu_backend, monkeypatch, dim, grid, refs):
+    """Shared-memory-resident blocked Gauss-Jordan (default) vs the global-memory blocked kernel: same V-cycle to
+    rounding, and the V-cycle equals the oracle's (exact sparse-LU base solve) -- pins the coarse inverse directly."""
+    monkeypatch.setenv("ADMM_B200_NO_CACHE", "1")
+    g, o = _pair(gpu_backend, dim, grid, refs)
+    _seed_state(g, o, amp=0.01)
+    b = np.random.default_rng(11).standard_normal(o.u.v.size)
+    zs = []
+    try:
+        for variant in (0, 1):
+            gpu_backend.set_tuning("coarse_variant", variant)
+            g.Hessian_ElemDisc.set_lambda_vol(0.2)
+            DD = g.DeformationEquation_DomainDisc
+            DD.assemble_jacobian(g.A_u_Hessian, g.u)
+            g.Lu.from_numpy(b, 2)
+            DD.adjust_solution(g.Lu)
+            s = g.SmallProblemRHS_Solver
+            s.init(g.A_u_Hessian, g.sigma)
+            s.vcycle(g.sigma, g.Lu)
+            zs.append(g.sigma.to_numpy())
+    finally:
+        gpu_backend.set_tuning("coarse_variant", 0)
+    assert _rel(zs[0], zs[1]) < 1e-10
+    # oracle V-cycle with the same smoother and an exact base solve
+    o.Hessian_ElemDisc.set_lambda_vol(0.2)
+    DDo = o.DeformationEquation_DomainDisc
+    DDo.assemble_jacobian(o.A_u_Hessian, o.u)
+    o.Lu.from_numpy(b, 2)
+    DDo.adjust_solution(o.Lu)
+    so = o.SmallProblemRHS_Solver
+    so.init(o.A_u_Hessian, o.sigma)
+    if hasattr(so, "vcycle"):
+        so.vcycle(o.sigma, o.Lu)
+        assert _rel(zs[0], o.sigma.to_numpy()) < 1e-9
+
+
 
 def test_blocked_coarse_inverse_matches_pivoted(gpu_backend, monkeypatch):
     """The unpivoted blocked Gauss-Jordan (fast path) and the partially pivoted kernel give the same V-cycle."""
