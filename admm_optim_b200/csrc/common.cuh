@@ -150,9 +150,26 @@ inline void launch_pdl(Context* ctx, void (*kernel)(KArgs...), int grid, int blo
 }
 #define AB_LAUNCH_PDL(ctx, kernel, grid, block, smem, ...) ab::launch_pdl((ctx), kernel, (grid), (block), (smem), __VA_ARGS__)
 
+// Data that no kernel of the chain writes (matrix values, patterns, transfer tables, the coarse inverse: all final
+// before the stream synchronisation that ends every setup) may be fetched BEFORE pdl_wait(): that part of a kernel's
+// latency then overlaps the tail of its predecessor.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_trigger();
+    pdl_wait();
+}
+// Loads of static data that must be ISSUED before pdl_wait(): volatile asm keeps its program order relative to the
+// griddepcontrol instructions (the compiler otherwise sinks or hoists LDG.CONSTANT loads freely across them).
+__device__ __forceinline__ double ld_static(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_static(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
 
 inline int grid_for(int64_t n, int block, int max_blocks) {
@@ -179,8 +196,10 @@ __device__ __forceinline__ double warp_max(double v) {
 // Reduce NV per-thread values over the whole grid (block size: multiple of 32, <= 1024). OP: 0 = sum, 1 = max.
 // Results are written to out[0..NV) by the last block to finish, combining the per-block partials in block
 // order (bitwise reproducible for a fixed launch configuration).
+// Returns true in every thread of the block that finished last (block-uniform), e.g. to append a scalar epilogue
+// (after a __syncthreads(): out[] is written by lane 0 of warps 0..NV-1).
 template <int NV, int OP>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* __restrict__ ticket,
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* __restrict__ ticket,
                                             double* __restrict__ out) {
     __shared__ double sm[NV][32];
     __shared__ bool is_last;
@@ -216,6 +235,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict_
         }
         if (threadIdx.x == 0) *ticket = 0u;
     }
+    return is_last;
 }
 
 // ---------------------------------------------------------------------------------------------

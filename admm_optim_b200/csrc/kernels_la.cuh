@@ -9,6 +9,10 @@
 namespace ab {
 namespace cg = cooperative_groups;
 
+// PDL rule (common.cuh): in a kernel launched with AB_LAUNCH_PDL, pointers to data written by preceding kernels of the chain
+// are NOT `const __restrict__`: nvcc turns such loads into LDG.CONSTANT and is then free to hoist them above the
+// griddepcontrol.wait (observed in SASS).  Only data that is static during a solve keeps the qualifier.
+
 // ---------------------------------------------------------------------------------------------
 // BLAS-1
 // ---------------------------------------------------------------------------------------------
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(256) k_dot_multi(int64_t n, const double* x0, 
 enum { SC_RHO = 0, SC_RHO_OLD, SC_ALPHA, SC_OMEGA, SC_RV, SC_TS, SC_TT, SC_RR, SC_SS, SC_BETA, SC_PQ, SC_RZ, SC_RZ_OLD, SC_COUNT };
 
 // p = r + beta (p - omega v),  beta = (rho/rho_old)(alpha/omega)   [BiCGStab]
-__global__ void k_bicg_update_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
+__global__ void k_bicg_update_p(int64_t n, const double* sc, const double* r, const double* v,
                                 double* __restrict__ p) {
     pdl_prologue();
     const double beta = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
@@ -59,7 +63,7 @@ __global__ void k_bicg_update_p(int64_t n, const double* __restrict__ sc, const 
         p[i] = r[i] + beta * (p[i] - omega * v[i]);
 }
 // alpha = rho / <rh,v>;  s = r - alpha v;  reduce |s|^2
-__global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v,
+__global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* r, const double* v,
                                                 double* __restrict__ s, double* partials, unsigned int* ticket) {
     pdl_prologue();
     const double alpha = sc[SC_RHO] / sc[SC_RV];
@@ -71,12 +75,44 @@ __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ 
     }
     grid_reduce<1, 0>(acc, partials, ticket, sc + SC_SS);
 }
-// omega = <t,s>/<t,t>; x += alpha ph + omega sh; r = s - omega t; reduce |r|^2 and <rh,r> (next rho)
-__global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* __restrict__ sc, const double* __restrict__ ph, const double* __restrict__ sh,
-                                                 const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ rh,
+// Fused with the first smoothing step of the V-cycle that follows (zero initial guess: d = c2 D^-1 rhs, x = d):
+//   FIRST = 0:  p = r + beta (p - omega v)   ; d = c2 dinv p ; x = d
+//   FIRST = 1:  s = r - alpha v              ; d = c2 dinv s ; x = d      (|s|^2 is not needed by the recurrence)
+// identical arithmetic to k_bicg_update_p / k_bicg_s followed by k_smooth_first, one pass and one launch less each.
+template <int FIRST>
+__global__ void __launch_bounds__(256) k_bicg_fused_first(int64_t n, const double* sc, const double* r, const double* v, double* pv,
+                                                          const double* __restrict__ dinv, const double* __restrict__ cf, double* d, double* x) {
+    pdl_trigger();
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    const double c2 = ld_static(cf + 1);                       // static during a solve: fetched before the dependency wait
+    double di = i0 < n ? ld_static(dinv + i0) : 0.0;
+    pdl_wait();
+    double a, b;                                               // FIRST = 0: pn = r + a (pv - b v);  FIRST = 1: s = r - a v
+    if (FIRST == 0) {
+        a = (sc[SC_RHO] / sc[SC_RHO_OLD]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
+        b = sc[SC_OMEGA];
+    } else {
+        a = sc[SC_RHO] / sc[SC_RV];
+        b = 0.0;
+    }
+    for (int64_t i = i0; i < n; i += stride) {
+        if (i != i0) di = dinv[i];
+        const double pn = FIRST == 0 ? r[i] + a * (pv[i] - b * v[i]) : r[i] - a * v[i];
+        pv[i] = pn;
+        const double dn = c2 * di * pn;
+        d[i] = dn;
+        x[i] = dn;
+    }
+}
+// omega = <t,s>/<t,t>; x += alpha ph + omega sh; r = s - omega t; reduce |r|^2 and <rh,r> (next rho).
+// ROLL: the block that finishes last also does the bookkeeping of k_bicg_roll (one launch less per iteration).
+template <int ROLL>
+__global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* sc, const double* ph, const double* sh,
+                                                 const double* s, const double* t, const double* rh,
                                                  double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2) {
     pdl_prologue();
-    const double alpha = sc[SC_RHO] / sc[SC_RV];
+    const double rho = sc[SC_RHO];
+    const double alpha = rho / sc[SC_RV];
     const double tt = sc[SC_TT];
     const double omega = tt > 0.0 ? sc[SC_TS] / tt : 0.0;
     double acc[2] = {0.0, 0.0};
@@ -87,7 +123,17 @@ __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* __restrict__
         acc[0] += ri * ri;
         acc[1] += rh[i] * ri;
     }
-    grid_reduce<2, 0>(acc, partials, ticket, out2);   // out2[0] = |r|^2, out2[1] = <rh,r>
+    const bool last = grid_reduce<2, 0>(acc, partials, ticket, out2);   // out2[0] = |r|^2, out2[1] = <rh,r>
+    if (ROLL && last) {          // every other block read the scalars before it took its ticket
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sc[SC_RHO_OLD] = rho;
+            sc[SC_ALPHA] = alpha;
+            sc[SC_OMEGA] = omega;
+            sc[SC_RR] = out2[0];
+            sc[SC_RHO] = out2[1];
+        }
+    }
 }
 // bookkeeping between iterations: rho_old = rho; alpha, omega stored; rho = <rh,r>
 __global__ void k_bicg_roll(double* sc, const double* out2) {
@@ -171,10 +217,10 @@ __device__ __forceinline__ double ld_stream(const double* p) {
 
 template <int D, int LPR, int MODE, int DOTS, int BATCH = D * D, int MINB = 3>
 __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                  const double* __restrict__ vals, const double* __restrict__ x,
-                                                  const double* __restrict__ b, double* __restrict__ y,
+                                                  const double* __restrict__ vals, const double* x,
+                                                  const double* b, double* __restrict__ y,
                                                   const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
-                                                  const double* __restrict__ w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
+                                                  const double* w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf, int prefetch) {
     pdl_prologue();
     if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
     constexpr int DD = D * D;
@@ -234,7 +280,7 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
                     const int r = wq / D;
                     const int c = wq - r * D;
                     const int col = __shfl_sync(gmask, mycol, gbase + blk);
-                    const double xv = (it0 + j < DD && k < nent) ? __ldg(x + (unsigned)(col * D + c)) : 0.0;
+                    const double xv = (it0 + j < DD && k < nent) ? x[(unsigned)(col * D + c)] : 0.0;
                     const double pr = a[j] * xv;
 #pragma unroll
                     for (int rr = 0; rr < D; ++rr) acc[rr] += (rr == r) ? pr : 0.0;
@@ -280,10 +326,10 @@ __global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __res
 // ---------------------------------------------------------------------------------------------
 template <int D, int MODE, int DOTS, int U>
 __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                       const double* __restrict__ vals, const double* __restrict__ x,
-                                                       const double* __restrict__ b, double* __restrict__ y,
+                                                       const double* __restrict__ vals, const double* x,
+                                                       const double* b, double* __restrict__ y,
                                                        const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
-                                                       const double* __restrict__ w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
+                                                       const double* w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf, int prefetch) {
     pdl_prologue();
     if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
     constexpr int DD = D * D;
@@ -316,7 +362,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
             for (int u = 0; u < U; ++u) {
                 const int blk = blk0 + u * BPS + lb;
                 const bool valid = lane_on && blk < e;
-                const double xv = valid ? __ldg(x + (unsigned)(col[u] * D + c)) : 0.0;
+                const double xv = valid ? x[(unsigned)(col[u] * D + c)] : 0.0;
                 acc = fma(a[u], xv, acc);
             }
         }
@@ -386,12 +432,12 @@ struct SpmvTma {
 template <int D, int MODE, int DOTS, int U>
 __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, const int* __restrict__ tile_info, const int* __restrict__ rowptr,
                                                                  const int* __restrict__ colidx, const double* __restrict__ vals,
-                                                                 const double* __restrict__ x, const double* __restrict__ b,
+                                                                 const double* x, const double* b,
                                                                  double* __restrict__ y, const double* __restrict__ dinv,
-                                                                 const double* dvec, double* dout, double c1, double c2, const double* __restrict__ w,
-                                                                 double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf) {
-    pdl_prologue();
-    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
+                                                                 const double* dvec, double* dout, double c1, double c2, const double* w,
+                                                                 double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf, int prefetch) {
+    pdl_trigger();                           // dependents may be scheduled; this kernel waits for ITS predecessor below (pdl_wait)
+    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches; written at setup)
     using T = SpmvTma<D>;
     constexpr int DD = T::DD, BPS = 32 / DD, NS = T::NSTAGE, NW = T::NT / 32 - 1;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -416,9 +462,10 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
     if (warp == NW) {
         // ---------------- producer ----------------
         if (lane == 0) {
-            for (int i = 0; i < n_my; ++i) {
+            // one tile into ring stage i % NS.  The matrix part (values, columns, row extents) is static during a solve; the
+            // vector slices of the epilogue are written by preceding kernels of the chain.
+            auto produce = [&](int i, bool do_matrix, bool do_aux) {
                 const int st = i % NS;
-                if (i >= NS) mbar_wait(empty + st, ((i / NS) - 1) & 1);
                 const int tile = blockIdx.x + i * gridDim.x;
                 const int r0 = __ldg(tile_info + 2 * tile), b0 = __ldg(tile_info + 2 * tile + 1);
                 const int r1 = __ldg(tile_info + 2 * tile + 2), b1 = __ldg(tile_info + 2 * tile + 3);
@@ -442,17 +489,34 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
                         total += na[k];
                     }
                 }
-                meta[0] = r0; meta[1] = nr; meta[2] = b0; meta[3] = ov; meta[4] = oc; meta[5] = orw;
+                if (do_matrix) {
+                    meta[0] = r0; meta[1] = nr; meta[2] = b0; meta[3] = ov; meta[4] = oc; meta[5] = orw;
 #pragma unroll
-                for (int k = 0; k < T::NAUX; ++k) meta[6 + k] = oa[k];
-                mbar_arrive_expect_tx(full + st, total);
-                bulk_g2s(sb, (const void*)(pv - ov), nv_b, full + st);
-                bulk_g2s(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st);
-                bulk_g2s(sb + T::VALS_B + T::COLS_B, (const void*)(pr - orw), nr_b, full + st);
+                    for (int k = 0; k < T::NAUX; ++k) meta[6 + k] = oa[k];
+                    mbar_arrive_expect_tx(full + st, total);
+                    bulk_g2s(sb, (const void*)(pv - ov), nv_b, full + st);
+                    bulk_g2s(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st);
+                    bulk_g2s(sb + T::VALS_B + T::COLS_B, (const void*)(pr - orw), nr_b, full + st);
+                }
+                if (do_aux) {
 #pragma unroll
-                for (int k = 0; k < T::NAUX; ++k)
-                    if (aux_src[k]) bulk_g2s(sb + T::VALS_B + T::COLS_B + T::ROWS_B + k * T::AUX_B, (const void*)((uintptr_t)(aux_src[k] + (int64_t)r0 * D) - oa[k]), na[k], full + st);
+                    for (int k = 0; k < T::NAUX; ++k)
+                        if (aux_src[k]) bulk_g2s(sb + T::VALS_B + T::COLS_B + T::ROWS_B + k * T::AUX_B, (const void*)((uintptr_t)(aux_src[k] + (int64_t)r0 * D) - oa[k]), na[k], full + st);
+                }
+            };
+            // first ring fill: the matrix stream starts before the dependency wait, the vector slices after it
+            // (prefetch = 0: the caller cannot vouch that the matrix was final before the last stream synchronisation)
+            const int npre = min(n_my, NS);
+            if (!prefetch) pdl_wait();
+            for (int i = 0; i < npre; ++i) produce(i, true, false);
+            pdl_wait();
+            for (int i = 0; i < npre; ++i) produce(i, false, true);
+            for (int i = npre; i < n_my; ++i) {
+                mbar_wait(empty + i % NS, ((i / NS) - 1) & 1);
+                produce(i, true, true);
             }
+        } else {
+            pdl_wait();
         }
     } else {
         // ---------------- consumers ----------------
@@ -466,6 +530,7 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
         const int hl = lane % HL, half = lane / HL;
         const int lb = hl / D, c = hl - lb * D;
         const bool lane_on = lb < BPH;
+        pdl_wait();                                     // x, b, d ... come from the preceding kernels
         for (int i = 0; i < n_my; ++i) {
             const int st = i % NS;
             mbar_wait(full + st, (i / NS) & 1);
@@ -492,7 +557,7 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
                         const int blk = s + off + u * BPH + lb;
                         if (lane_on && blk < e) {
                             const int col = sc[blk];
-                            const double xv = __ldg(x + (unsigned)(col * D + c));
+                            const double xv = x[(unsigned)(col * D + c)];   // plain load: x is written by the preceding kernel (PDL rule)
                             const double* ap = sv + blk * DD + c;
 #pragma unroll
                             for (int r = 0; r < D; ++r) acc[r] = fma(ap[r * D], xv, acc[r]);
@@ -535,12 +600,16 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
 }
 
 // first Chebyshev/Jacobi step from a zero initial guess: d = c2*dinv*b ; x = d   (no matrix pass)
-__global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* __restrict__ b,
+__global__ void k_smooth_first(int64_t n, double c2, const double* __restrict__ dinv, const double* b,
                                double* __restrict__ d, double* __restrict__ x, const double* __restrict__ cf) {
-    pdl_prologue();
-    if (cf) c2 = cf[1];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double dn = c2 * dinv[i] * b[i];
+    pdl_trigger();
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (cf) c2 = ld_static(cf + 1);                            // static during a solve: fetched before the dependency wait
+    double di = i0 < n ? ld_static(dinv + i0) : 0.0;
+    pdl_wait();
+    for (int64_t i = i0; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i != i0) di = dinv[i];
+        double dn = c2 * di * b[i];
         d[i] = dn;
         x[i] = dn;
     }
@@ -573,16 +642,15 @@ __global__ void __launch_bounds__(256) k_diag_gershgorin(int nb, const int* __re
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, const int* __restrict__ pb,
-                              const double* __restrict__ xc, const double* xin, double* xout) {
-    pdl_prologue();
+                              const double* xc, const double* xin, double* xout) {
+    pdl_trigger();
+    bool waited = false;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvf * D; t += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
-        double add;
-        if (v < nvc) add = xc[t];
-        else {
-            const int k = v - nvc;
-            add = 0.5 * (xc[(int64_t)pa[k] * D + c] + xc[(int64_t)pb[k] * D + c]);
-        }
+        int ia = -1, ib = -1;
+        if (v >= nvc) { ia = ld_static(pa + (v - nvc)); ib = ld_static(pb + (v - nvc)); }   // static parent table: fetched before the dependency wait
+        if (!waited) { pdl_wait(); waited = true; }
+        const double add = v < nvc ? xc[t] : 0.5 * (xc[(int64_t)ia * D + c] + xc[(int64_t)ib * D + c]);
         xout[t] = xin[t] + add;
     }
 }
@@ -592,19 +660,32 @@ __global__ void k_prolong_add(int nvc, int nvf, const int* __restrict__ pa, cons
 // shuffle-reduce -- two dependent loads per vertex instead of a serial walk over its ~15 neighbours.
 template <int D>
 __global__ void __launch_bounds__(256) k_restrict(int nvc, const int* __restrict__ rowptr, const int* __restrict__ mid, const int* __restrict__ diagpos,
-                                                  const unsigned char* __restrict__ dirmask, const double* __restrict__ rf, double* __restrict__ rc) {
-    pdl_prologue();
+                                                  const unsigned char* __restrict__ dirmask, const double* rf, double* __restrict__ rc) {
+    pdl_trigger();
     const int hl = threadIdx.x & 15;
     const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
     const int64_t rounds = (nvc + nhw - 1) / nhw;
     for (int64_t it = 0; it < rounds; ++it) {
         const int64_t v = hw + it * nhw;
         const bool on = v < nvc;
-        const int s = on ? rowptr[v] : 0, e = on ? rowptr[v + 1] : 0, dp = on ? diagpos[v] : -1;
+        // static part (pattern, midpoint table, Dirichlet mask): for the first round fetched before the dependency wait
+        const int s = on ? ld_static(rowptr + v) : 0, e = on ? ld_static(rowptr + v + 1) : 0, dp = on ? ld_static(diagpos + v) : -1;
+        const int k0 = s + hl, k1 = k0 + 16;
+        const int m0 = (k0 < e && k0 != dp) ? ld_static(mid + k0) : -1, m1 = (k1 < e && k1 != dp) ? ld_static(mid + k1) : -1;
+        const bool fixed = on && hl < D && dirmask && ((dirmask[v] >> hl) & 1);
+        if (it == 0) pdl_wait();
         double acc[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) acc[c] = 0.0;
-        for (int k = s + hl; k < e; k += 16) {
+        if (m0 >= 0) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] += rf[(int64_t)m0 * D + c];
+        }
+        if (m1 >= 0) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] += rf[(int64_t)m1 * D + c];
+        }
+        for (int k = k0 + 32; k < e; k += 16) {
             if (k == dp) continue;
             const int64_t m = (int64_t)mid[k] * D;
 #pragma unroll
@@ -619,9 +700,7 @@ __global__ void __launch_bounds__(256) k_restrict(int nvc, const int* __restrict
             double h = acc[0];
 #pragma unroll
             for (int c = 1; c < D; ++c) h = (hl == c) ? acc[c] : h;
-            double val = rf[v * D + hl] + 0.5 * h;
-            if (dirmask && ((dirmask[v] >> hl) & 1)) val = 0.0;
-            rc[v * D + hl] = val;
+            rc[v * D + hl] = fixed ? 0.0 : rf[v * D + hl] + 0.5 * h;
         }
     }
 }
@@ -873,7 +952,22 @@ __global__ void __launch_bounds__(640) k_gauss_jordan_resident(int n, const doub
     for (int k0 = 0; k0 < n; k0 += K, ++step) {
         const int kk = min(K, n - k0);
         const double* pb = panelbuf + (size_t)(step & 1) * K * n;
-        for (int idx = tid; idx < kk * n; idx += nt) panel[idx] = __ldcg(pb + idx);   // written by other CTAs: read through L2
+        {   // written by other CTAs: read through L2, eight independent loads in flight per thread
+            const int tot = kk * n;
+            for (int base = 0; base < tot; base += 8 * nt) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * nt + tid;
+                    v[u] = idx < tot ? __ldcg(pb + idx) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base + u * nt + tid;
+                    if (idx < tot) panel[idx] = v[u];
+                }
+            }
+        }
         __syncthreads();
         if (tid < 32) {      // invert the K x K pivot block: lane l holds row l (identity padding beyond kk)
             const int lane = tid;
@@ -964,15 +1058,40 @@ __global__ void k_extract_inverse(int n, const double* __restrict__ M, const int
 // x0 = scatter(Ainv * gather(b0)) ; Dirichlet dofs: x = b (identity rows).  The compact right-hand side is staged in
 // shared memory once per block, then one warp per free row streams its row of the inverse with independent loads.
 __global__ void __launch_bounds__(256) k_coarse_solve(int n, int ndof, const double* __restrict__ Ainv, const int* __restrict__ free2dof,
-                                                      const int* __restrict__ dof2free, const double* __restrict__ b, double* __restrict__ x) {
-    pdl_prologue();
+                                                      const int* __restrict__ dof2free, const double* b, double* __restrict__ x, int one) {
+    pdl_trigger();
     extern __shared__ double sb[];
-    for (int c = threadIdx.x; c < n; c += blockDim.x) sb[c] = b[free2dof[c]];
-    __syncthreads();
+    constexpr int PF = 20;                                  // the first 32*PF columns of a warp's first row wait in registers
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < n; i += nwarps) {
+    // static data (the inverse, the index maps) is fetched before the dependency wait
+    double a[PF];
+    int myfree = 0;
+    for (int rep = 0; rep < one; ++rep) {                   // one == 1: a loop boundary keeps ptxas from moving the wait above these loads
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int c = lane + 32 * k;
+            a[k] = (warp < n && c < n) ? ld_static(Ainv + warp * n + c) : 0.0;
+        }
+        myfree = (warp < n && lane == 0) ? ld_static(free2dof + warp) : 0;
+    }
+    pdl_wait();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) sb[c] = b[free2dof[c]];
+    __syncthreads();
+    if (warp < n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int c = lane + 32 * k;
+            if (c < n) acc += a[k] * sb[c];
+        }
+        const double* row = Ainv + warp * n;
+        for (int c = lane + 32 * PF; c < n; c += 32) acc += row[c] * sb[c];
+        acc = warp_sum(acc);
+        if (lane == 0) x[myfree] = acc;
+    }
+    for (int64_t i = warp + nwarps; i < n; i += nwarps) {
         const double* row = Ainv + i * n;
         double acc = 0.0;
 #pragma unroll 8

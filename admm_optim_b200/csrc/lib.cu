@@ -315,13 +315,13 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
 template <int D, int BATCH, int MINB>
 static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
+                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     constexpr int LPR = D == 3 ? 16 : 8;
     const int64_t groups_per_block = 256 / LPR;
     const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * MINB * ctx->spmv_waves);
     const int g = std::min(std::max(grid, 1), (int)Context::kMaxBlocks);
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH_PDL(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf)
+    AB_LAUNCH_PDL(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -332,12 +332,12 @@ static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int
 }
 template <int D, int U>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                            const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
+                            const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     using T = SpmvTma<D>;
     const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
     do {                                                                                                                              \
-        AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf); \
+        AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch); \
     } while (0)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
@@ -349,11 +349,11 @@ static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals,
 }
 template <int D, int U>
 static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf) {
+                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     const int64_t want = ((int64_t)L.nv + 7) / 8;        // 8 warps (rows) per CTA
     const int g = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min(ctx->num_sms * ctx->spmv_waves, (int)Context::kMaxBlocks)));
 #define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH_PDL(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf)
+    AB_LAUNCH_PDL(ctx, (k_bsr_spmv_warp<D, MODE, DOTS, U>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
         else if (dots == 1) AB_SPMV(0, 1);
@@ -379,23 +379,25 @@ static void spmv_prepare_kernels() {
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr,
-                 double* dout = nullptr, const double* cf = nullptr) {
+                 double* dout = nullptr, const double* cf = nullptr, int prefetch = 0) {
+    // prefetch = 1 (solver / multigrid path only): the matrix and its pattern were final before the last stream
+    // synchronisation, so the kernel may stream them before its programmatic-dependency wait (common.cuh, PDL)
     if (!dout) dout = dvec;
     // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path,
     // 2 = first-generation sub-warp row groups (kept for the comparisons in profiles/)
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
-            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
-            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             return;
         case 2:
-            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
-            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             return;
         default:
-            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
-            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf);
+            if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            else spmv_warp_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             return;
     }
 }
@@ -442,9 +444,20 @@ struct Gmg {
     std::unique_ptr<KrylovWs> ws;     // single-GPU BiCGStab workspace + iteration graph
     std::string pool_key;             // descriptor + Dirichlet set (Domain::gmg_pool)
     void setup(const std::shared_ptr<MatrixData>& A);
-    void vcycle(int l, const double* b, double* x);
-    void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf);
-    void apply(const double* r, double* z) { vcycle((int)L.size() - 1, r, z); }
+    void vcycle(int l, const double* b, double* x, bool first_done = false);
+    void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
+                bool first_done = false);
+    // first_done: the caller already performed the first pre-smoothing step of the top level (fused into its own kernel)
+    void apply(const double* r, double* z, bool first_done = false) { vcycle((int)L.size() - 1, r, z, first_done); }
+    // where the first pre-smoothing step (zero initial guess) of a cycle writing its result to z puts d and x on the top level;
+    // false when that step cannot be fused by the caller (single level, no pre-smoothing, multi-GPU interface fix-ups)
+    bool first_step_targets(double* z, double** d, double** x) {
+        const int top = (int)L.size() - 1;
+        if (top < 1 || desc.pre_smooth < 1 || dom->distributed() || !L[top].cf_pre) return false;
+        *d = L[top].d.p;
+        *x = ((desc.pre_smooth - 1) % 2 == 0) ? z : L[top].x2.p;
+        return true;
+    }
 };
 
 static std::string gmg_key(const ab_gmg_desc& d) {
@@ -650,7 +663,8 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
 }
 
-void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf) {
+void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
+                 bool first_done) {
     if (nu <= 0) { if (zero_guess) dev_fill(dom->ctx, x, (int64_t)dom->dev[l].nv * dom->dim(), 0.0); return; }
     Context* ctx = dom->ctx;
     const LevelDev& Ld = dom->dev[l];
@@ -667,7 +681,7 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     int dcur = 0;
     if (zero_guess) {
         cur = ((nu - 1) % 2 == 0) ? 0 : 1;
-        AB_LAUNCH_PDL(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur], cf);
+        if (!first_done) AB_LAUNCH_PDL(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur], cf);
         if (p2p) {          // d = c2 D^-1 b is additive at the interfaces: sum it, x = d there -- one fused launch
             smooth_exchange_p2p(dom, l, D, 0.0, nullptr, dbuf[dcur], nullptr, bufs[cur]);
         } else if (dist) {
@@ -685,12 +699,12 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
         // c2 D^-1 r_local is additive -> sum it over the interfaces and rebuild d, x there (comm.cuh)
         const double c1 = coef[k].first, c2 = coef[k].second;
         if (p2p) {
-            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, dbuf[dcur], c1, c2, nullptr, nullptr, dbuf[1 - dcur]);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, dbuf[dcur], c1, c2, nullptr, nullptr, dbuf[1 - dcur], nullptr, 1);
             smooth_exchange_p2p(dom, l, D, c1, dbuf[dcur], dbuf[1 - dcur], bufs[cur], bufs[1 - cur]);
             dcur = 1 - dcur;
         } else {
             if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1 != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
-            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2, nullptr, nullptr, nullptr, cf ? cf + 2 * k : nullptr);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2, nullptr, nullptr, nullptr, cf ? cf + 2 * k : nullptr, 1);
             if (dist) {
                 AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1, I->save.p, g.d.p);
                 exchange_sum(dom, l, g.d.p, D);
@@ -701,14 +715,14 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     }
 }
 
-void Gmg::vcycle(int l, const double* b, double* x) {
+void Gmg::vcycle(int l, const double* b, double* x, bool first_done) {
     Context* ctx = dom->ctx;
     const int dim = dom->dim();
     if (l == 0) {
         const int n = n_free;
         const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
         if (!dom->distributed()) {
-            AB_LAUNCH_PDL(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x);
+            AB_LAUNCH_PDL(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x, 1);
         } else {   // replicated solve of the global level-0 system (the reference keeps level 0 on one process, 3d_admm.lua:158-161)
             AB_CUDA(cudaMemsetAsync(bg.p, 0, (size_t)n * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, k_coarse_gather, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, b, bg.p);
@@ -723,8 +737,8 @@ void Gmg::vcycle(int l, const double* b, double* x) {
     GmgLevel& g = L[l];
     GmgLevel& gc = L[l - 1];
     const int64_t n = (int64_t)Ld.nv * dim, nc = (int64_t)Lc.nv * dim;
-    smooth(l, b, x, desc.pre_smooth, true, g.coef_pre, g.cf_pre);
-    spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p);
+    smooth(l, b, x, desc.pre_smooth, true, g.coef_pre, g.cf_pre, first_done);
+    spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
     const int rg = grid_for((int64_t)Lc.nv * 16, 256, ctx->num_sms * 8);
     if (dim == 2) AB_LAUNCH_PDL(ctx, (k_restrict<2>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
     else AB_LAUNCH_PDL(ctx, (k_restrict<3>), rg, 256, 0, Lc.nv, Lc.rowptr.p, Lc.mid.p, Lc.diagpos.p, gc.mask, g.r.p, gc.b.p);
@@ -802,18 +816,33 @@ static void solver_init(Solver* S, Operator* A) {
     }
 }
 
-// one full BiCGStab iteration on the workspace vectors; ends with the D2H copy of the scalars the ConvCheck reads
+// one full BiCGStab iteration on the workspace vectors; ends with the D2H copy of the scalars the ConvCheck reads.
+// The vector updates that feed a V-cycle are fused with that cycle's first smoothing step, the scalar bookkeeping
+// with the last reduction: 41 launches per iteration at three levels instead of 44.
 static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
     double* sc = W.sc.p;
-    AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p);
-    G->apply(W.p.p, W.ph.p);
-    spmv(ctx, dim, Lt, Av, 0, 1, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, W.rh.p, sc + SC_RV);
-    AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, ctx->d_partials, ctx->d_tickets);
-    G->apply(W.s.p, W.sh.p);
-    spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS);
-    AB_LAUNCH_PDL(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
-              ctx->d_tickets, W.out2.p);
-    AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, W.out2.p);
+    double *fd = nullptr, *fx = nullptr;
+    const bool fuse = G->first_step_targets(W.ph.p, &fd, &fx);
+    const GmgLevel& gt = G->L.back();
+    if (fuse) {
+        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<0>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p, gt.dinv.p, gt.cf_pre, fd, fx);
+        G->apply(W.p.p, W.ph.p, true);
+    } else {
+        AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p);
+        G->apply(W.p.p, W.ph.p);
+    }
+    spmv(ctx, dim, Lt, Av, 0, 1, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, W.rh.p, sc + SC_RV, nullptr, nullptr, 1);
+    if (fuse) {
+        G->first_step_targets(W.sh.p, &fd, &fx);
+        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<1>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, gt.dinv.p, gt.cf_pre, fd, fx);
+        G->apply(W.s.p, W.sh.p, true);
+    } else {
+        AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, ctx->d_partials, ctx->d_tickets);
+        G->apply(W.s.p, W.sh.p);
+    }
+    spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS, nullptr, nullptr, 1);
+    AB_LAUNCH_PDL(ctx, k_bicg_xr<1>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
+                  ctx->d_tickets, W.out2.p);
     AB_CUDA(cudaMemcpyAsync(ctx->h_results, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 }
 
@@ -839,6 +868,7 @@ static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, co
         throw;
     }
     AB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    if (const char* dot = getenv("ADMM_B200_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, cudaGraphDebugDotFlagsVerbose);   // diagnostics
     W.nodes = ctx->launches - l0;
     ctx->launches = l0;                      // capturing launches nothing
     if (W.exec) {                            // same topology, new pointers: update in place (cheaper than instantiating)
@@ -968,16 +998,16 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
         AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
         to_unique(dom, n, S->p.p, uniq);
         S->gmg->apply(uniq, S->ph.p);
-        spmv(ctx, dim, Lt, Av, 0, 0, S->ph.p, nullptr, S->v.p);
+        spmv(ctx, dim, Lt, Av, 0, 0, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
         exchange_sum(dom, top, S->v.p, dim);
         dot_owned(dom, n, S->rh.p, nullptr, S->v.p, 1, sc + SC_RV);
         AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
         to_unique(dom, n, S->s.p, uniq);
         S->gmg->apply(uniq, S->sh.p);
-        spmv(ctx, dim, Lt, Av, 0, 0, S->sh.p, nullptr, S->t.p);
+        spmv(ctx, dim, Lt, Av, 0, 0, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
         exchange_sum(dom, top, S->t.p, dim);
         dot_owned(dom, n, S->s.p, S->t.p, S->t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
-        AB_LAUNCH_PDL(ctx, k_bicg_xr, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
+        AB_LAUNCH_PDL(ctx, k_bicg_xr<0>, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
                   ctx->d_tickets, S->out2.p);                                    // local sums overwritten below
         dot_owned(dom, n, S->r.p, S->rh.p, S->r.p, 2, S->out2.p);               // <r,r>, <rh,r>
         AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
