@@ -62,6 +62,29 @@ __global__ void k_bicg_update_p(int64_t n, const double* sc, const double* r, co
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = r[i] + beta * (p[i] - omega * v[i]);
 }
+// Start of a BiCGStab solve in one pass: x_ws = x ; rh = r ; p = v = 0 ; |r|^2 -> scalars {rho = |r|^2, rho_old = alpha = omega = 1}
+__global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in, double* __restrict__ x_ws, const double* r, double* __restrict__ rh,
+                                                   double* __restrict__ p, double* __restrict__ v, double* sc, double* partials,
+                                                   unsigned int* ticket, double* out2) {
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = r[i];
+        x_ws[i] = x_in[i];
+        rh[i] = ri;
+        p[i] = 0.0;
+        v[i] = 0.0;
+        acc[0] += ri * ri;
+    }
+    const bool last = grid_reduce<1, 0>(acc, partials, ticket, out2);
+    if (last) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double rr = out2[0];
+            for (int k = 0; k < SC_COUNT; ++k) sc[k] = 0.0;
+            sc[SC_RHO] = rr; sc[SC_RHO_OLD] = 1.0; sc[SC_ALPHA] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_RR] = rr;
+        }
+    }
+}
 // alpha = rho / <rh,v>;  s = r - alpha v;  reduce |s|^2
 __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* r, const double* v,
                                                 double* __restrict__ s, double* partials, unsigned int* ticket) {

@@ -60,6 +60,9 @@ struct Domain {
     bool host_xyz_stale = false;
     std::vector<std::weak_ptr<MatrixData>> live;   // assembled matrices, for signature sharing
     std::vector<std::shared_ptr<struct Gmg>> gmg_pool;   // hierarchies are recycled (buffers, BiCGStab workspace, iteration graph)
+    // every ADMM iteration resets the multipliers (3d_admm.lua:884-894), so the first Newton iteration of each asks for the
+    // SAME u-independent operator: the latest such matrix (and the hierarchies built on it) is kept alive for the signature cache
+    std::shared_ptr<MatrixData> keep_lam0;
     // multi-GPU: shared-vertex interfaces per level (host staging until finalize) and the replicated level-0 numbering
     struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
     std::vector<HostIface> host_iface;
@@ -210,9 +213,42 @@ struct Vector {
     DevBuf<double> d;
     int storage = AB_PST_CONSISTENT;
     uint64_t version = 0, id = 0;
+    bool aliased = false;            // the device pointer was handed out (ab_vector_device_ptr): contents may change unseen -> never cached
+    // L2Norm(gf, cmp) is called once per component by the scripts (3d_admm.lua:1137-1146, 1237-1251); one element pass yields
+    // all of them, so the components are remembered until the vector or the coordinates change
+    uint64_t l2_version = 0, l2_coords = 0;
+    int l2_storage = 0;
+    double l2_vals[9];
     int64_t n() const { return sp->ndofs; }
     void touch() { version = ++g_version_counter; }
 };
+
+// VecProd results remembered per (x, y, versions).  The Newton/Schur loop asks for <B_r, y> with the SAME y for r = 1..m in
+// consecutive calls (3d_admm.lua:993-995, 1014-1059): on a miss the products of y with the last few distinct x operands are
+// computed in the same pass over y (one launch, one read-back instead of m), bitwise equal to the separate products.
+struct DotCache {
+    struct Entry { uint64_t xid, xver, yid, yver; int xst, yst; double val; };
+    std::vector<Entry> entries;      // small ring
+    size_t next = 0;
+    std::vector<Vector*> recent_x;   // most recent first, at most 4
+    bool lookup(const Vector* x, const Vector* y, double* out) const {
+        for (const Entry& e : entries)
+            if (e.xid == x->id && e.xver == x->version && e.yid == y->id && e.yver == y->version && e.xst == x->storage && e.yst == y->storage) { *out = e.val; return true; }
+        return false;
+    }
+    void store(const Vector* x, const Vector* y, double val) {
+        Entry e{x->id, x->version, y->id, y->version, x->storage, y->storage, val};
+        if (entries.size() < 32) entries.push_back(e);
+        else { entries[next] = e; next = (next + 1) % entries.size(); }
+    }
+    void used(Vector* x) {
+        recent_x.erase(std::remove(recent_x.begin(), recent_x.end(), x), recent_x.end());
+        recent_x.insert(recent_x.begin(), x);
+        if (recent_x.size() > 4) recent_x.pop_back();
+    }
+    void forget(Vector* v) { recent_x.erase(std::remove(recent_x.begin(), recent_x.end(), v), recent_x.end()); }
+};
+static std::map<Context*, DotCache> g_dot_cache;
 
 struct ElemDisc {
     Space* sp;
@@ -633,32 +669,35 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     for (int l = 0; l <= top; ++l) L[l].mask = A->dd ? A->dd->mask(l) : nullptr;
     L[top].vals = A->vals.p;
     if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
-    // one synchronisation per setup: Gershgorin bounds (+ singularity flag) -> smoother coefficients
+    // ONE synchronisation per setup: Gershgorin bounds and the singularity flag come back together (pinned memory)
+    int* h_fail = reinterpret_cast<int*>(ctx->h_results + Context::kResultSlots - 1);
+    auto fetch = [&]() {
+        if (top >= 1) AB_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results + 1, top * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        AB_CUDA(cudaMemcpyAsync(h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return *h_fail;
+    };
+    int hfail = fetch();
+    if (hfail == 2 && !force_pivoting) {          // tiny pivot without row exchanges: redo everything with partial pivoting
+        force_pivoting = true;
+        if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
+        hfail = fetch();
+    }
     if (top >= 1) {
-        std::vector<double> lm(top + 1, 0.0);
-        read_back(ctx, ctx->d_results + 1, top, lm.data() + 1);
         std::vector<double> hc((size_t)(top + 1) * 2 * coef_stride, 0.0);
         for (int l = 1; l <= top; ++l) {
-            L[l].lmax = lm[l];
-            smoother_coefs(desc, lm[l], desc.pre_smooth, L[l].coef_pre);
-            smoother_coefs(desc, lm[l], desc.post_smooth, L[l].coef_post);
+            L[l].lmax = ctx->h_results[l - 1];
+            smoother_coefs(desc, L[l].lmax, desc.pre_smooth, L[l].coef_pre);
+            smoother_coefs(desc, L[l].lmax, desc.post_smooth, L[l].coef_post);
             double* hp = hc.data() + (size_t)l * 2 * coef_stride;
             for (size_t k = 0; k < L[l].coef_pre.size(); ++k) { hp[2 * k] = L[l].coef_pre[k].first; hp[2 * k + 1] = L[l].coef_pre[k].second; }
             for (size_t k = 0; k < L[l].coef_post.size(); ++k) { hp[coef_stride + 2 * k] = L[l].coef_post[k].first; hp[coef_stride + 2 * k + 1] = L[l].coef_post[k].second; }
             L[l].cf_pre = coefs.p + (size_t)l * 2 * coef_stride;
             L[l].cf_post = L[l].cf_pre + coef_stride;
         }
-        // pageable source: the call returns once the buffer is staged, so `hc` may go out of scope
+        // stream-ordered before every later launch (a kernel that follows a copy waits for it, PDL or not); pageable source:
+        // the call returns once the buffer is staged, so `hc` may go out of scope
         AB_CUDA(cudaMemcpyAsync(coefs.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    int hfail = 0;
-    AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    AB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (hfail == 2 && !force_pivoting) {          // tiny pivot without row exchanges: redo everything with partial pivoting
-        force_pivoting = true;
-        if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
-        AB_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        AB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
 }
@@ -902,19 +941,9 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     double* sc = W.sc.p;
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
-    // r = b - A x ; rh = r ; rho = <r,r>
-    dev_copy(ctx, n, x->d.p, W.x.p);
-    spmv(ctx, dim, Lt, Av, 1, 0, W.x.p, b->d.p, W.r.p);
-    dev_copy(ctx, n, W.r.p, W.rh.p);
-    {
-        const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        const double* xs[1] = {W.r.p};
-        dev_dots(ctx, n, 1, xs, W.r.p, sc + SC_RR);
-        AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    dev_fill(ctx, W.p.p, n, 0.0);
-    dev_fill(ctx, W.v.p, n, 0.0);
+    // r = b - A x ; then in one pass: workspace x = x, rh = r, p = v = 0, rho = <r,r> and the other scalars
+    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, W.r.p);
+    AB_LAUNCH(ctx, k_bicg_init, red_grid(ctx, n), 256, 0, n, x->d.p, W.x.p, W.r.p, W.rh.p, W.p.p, W.v.p, sc, ctx->d_partials, ctx->d_tickets, W.out2.p);
     read_back(ctx, sc, SC_COUNT, h);
     const double rr0 = h[SC_RR];
     double rr = rr0;
@@ -1151,6 +1180,7 @@ static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
     }
     M.sig = sig;
     M.assembled = true;
+    if (cache && sig.kind == 1 && sig.u_id == 0 && M.vals.n * sizeof(double) <= ((size_t)4 << 30)) dom->keep_lam0 = A->data;
 }
 
 template <int D>
@@ -1270,6 +1300,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
         c->own_stream = true;
     }
     if (const char* v = getenv("ADMM_B200_GRAPH")) c->use_graph = atoi(v) != 0;
+    if (env_flag("ADMM_B200_NO_CACHE")) c->use_cache = false;
     if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
     spmv_prepare_kernels();
@@ -1290,6 +1321,7 @@ int ab_context_destroy(ab_context* ctx) {
     AB_TRY
     if (!ctx) return AB_OK;
     cudaStreamSynchronize(ctx->stream);
+    g_dot_cache.erase(ctx);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_tickets); cudaFree(ctx->d_results); cudaFreeHost(ctx->h_results);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1629,6 +1661,10 @@ int ab_vector_create(ab_space* sp, ab_vector** out) {
 }
 int ab_vector_destroy(ab_vector* v) {
     AB_TRY
+    if (v) {
+        auto it = g_dot_cache.find(v->sp->dom->ctx);
+        if (it != g_dot_cache.end()) it->second.forget(v);
+    }
     delete v;
     AB_CATCH
 }
@@ -1660,6 +1696,7 @@ int ab_vector_device_ptr(ab_vector* v, void** out, int64_t* n) {
     AB_TRY
     *out = v->d.p;
     if (n) *n = v->n();
+    v->aliased = true;
     v->touch();   // the caller may write through the pointer
     AB_CATCH
 }
@@ -1744,8 +1781,26 @@ int ab_vec_prod_multi(int n, ab_vector* const* xs, ab_vector* y, double* out) {
     AB_CATCH
 }
 int ab_vec_prod(ab_vector* x, ab_vector* y, double* out) {
-    ab_vector* xs[1] = {x};
-    return ab_vec_prod_multi(1, xs, y, out);
+    Domain* dom = y->sp->dom;
+    Context* ctx = dom->ctx;
+    const bool cacheable = ctx->use_cache && !dom->distributed() && !x->aliased && !y->aliased && x->n() == y->n();
+    if (!cacheable) {
+        ab_vector* xs[1] = {x};
+        return ab_vec_prod_multi(1, xs, y, out);
+    }
+    DotCache& dc = g_dot_cache[ctx];
+    if (dc.lookup(x, y, out)) { dc.used(x); return AB_OK; }
+    ab_vector* xs[4] = {x, nullptr, nullptr, nullptr};
+    int nx = 1;
+    for (Vector* c : dc.recent_x)
+        if (nx < 4 && c != x && c != y && !c->aliased && c->sp == x->sp) xs[nx++] = static_cast<ab_vector*>(c);
+    double vals[4];
+    const int rc = ab_vec_prod_multi(nx, xs, y, vals);
+    if (rc != AB_OK) return rc;
+    for (int i = 0; i < nx; ++i) dc.store(xs[i], y, vals[i]);
+    dc.used(x);
+    *out = vals[0];
+    return AB_OK;
 }
 int ab_vec_norm(ab_vector* x, double* out) {
     double v = 0;
@@ -1786,10 +1841,18 @@ int ab_l2norm_all(ab_vector* v, double* out) {
     AB_CATCH
 }
 int ab_l2norm(ab_vector* v, int comp, double* out) {
+    if (comp < 0 || comp >= v->sp->ncomp || comp >= 9) { g_last_error = "L2Norm: component out of range"; return AB_ERR_ARG; }
+    Domain* dom = v->sp->dom;
+    const bool cacheable = dom->ctx->use_cache && !v->aliased;
+    if (cacheable && v->l2_version == v->version && v->l2_coords == dom->coords_version && v->l2_storage == v->storage) {
+        *out = v->l2_vals[comp];
+        return AB_OK;
+    }
     double tmp[9];
     int rc = ab_l2norm_all(v, tmp);
     if (rc != AB_OK) return rc;
-    if (comp < 0 || comp >= v->sp->ncomp) { g_last_error = "L2Norm: component out of range"; return AB_ERR_ARG; }
+    for (int i = 0; i < v->sp->ncomp && i < 9; ++i) v->l2_vals[i] = tmp[i];
+    v->l2_version = v->version; v->l2_coords = dom->coords_version; v->l2_storage = v->storage;
     *out = tmp[comp];
     return AB_OK;
 }

@@ -305,6 +305,49 @@ def test_blocked_coarse_inverse_matches_pivoted(gpu_backend, monkeypatch):
     assert np.linalg.norm(r - A @ z) < 0.2 * np.linalg.norm(r)
 
 
+def test_vecprod_and_l2norm_result_caches_are_transparent(gpu_backend):
+    """VecProd remembers <x, y> per (x, y, versions) and computes the products of y with the last few x operands in one
+    pass (the Schur-column pattern 3d_admm.lua:1014-1017); L2Norm remembers all components of a vector.  Any change of
+    an operand (through ANY entry point) must invalidate: compare every answer with NumPy on the downloaded data."""
+    from admm_optim_b200.driver import ObstacleOptim
+    ug = gpu_backend
+    g = ObstacleOptim(ug, 3, numRefs=1, grid=GRID3D).setup()
+    rng = np.random.default_rng(42)
+    n = g.DeformationSpace_ApproxSpace.num_dofs()
+    xs = g.B_vector + [g.Lu]
+    ys = [g.sigma, g.delta_u]
+    for v in xs + ys:
+        v.from_numpy(rng.standard_normal(n))
+
+    def check():
+        for y in ys:
+            yh = y.to_numpy()
+            for x in xs:
+                ref = float(np.dot(x.to_numpy(), yh))
+                got = ug.VecProd(x, y)
+                assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (got, ref)
+    check()
+    check()                                             # second round: served from the cache where possible
+    ug.VecScaleAssign(xs[1], 2.0, xs[1]); check()       # x changed by a vector op
+    g.DeformationEquation_DomainDisc.adjust_solution(ys[0]); check()   # y changed by adjust_solution
+    ys[1].from_numpy(rng.standard_normal(n)); check()   # y changed by an upload
+    ug.VecScaleAdd2(xs[0], 1.0, xs[0], -3.0, xs[2]); check()
+    ug.SetZeroAwayFromSubset(xs[3], g.ucmps, "obstacle_surface"); check()
+    # L2Norm components: cached per vector version and coordinate version
+    cm = g.ucmps.split(",")
+    a = [ug.L2Norm(g.sigma, c, 4, "outer") for c in cm]
+    assert np.allclose(a, ug.L2NormAll(g.sigma), rtol=1e-14)
+    ug.VecScaleAssign(g.sigma, 3.0, g.sigma)
+    b = [ug.L2Norm(g.sigma, c, 4, "outer") for c in cm]
+    assert np.allclose(b, 3.0 * np.array(a), rtol=1e-13)
+    g.u.from_numpy(1e-3 * rng.standard_normal(n))
+    g.DeformationEquation_DomainDisc.adjust_solution(g.u)
+    ug.TransformDomainByDisplacement(g.u, g.ucmps)      # the mesh moved: same vector, different mass matrix
+    c = [ug.L2Norm(g.sigma, cc, 4, "outer") for cc in cm]
+    assert np.allclose(c, ug.L2NormAll(g.sigma), rtol=1e-14)
+    assert not np.allclose(c, b, rtol=1e-9)
+
+
 def test_multi_gpu_matches_single_gpu():
     """Domain decomposition over 2 GPUs reproduces the single-GPU ADMM iterates (tools/dist_check.py asserts 1e-9)."""
     import os
