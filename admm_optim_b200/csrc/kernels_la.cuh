@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
 template <int D>
 struct SpmvTma {
     static constexpr int DD = D * D;
-    static constexpr int TB = D == 3 ? 256 : 512;            // max blocks per tile
+    static constexpr int TB = D == 3 ? 360 : 512;            // max blocks per tile (3 stages x 2 CTAs fit the 227 KB of an SM)
     static constexpr int RMAX = TB / (D + 1);                 // max rows per tile (a P1 row has >= D+1 blocks)
     static constexpr int NSTAGE = 3;
     static constexpr int NT = 512;                            // 15 consumer warps + 1 producer warp

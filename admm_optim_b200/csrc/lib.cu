@@ -103,17 +103,38 @@ void Domain::finalize() {
         int mr = 0;
         for (int i = 0; i < H.nv; ++i) mr = std::max(mr, P.rowptr[i + 1] - P.rowptr[i]);
         L.maxrow = mr;
-        {   // TMA SpMV tiles: greedy runs of consecutive rows with <= TB blocks and <= RMAX rows
+        {   // TMA SpMV tiles: greedy runs of consecutive rows with <= budget blocks and <= RMAX rows.  The kernel runs one
+            // persistent CTA pair per SM (G CTAs), CTA c takes tiles c, c+G, ...: the block budget is lowered from the
+            // shared-memory capacity TB to the smallest value that still needs no more rounds, so that no CTA is left with a
+            // straggler tile (at 44 730 DoFs: 900 tiles on 296 CTAs = 4 rounds for 12 CTAs -> 888 tiles = 3 rounds for all).
             const int TB = H.dim == 3 ? SpmvTma<3>::TB : SpmvTma<2>::TB, RMAX = H.dim == 3 ? SpmvTma<3>::RMAX : SpmvTma<2>::RMAX;
             std::vector<int> ti;
-            ti.push_back(0); ti.push_back(0);
-            int start = 0;
             bool ok = true;
-            for (int i = 0; i < H.nv; ++i) {
-                if (P.rowptr[i + 1] - P.rowptr[i] > TB) ok = false;
-                if (P.rowptr[i + 1] - P.rowptr[start] > TB || i + 1 - start > RMAX) { ti.push_back(i); ti.push_back(P.rowptr[i]); start = i; }
+            auto tile = [&](int budget, bool keep) {
+                if (keep) { ti.clear(); ti.push_back(0); ti.push_back(0); }
+                int start = 0, count = 0;
+                for (int i = 0; i < H.nv; ++i) {
+                    if (P.rowptr[i + 1] - P.rowptr[i] > budget) { if (budget == TB) ok = false; return INT32_MAX; }
+                    if (P.rowptr[i + 1] - P.rowptr[start] > budget || i + 1 - start > RMAX) {
+                        if (keep) { ti.push_back(i); ti.push_back(P.rowptr[i]); }
+                        start = i; ++count;
+                    }
+                }
+                if (keep) { ti.push_back(H.nv); ti.push_back(P.rowptr[H.nv]); }
+                return count + 1;
+            };
+            int budget = TB;
+            const int G = 2 * ctx->num_sms, t_full = tile(TB, false);
+            if (ok && t_full > G) {
+                const int64_t target = (int64_t)G * ((t_full + G - 1) / G);
+                int lo = std::max(mr, (int)(L.nnzb / target)), hi = TB;       // smallest budget with tile count <= target
+                while (lo < hi) {
+                    const int m = (lo + hi) / 2;
+                    if ((int64_t)tile(m, false) <= target) hi = m; else lo = m + 1;
+                }
+                budget = hi;
             }
-            ti.push_back(H.nv); ti.push_back(P.rowptr[H.nv]);
+            if (ok) tile(budget, true); else { ti.assign({0, 0, H.nv, P.rowptr[H.nv]}); }
             L.ntiles = ok ? (int)ti.size() / 2 - 1 : 0;      // 0: a row exceeds the tile (fall back to the warp kernel)
             L.tile_info.upload(ti, ctx->stream);
         }
