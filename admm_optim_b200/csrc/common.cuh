@@ -42,6 +42,7 @@ struct Context {
     bool own_stream = false;
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
+    bool use_tail = false;  // ADMM_B200_TAIL=1: levels 1 and 0 of the V-cycle in one cluster kernel (kernels_tail.cuh; experimental, slower)
     int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "kernels_fe.cuh"
 #include "kernels_la.cuh"
+#include "kernels_tail.cuh"
 #include "mesh.hpp"
 
 namespace ab {
@@ -42,6 +43,7 @@ struct LevelDev {
     int64_t nnzb = 0;
     DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
     DevBuf<int> tile_info;                       // TMA SpMV tiles: (first row, first block) per tile, ntiles+1 entries
+    std::vector<int> h_rowptr;                   // host copy on levels 0 and 1 (row partition of the cluster tail kernel)
     int ntiles = 0;
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
@@ -139,6 +141,7 @@ void Domain::finalize() {
             L.tile_info.upload(ti, ctx->stream);
         }
         L.rowptr.upload(P.rowptr, ctx->stream);
+        if (l <= 1) L.h_rowptr = P.rowptr;
         L.colidx.upload(P.colidx, ctx->stream);
         L.diagpos.upload(P.diagpos, ctx->stream);
         if (l < nl - 1) L.mid.upload(P.mid, ctx->stream);
@@ -500,6 +503,9 @@ struct Gmg {
     int coef_stride = 0;              // doubles per (level, pre|post) slot
     std::unique_ptr<KrylovWs> ws;     // single-GPU BiCGStab workspace + iteration graph
     std::string pool_key;             // descriptor + Dirichlet set (Domain::gmg_pool)
+    // levels 1 and 0 in one cluster kernel (kernels_tail.cuh)
+    struct Tail { bool tried = false, ok = false; int nc = 0; DevBuf<int> part; size_t smem = 0; int max_rows = 0, max_blocks = 0; } tail;
+    bool use_tail() const { return tail.ok && dom->ctx->use_tail; }
     void setup(const std::shared_ptr<MatrixData>& A);
     void vcycle(int l, const double* b, double* x, bool first_done = false);
     void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
@@ -633,6 +639,103 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     }
 }
 
+// ---- cluster tail (levels 1 and 0 in one kernel) ----------------------------------------------------------------
+template <int D>
+static void tail_config(const Gmg& G, int nc, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
+    Context* ctx = G.dom->ctx;
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)nc);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = G.tail.smem;
+    cfg.stream = ctx->stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ctx->use_pdl ? 2 : 1;
+}
+// decide once per hierarchy whether the tail kernel applies: single GPU, at least three levels, both smoothers active,
+// the level-1 operator split over nc CTAs fits their shared memory and a cluster of nc such CTAs can be scheduled
+template <int D>
+static void tail_prepare(Gmg& G) {
+    G.tail.tried = true;
+    Domain* dom = G.dom;
+    Context* ctx = dom->ctx;
+    const int top = dom->top();
+    if (dom->distributed() || top < 2 || G.desc.pre_smooth < 1 || G.desc.post_smooth < 1 || G.n_free < 1) return;
+    const LevelDev& L1 = dom->dev[1];
+    const std::vector<int>& rp = L1.h_rowptr;
+    if ((int)rp.size() != L1.nv + 1) return;
+    const int n0 = dom->dev[0].nv * D;
+    for (int nc : {L1.nv >= 1024 ? 16 : 8, 8}) {
+        if (L1.nv < nc) continue;
+        std::vector<int> part(nc + 1, 0);
+        int row = 0;
+        for (int c = 1; c < nc; ++c) {                       // contiguous row slices balanced by blocks
+            const int64_t want = (int64_t)rp[L1.nv] * c / nc;
+            while (row < L1.nv && rp[row] < want) ++row;
+            part[c] = row;
+        }
+        part[nc] = L1.nv;
+        int max_rows = 0, max_blocks = 0;
+        for (int c = 0; c < nc; ++c) { max_rows = std::max(max_rows, part[c + 1] - part[c]); max_blocks = std::max(max_blocks, rp[part[c + 1]] - rp[part[c]]); }
+        TailSmem<D> lay(L1.nv, n0, G.n_free, max_rows, max_blocks);
+        if (lay.total > 227 * 1024) continue;
+        G.tail.smem = lay.total; G.tail.max_rows = max_rows; G.tail.max_blocks = max_blocks;
+        if (cudaFuncSetAttribute(k_vcycle_tail<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (nc > 8 && cudaFuncSetAttribute(k_vcycle_tail<D>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[2];
+        tail_config<D>(G, nc, cfg, attr);
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, k_vcycle_tail<D>, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+        G.tail.part.upload(part, ctx->stream);
+        G.tail.nc = nc;
+        G.tail.ok = true;
+        return;
+    }
+}
+template <int D>
+static void tail_launch(Gmg& G, const double* b, double* x) {
+    Domain* dom = G.dom;
+    Context* ctx = dom->ctx;
+    const LevelDev& L1 = dom->dev[1];
+    const LevelDev& L0 = dom->dev[0];
+    TailArgs a;
+    a.nv1 = L1.nv; a.nvc = L0.nv;
+    a.rowptr1 = L1.rowptr.p; a.colidx1 = L1.colidx.p; a.vals1 = G.L[1].vals; a.dinv1 = G.L[1].dinv.p;
+    a.part = G.tail.part.p;
+    a.cf_pre = G.L[1].cf_pre; a.cf_post = G.L[1].cf_post;
+    a.nu_pre = G.desc.pre_smooth; a.nu_post = G.desc.post_smooth;
+    a.rowptr0 = L0.rowptr.p; a.mid0 = L0.mid.p; a.diagpos0 = L0.diagpos.p; a.mask0 = G.L[0].mask;
+    a.pa1 = L1.pa.p; a.pb1 = L1.pb.p;
+    a.n_free = G.n_free; a.n0 = G.n0;
+    a.Ainv = G.Ainv.p; a.free2dof = G.free2dof.p; a.dof2free = G.dof2free.p;
+    a.b = b; a.x = x;
+    a.max_rows = G.tail.max_rows; a.max_blocks = G.tail.max_blocks;
+    a.prof = nullptr;
+    if (env_flag("ADMM_B200_TAIL_PROF")) {      // diagnostics: phase time stamps of the LAST tail launch, printed by the next one
+        static unsigned long long* d_prof = nullptr;
+        static unsigned long long h_prof[16];
+        if (!d_prof) { AB_CUDA(cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long))); AB_CUDA(cudaMemset(d_prof, 0, 16 * sizeof(unsigned long long))); }
+        else {
+            AB_CUDA(cudaMemcpy(h_prof, d_prof, sizeof(h_prof), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[tail prof ns]");
+            for (int i = 1; i <= 12; ++i) fprintf(stderr, " %lld", (long long)(h_prof[i] - h_prof[i - 1]));
+            fprintf(stderr, "  total %lld\n", (long long)(h_prof[12] - h_prof[0]));
+        }
+        a.prof = d_prof;
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    tail_config<D>(G, G.tail.nc, cfg, attr);
+    AB_CUDA(cudaLaunchKernelEx(&cfg, k_vcycle_tail<D>, a));
+    ctx->launches++;
+}
+
 void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     Context* ctx = dom->ctx;
     TraceTimer tt(ctx->stream, "gmg: setup total");
@@ -721,6 +824,7 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
         AB_CUDA(cudaMemcpyAsync(coefs.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
+    if (!tail.tried) { if (dim == 2) tail_prepare<2>(*this); else tail_prepare<3>(*this); }
 }
 
 void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
@@ -790,6 +894,10 @@ void Gmg::vcycle(int l, const double* b, double* x, bool first_done) {
             AB_LAUNCH(ctx, k_dense_gemv, grid, 256, 0, n, Ainv.p, bg.p, xg.p);
             AB_LAUNCH(ctx, k_coarse_scatter, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, xg.p, x);
         }
+        return;
+    }
+    if (l == 1 && use_tail()) {          // levels 1 and 0: one cluster kernel
+        if (dim == 2) tail_launch<2>(*this, b, x); else tail_launch<3>(*this, b, x);
         return;
     }
     const LevelDev& Ld = dom->dev[l];
@@ -912,7 +1020,7 @@ static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, co
     key.push_back(Av);
     key.push_back(G->Ainv.p);
     key.push_back(G->coefs.p);
-    key.push_back((const void*)(intptr_t)(G->n_free * 16 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
+    key.push_back((const void*)(intptr_t)(G->n_free * 32 + (G->use_tail() ? 16 : 0) + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
     if (W.exec && W.key == key) return;
     TraceTimer tt(ctx->stream, "bicgstab: graph capture");
@@ -1323,6 +1431,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (const char* v = getenv("ADMM_B200_GRAPH")) c->use_graph = atoi(v) != 0;
     if (env_flag("ADMM_B200_NO_CACHE")) c->use_cache = false;
     if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("ADMM_B200_TAIL")) c->use_tail = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
     spmv_prepare_kernels();
     cudaDeviceProp prop;
@@ -1366,6 +1475,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "graph") ctx->use_graph = value != 0;
     else if (k == "coarse_variant") ctx->coarse_variant = value;
     else if (k == "pdl") ctx->use_pdl = value != 0;
+    else if (k == "tail") ctx->use_tail = value != 0;
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }

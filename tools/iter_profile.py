@@ -46,7 +46,8 @@ for g, pdl, cv, sv in CONFIGS:
     ug.set_tuning("graph", g)
     ug.set_tuning("pdl", pdl)
     ug.set_tuning("coarse_variant", cv)
-    ug.set_tuning("spmv_variant", sv)
+    ug.set_tuning("spmv_variant", sv % 10)
+    ug.set_tuning("tail", 1 if sv >= 10 else 0)          # spmv_variant + 10: experimental cluster tail kernel on
     p.admm_iteration()
     dt, launches, nn, its = timed_iterations()
     print("graph=%d pdl=%d coarse_variant=%d spmv_variant=%d: %.2f ms / ADMM iteration (%.1f us per BiCGStab it incl. everything), %.0f launches, %d Newton its, %d BiCGStab its (last)" %
