@@ -739,18 +739,19 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
                                              const int* __restrict__ frowptr, const int* __restrict__ fcol, const double* __restrict__ fvals,
                                              const int* __restrict__ pa, const int* __restrict__ pb,
                                              const unsigned char* __restrict__ dirmask, double* __restrict__ cvals) {
+    // one CTA per coarse block row, its warps take the children of the row in turn (the walk over one child's fine row is a
+    // dependent chain of binary searches and shared-memory atomics: the children are the available parallelism)
     constexpr int DD = D * D;
     extern __shared__ double sm_rap[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* acc = sm_rap + (size_t)wib * maxrow * DD;
-    int* cols = (int*)(sm_rap + (size_t)(blockDim.x >> 5) * maxrow * DD) + (size_t)wib * maxrow;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib; I < nvc; I += nwarps) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double* acc = sm_rap;                                   // maxrow x DD
+    int* cols = (int*)(sm_rap + (size_t)maxrow * DD);       // maxrow
+    for (int64_t I = blockIdx.x; I < nvc; I += gridDim.x) {
         const int cs = crowptr[I], ce = crowptr[I + 1], len = ce - cs;
-        for (int k = lane; k < len * DD; k += 32) acc[k] = 0.0;
-        for (int k = lane; k < len; k += 32) cols[k] = ccol[cs + k];
-        __syncwarp();
-        for (int ck = 0; ck < len; ++ck) {                       // children of I
+        for (int k = threadIdx.x; k < len * DD; k += blockDim.x) acc[k] = 0.0;
+        for (int k = threadIdx.x; k < len; k += blockDim.x) cols[k] = ccol[cs + k];
+        __syncthreads();
+        for (int ck = wib; ck < len; ck += nw) {                 // children of I
             const int child = cmid[cs + ck];
             const double wI = (cs + ck == cdiag[I]) ? 1.0 : 0.5;
             const int fs = frowptr[child], fe = frowptr[child + 1];
@@ -775,9 +776,9 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
         const unsigned char mI = dirmask ? dirmask[I] : 0;
-        for (int k = lane; k < len * DD; k += 32) {
+        for (int k = threadIdx.x; k < len * DD; k += blockDim.x) {
             const int blk = k / DD, rc = k - blk * DD, r = rc / D, c = rc - r * D;
             double val = acc[k];
             if (dirmask) {
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
             }
             cvals[(int64_t)cs * DD + k] = val;
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 

@@ -560,16 +560,15 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
         GmgLevel& gc = G.L[l - 1];
         if (gc.vals_own.n != (size_t)C.nnzb * DD) gc.vals_own.alloc((size_t)C.nnzb * DD);   // pointers stay put across setups (graph replay)
         gc.vals = gc.vals_own.p;
-        const int warps = 8;
-        const size_t smem = (size_t)warps * C.maxrow * (DD * sizeof(double) + sizeof(int));
+        const size_t smem = (size_t)C.maxrow * (DD * sizeof(double) + sizeof(int));      // one coarse row per CTA
         static bool attr_set[2] = {false, false};
         if (smem > 48 * 1024 && !attr_set[D - 2]) {
             AB_CUDA(cudaFuncSetAttribute(k_rap<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_set[D - 2] = true;
         }
         AB_REQUIRE(smem <= 200 * 1024, AB_ERR_UNSUPPORTED, "coarse row too long for k_rap shared memory");
-        const int grid = (int)std::min<int64_t>(((int64_t)C.nv + warps - 1) / warps, (int64_t)ctx->num_sms * 4);
-        AB_LAUNCH(ctx, (k_rap<D>), std::max(grid, 1), warps * 32, smem, C.nv, C.maxrow, C.rowptr.p, C.colidx.p, C.mid.p, C.diagpos.p, F.rowptr.p,
+        const int grid = (int)std::min<int64_t>((int64_t)C.nv, (int64_t)ctx->num_sms * 8);
+        AB_LAUNCH(ctx, (k_rap<D>), std::max(grid, 1), 256, smem, C.nv, C.maxrow, C.rowptr.p, C.colidx.p, C.mid.p, C.diagpos.p, F.rowptr.p,
                   F.colidx.p, G.L[l].vals, F.pa.p, F.pb.p, gc.mask, gc.vals_own.p);
     }
     // smoother data on levels >= 1
