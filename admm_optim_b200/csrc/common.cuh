@@ -40,6 +40,7 @@ struct Context {
     int spmv_waves = 8;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
     bool use_graph = true;  // ADMM_B200_GRAPH: replay the BiCGStab iteration as a CUDA graph (single GPU)
     bool own_stream = false;
+    bool l2_hint = true;    // ADMM_B200_L2_HINT: evict-first hint on the matrix stream of levels larger than L2
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
     bool use_tail = false;  // ADMM_B200_TAIL=1: levels 1 and 0 of the V-cycle in one cluster kernel (kernels_tail.cuh; experimental, slower)
@@ -272,6 +273,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// same with an L2 eviction-priority hint: the matrix stream is read exactly once per product, marking it evict-first keeps the
+// gathered vector (re-read ~27 times per row neighbourhood) resident in L2 instead of being flushed by the stream
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 

@@ -487,6 +487,8 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
         if (lane == 0) {
             // one tile into ring stage i % NS.  The matrix part (values, columns, row extents) is static during a solve; the
             // vector slices of the epilogue are written by preceding kernels of the chain.
+            const bool stream_hint = (prefetch & 2) != 0;     // bit 1 of `prefetch`: matrix larger than L2
+            const uint64_t pol = l2_policy_evict_first();
             auto produce = [&](int i, bool do_matrix, bool do_aux) {
                 const int st = i % NS;
                 const int tile = blockIdx.x + i * gridDim.x;
@@ -517,20 +519,30 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
 #pragma unroll
                     for (int k = 0; k < T::NAUX; ++k) meta[6 + k] = oa[k];
                     mbar_arrive_expect_tx(full + st, total);
-                    bulk_g2s(sb, (const void*)(pv - ov), nv_b, full + st);
-                    bulk_g2s(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st);
+                    if (stream_hint) {       // read-once matrix stream: first in line for eviction from L2
+                        bulk_g2s_hint(sb, (const void*)(pv - ov), nv_b, full + st, pol);
+                        bulk_g2s_hint(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st, pol);
+                    } else {
+                        bulk_g2s(sb, (const void*)(pv - ov), nv_b, full + st);
+                        bulk_g2s(sb + T::VALS_B, (const void*)(pc - oc), nc_b, full + st);
+                    }
                     bulk_g2s(sb + T::VALS_B + T::COLS_B, (const void*)(pr - orw), nr_b, full + st);
                 }
                 if (do_aux) {
 #pragma unroll
                     for (int k = 0; k < T::NAUX; ++k)
-                        if (aux_src[k]) bulk_g2s(sb + T::VALS_B + T::COLS_B + T::ROWS_B + k * T::AUX_B, (const void*)((uintptr_t)(aux_src[k] + (int64_t)r0 * D) - oa[k]), na[k], full + st);
+                        if (aux_src[k]) {
+                            unsigned char* da = sb + T::VALS_B + T::COLS_B + T::ROWS_B + k * T::AUX_B;
+                            const void* sa_ = (const void*)((uintptr_t)(aux_src[k] + (int64_t)r0 * D) - oa[k]);
+                            if (stream_hint && k != 3) bulk_g2s_hint(da, sa_, na[k], full + st, pol);   // b, D^-1, d: read once (slot 3 = x is also gathered)
+                            else bulk_g2s(da, sa_, na[k], full + st);
+                        }
                 }
             };
             // first ring fill: the matrix stream starts before the dependency wait, the vector slices after it
             // (prefetch = 0: the caller cannot vouch that the matrix was final before the last stream synchronisation)
             const int npre = min(n_my, NS);
-            if (!prefetch) pdl_wait();
+            if (!(prefetch & 1)) pdl_wait();
             for (int i = 0; i < npre; ++i) produce(i, true, false);
             pdl_wait();
             for (int i = 0; i < npre; ++i) produce(i, false, true);

@@ -395,6 +395,8 @@ static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals,
                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     using T = SpmvTma<D>;
     const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
+    // bit 1: the level does not fit L2 anyway -> the matrix stream is marked evict-first so that it does not flush the gathered vector
+    if (ctx->l2_hint && L.nnzb * (int64_t)(D * D * 8 + 4) > ((int64_t)48 << 20)) prefetch |= 2;
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
     do {                                                                                                                              \
         AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch); \
@@ -1431,6 +1433,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (env_flag("ADMM_B200_NO_CACHE")) c->use_cache = false;
     if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_TAIL")) c->use_tail = atoi(v) != 0;
+    if (const char* v = getenv("ADMM_B200_L2_HINT")) c->l2_hint = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
     spmv_prepare_kernels();
     cudaDeviceProp prop;
@@ -1475,6 +1478,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "coarse_variant") ctx->coarse_variant = value;
     else if (k == "pdl") ctx->use_pdl = value != 0;
     else if (k == "tail") ctx->use_tail = value != 0;
+    else if (k == "l2_hint") ctx->l2_hint = value != 0;
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }

@@ -32,13 +32,15 @@ s = big.SmallProblemRHS_Solver
 s.init(big.A_u_Hessian, big.sigma)
 levels = [s.level_info(l) for l in range(refs + 1)]
 BV = bench.vcycle_bytes(3, levels)
+hints = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [1]
 for v in variants:
     for w in waves:
-        ug.set_tuning("spmv_variant", v); ug.set_tuning("spmv_waves", w)
-        ts = timeit(lambda: big.A_u_Hessian.apply(big.Lu, big.sigma), 20)
-        tv = timeit(lambda: s.vcycle(big.delta_u, big.sigma), 5)
-        print("variant %d waves %d: spmv %.1f us %.0f GB/s (%.3f of peak) | vcycle %.3f ms %.0f GB/s (%.3f)" %
-              (v, w, ts * 1e6, B / ts / 1e9, B / ts / 1e9 / peak, tv * 1e3, BV / tv / 1e9, BV / tv / 1e9 / peak))
+        for h in hints:
+            ug.set_tuning("spmv_variant", v); ug.set_tuning("spmv_waves", w); ug.set_tuning("l2_hint", h)
+            ts = timeit(lambda: big.A_u_Hessian.apply(big.Lu, big.sigma), 20)
+            tv = timeit(lambda: s.vcycle(big.delta_u, big.sigma), 5)
+            print("variant %d waves %d l2_hint %d: spmv %.1f us %.0f GB/s (%.3f of peak) | vcycle %.3f ms %.0f GB/s (%.3f)" %
+                  (v, w, h, ts * 1e6, B / ts / 1e9, B / ts / 1e9 / peak, tv * 1e3, BV / tv / 1e9, BV / tv / 1e9 / peak))
 # copy-bandwidth sanity: torch copy of the same byte volume
 a = torch.empty(B // 16, dtype=torch.float64, device="cuda"); b = torch.empty_like(a)
 with torch.cuda.stream(stream):
