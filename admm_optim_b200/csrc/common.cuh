@@ -40,6 +40,7 @@ struct Context {
     int spmv_waves = 8;     // ADMM_B200_SPMV_WAVES: persistent CTAs per SM for the SpMV kernels
     bool use_graph = true;  // ADMM_B200_GRAPH: replay the BiCGStab iteration as a CUDA graph (single GPU)
     bool own_stream = false;
+    int tma_small_ctas = 2; // persistent TMA-SpMV CTAs per SM on levels that fit L2 (tuning key "tma_small_ctas")
     bool l2_hint = true;    // ADMM_B200_L2_HINT: evict-first hint on the matrix stream of levels larger than L2
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain

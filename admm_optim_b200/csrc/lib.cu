@@ -394,7 +394,10 @@ template <int D, int U>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     using T = SpmvTma<D>;
-    const int g = std::max(1, std::min(L.ntiles, 2 * ctx->num_sms));
+    // persistent CTAs: two per SM; levels that live in L2 may run one per SM (tuning key "tma_small_ctas") so that the next
+    // kernel of the PDL chain finds room to become resident and prefetch while this one runs
+    const bool small = L.nnzb * (int64_t)(D * D * 8 + 4) <= ((int64_t)48 << 20);
+    const int g = std::max(1, std::min(L.ntiles, (small ? ctx->tma_small_ctas : 2) * ctx->num_sms));
     // bit 1: the level does not fit L2 anyway -> the matrix stream is marked evict-first so that it does not flush the gathered vector
     if (ctx->l2_hint && L.nnzb * (int64_t)(D * D * 8 + 4) > ((int64_t)48 << 20)) prefetch |= 2;
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
@@ -1021,7 +1024,7 @@ static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, co
     key.push_back(Av);
     key.push_back(G->Ainv.p);
     key.push_back(G->coefs.p);
-    key.push_back((const void*)(intptr_t)(G->n_free * 32 + (G->use_tail() ? 16 : 0) + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
+    key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + (G->use_tail() ? 16 : 0) + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
     if (W.exec && W.key == key) return;
     TraceTimer tt(ctx->stream, "bicgstab: graph capture");
@@ -1479,6 +1482,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "pdl") ctx->use_pdl = value != 0;
     else if (k == "tail") ctx->use_tail = value != 0;
     else if (k == "l2_hint") ctx->l2_hint = value != 0;
+    else if (k == "tma_small_ctas") ctx->tma_small_ctas = std::max(1, std::min(2, value));
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");
     AB_CATCH
 }
@@ -1795,10 +1799,8 @@ int ab_vector_create(ab_space* sp, ab_vector** out) {
 }
 int ab_vector_destroy(ab_vector* v) {
     AB_TRY
-    if (v) {
-        auto it = g_dot_cache.find(v->sp->dom->ctx);
-        if (it != g_dot_cache.end()) it->second.forget(v);
-    }
+    if (v)
+        for (auto& kv : g_dot_cache) kv.second.forget(v);   // no dereference of the space / domain: they may already be gone
     delete v;
     AB_CATCH
 }

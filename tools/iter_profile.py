@@ -47,7 +47,8 @@ for g, pdl, cv, sv in CONFIGS:
     ug.set_tuning("pdl", pdl)
     ug.set_tuning("coarse_variant", cv)
     ug.set_tuning("spmv_variant", sv % 10)
-    ug.set_tuning("tail", 1 if sv >= 10 else 0)          # spmv_variant + 10: experimental cluster tail kernel on
+    ug.set_tuning("tail", 1 if sv % 100 >= 10 else 0)    # spmv_variant + 10: experimental cluster tail kernel on
+    ug.set_tuning("tma_small_ctas", 1 if sv >= 100 else 2)   # spmv_variant + 100: one persistent SpMV CTA per SM on small levels
     p.admm_iteration()
     dt, launches, nn, its = timed_iterations()
     print("graph=%d pdl=%d coarse_variant=%d spmv_variant=%d: %.2f ms / ADMM iteration (%.1f us per BiCGStab it incl. everything), %.0f launches, %d Newton its, %d BiCGStab its (last)" %
