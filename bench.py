@@ -29,8 +29,9 @@ GRID3D = os.path.join(ROOT, "grids", "box_3D_elongated.npz")
 GRID2D = os.path.join(ROOT, "grids", "refined.npz")
 METRIC = "3D ADMM outer iters/s at fixed DoFs"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_bsr_spmv_tma<3,0,0,3> from the committed `ncu --set full`
-# captures (one GPU): numRefs=5 profiles/r01b_spmv_tma_L5_raw.csv, numRefs=4 profiles/r01_spmv_tma_raw.csv; other sizes -> null
-NCU_TRAFFIC_BYTES = {5: 8701282000 + 166542848, 4: 1059398000 + 24325888}
+# captures (one GPU): numRefs=5 profiles/r01b_spmv_tma_L5_hint_raw.csv (current kernel, L2 evict-first hint on the matrix stream;
+# without the hint 8.70 GB + 0.17 GB, r01b_spmv_tma_L5_raw.csv), numRefs=4 profiles/r01_spmv_tma_raw.csv; other sizes -> null
+NCU_TRAFFIC_BYTES = {5: 8517273000 + 150910464, 4: 1059398000 + 24325888}
 
 
 def measured_peak():
