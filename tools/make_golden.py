@@ -17,8 +17,13 @@ import numpy as np
 from admm_optim_b200.driver import ObstacleOptim
 from oracle import ug4_np
 
-CASES = {"3d_refs1": (3, "box_3D_elongated.npz", 1), "2d_refs2": (2, "refined.npz", 2)}
+# the last two are the scripts' DEFAULT refinements (BASELINE.json configs[1] / configs[0]: 44 730 / 18 016 deformation DoFs)
+CASES = {"3d_refs1": (3, "box_3D_elongated.npz", 1), "2d_refs2": (2, "refined.npz", 2),
+         "3d_refs2": (3, "box_3D_elongated.npz", 2), "2d_refs3": (2, "refined.npz", 3)}
+only = sys.argv[1:]
 for name, (dim, grid, refs) in CASES.items():
+    if only and name not in only:
+        continue
     p = ObstacleOptim(ug4_np.Backend(smoother="cheb"), dim, numRefs=refs, grid=os.path.join(ROOT, "grids", grid), admmSteps=2).setup()
     for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
         s.desc["convCheck"]["absolute"] = 1e-13
