@@ -136,12 +136,16 @@ template <int D>
 __global__ void __launch_bounds__(512, 1) k_vcycle_tail(const TailArgs a) {
     cgt::cluster_group cl = cgt::this_cluster();
     pdl_trigger();
+    // diagnostics: %globaltimer stamps of the phases, kept in registers and written at the very end (nothing is stored to global
+    // memory before the dependency wait, tools/check_pdl_sass.py)
+    unsigned long long ts[13];
     int prof_i = 0;
+    const bool prof_on = a.prof && cl.block_rank() == 0 && threadIdx.x == 0;
     auto stamp = [&]() {
-        if (a.prof && cl.block_rank() == 0 && threadIdx.x == 0) {
+        if (prof_on) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            a.prof[prof_i] = t;
+            ts[prof_i] = t;
         }
         ++prof_i;
     };
@@ -315,6 +319,10 @@ __global__ void __launch_bounds__(512, 1) k_vcycle_tail(const TailArgs a) {
     for (int i = tid; i < nd; i += nt) a.x[(size_t)r0 * D + i] = s_x[i];
     cl.sync();                 // no CTA exits while its shared memory may still be the target of a remote access
     stamp();   // 12: end
+    if (prof_on) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) a.prof[i] = ts[i];
+    }
 }
 
 }  // namespace ab

@@ -1919,7 +1919,7 @@ int ab_vec_prod_multi(int n, ab_vector* const* xs, ab_vector* y, double* out) {
 int ab_vec_prod(ab_vector* x, ab_vector* y, double* out) {
     Domain* dom = y->sp->dom;
     Context* ctx = dom->ctx;
-    const bool cacheable = ctx->use_cache && !dom->distributed() && !x->aliased && !y->aliased && x->n() == y->n();
+    const bool cacheable = ctx->use_cache && !env_flag("ADMM_B200_NO_CACHE") && !dom->distributed() && !x->aliased && !y->aliased && x->n() == y->n();
     if (!cacheable) {
         ab_vector* xs[1] = {x};
         return ab_vec_prod_multi(1, xs, y, out);
@@ -1979,7 +1979,7 @@ int ab_l2norm_all(ab_vector* v, double* out) {
 int ab_l2norm(ab_vector* v, int comp, double* out) {
     if (comp < 0 || comp >= v->sp->ncomp || comp >= 9) { g_last_error = "L2Norm: component out of range"; return AB_ERR_ARG; }
     Domain* dom = v->sp->dom;
-    const bool cacheable = dom->ctx->use_cache && !v->aliased;
+    const bool cacheable = dom->ctx->use_cache && !env_flag("ADMM_B200_NO_CACHE") && !v->aliased;
     if (cacheable && v->l2_version == v->version && v->l2_coords == dom->coords_version && v->l2_storage == v->storage) {
         *out = v->l2_vals[comp];
         return AB_OK;

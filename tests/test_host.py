@@ -183,3 +183,37 @@ def test_rcb_partition_is_balanced_and_deterministic():
         assert np.array_equal(part, P.rcb_partition(cent, n))
         sub = P.extract_submesh({k: z[k] for k in z.files}, part, 0)
         assert sub["elems"].max() == len(sub["l2g"]) - 1 and (np.diff(sub["l2g"]) > 0).all()
+
+
+def test_pdl_kernels_wait_before_touching_chain_data():
+    """Static SASS audit of the programmatic-dependent-launch chain ("Latency path"): every kernel that is
+    launched with AB_LAUNCH_PDL must contain griddepcontrol.wait (SASS ACQBULK), and nothing may be stored or reduced to global
+    memory before the first wait.  Loads before the wait are allowed for data that is static during a solve; the audit tool
+    (tools/check_pdl_sass.py) lists them."""
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    if not shutil.which("cuobjdump") or not shutil.which("cu++filt"):
+        pytest.skip("CUDA binary utilities not installed")
+    lib = os.path.join(ROOT, "admm_optim_b200", "libadmm_b200.so")
+    src = open(os.path.join(ROOT, "admm_optim_b200", "csrc", "lib.cu")).read()
+    launched = set(re.findall(r"AB_LAUNCH_PDL\(ctx,\s*\(?\s*(k_\w+)", src))
+    assert {"k_bsr_spmv_tma", "k_restrict", "k_prolong_add", "k_coarse_solve", "k_bicg_xr", "k_bicg_fused_first"} <= launched
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    seen = set()
+    for block in re.split(r"\n\s*Function : ", sass)[1:]:
+        mangled = block.split("\n", 1)[0].strip()
+        name = subprocess.run(["cu++filt", mangled], capture_output=True, text=True).stdout
+        m = re.search(r"ab::(k_\w+)", name)
+        if not m or m.group(1) not in launched:
+            continue
+        seen.add(m.group(1))
+        lines = block.split("\n")
+        waits = [i for i, l in enumerate(lines) if "ACQBULK" in l]
+        assert waits, "%s is launched with the PDL attribute but never waits" % m.group(1)
+        early = [l for l in lines[:waits[0]] if re.search(r"\b(STG|ATOMG|RED)\b", l)]
+        assert not early, "%s writes global memory before griddepcontrol.wait: %s" % (m.group(1), early[:2])
+    assert launched <= seen, launched - seen
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_pdl_sass.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
