@@ -190,3 +190,26 @@ def test_oracle_reproduces_committed_golden_trace(name):
     for k in ("u_diff", "lambda_inc", "max_norm"):
         assert abs(tr[0][k] - g[k]) <= 1e-9 * max(abs(g[k]), 1e-3), k
     assert np.allclose(tr[0]["Lambda"], g["Lambda"], rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,K", [(37, 16), (64, 16), (594, 16), (10, 16)])
+def test_blocked_sweep_inversion_is_the_inverse(n, K):
+    """The algorithm of k_gauss_jordan_resident (coarse direct solve, replaces SuperLU(), obstacle_optim_3d_util.lua:21) restated
+    in NumPy: in-place blocked Gauss-Jordan "sweep" without row exchanges.  Per block of K pivots P:
+        Dinv = T[P,P]^-1 ; pivot rows: T[P,J] = Dinv T[P,J], T[P,P] = Dinv ; other rows i: w = T[i,P] Dinv,
+        T[i,J] -= w T[P,J], T[i,P] = -w.      After all blocks T = A^-1 (checked against numpy.linalg.inv on an SPD matrix)."""
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n))
+    A = B @ B.T + n * np.eye(n)
+    T = A.copy()
+    for k0 in range(0, n, K):
+        P = np.arange(k0, min(k0 + K, n))
+        J = np.setdiff1d(np.arange(n), P)
+        Dinv = np.linalg.inv(T[np.ix_(P, P)])
+        R = T[np.ix_(P, J)].copy()
+        W = T[np.ix_(J, P)] @ Dinv
+        T[np.ix_(J, J)] -= W @ R
+        T[np.ix_(J, P)] = -W
+        T[np.ix_(P, J)] = Dinv @ R
+        T[np.ix_(P, P)] = Dinv
+    assert np.allclose(T, np.linalg.inv(A), rtol=1e-10, atol=1e-12)
