@@ -43,6 +43,7 @@ struct Context {
     int tma_small_ctas = 2; // persistent TMA-SpMV CTAs per SM on levels that fit L2 (tuning key "tma_small_ctas")
     bool l2_hint = true;    // ADMM_B200_L2_HINT: evict-first hint on the matrix stream of levels larger than L2
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
+    bool use_loop = true;   // ADMM_B200_LOOP: the whole BiCGStab loop as one graph launch (conditional WHILE node, device-side ConvCheck)
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
     bool use_tail = false;  // ADMM_B200_TAIL=1: levels 1 and 0 of the V-cycle in one cluster kernel (kernels_tail.cuh; experimental, slower)
     int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory

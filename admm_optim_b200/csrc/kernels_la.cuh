@@ -62,10 +62,14 @@ __global__ void k_bicg_update_p(int64_t n, const double* sc, const double* r, co
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = r[i] + beta * (p[i] - omega * v[i]);
 }
+// loop-control block of a solve (device memory): the conditional-graph loop reads its stopping rule from here
+enum { CTL_TOL2 = 0, CTL_RED2, CTL_RR0, CTL_MAXIT, CTL_IT, CTL_COUNT };
+
 // Start of a BiCGStab solve in one pass: x_ws = x ; rh = r ; p = v = 0 ; |r|^2 -> scalars {rho = |r|^2, rho_old = alpha = omega = 1}
+// and the loop-control block {tol^2, reduction^2, |r0|^2, max its, it = 0}
 __global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in, double* __restrict__ x_ws, const double* r, double* __restrict__ rh,
                                                    double* __restrict__ p, double* __restrict__ v, double* sc, double* partials,
-                                                   unsigned int* ticket, double* out2) {
+                                                   unsigned int* ticket, double* out2, double* ctl, double tol2, double red2, int max_it) {
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double ri = r[i];
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in
             const double rr = out2[0];
             for (int k = 0; k < SC_COUNT; ++k) sc[k] = 0.0;
             sc[SC_RHO] = rr; sc[SC_RHO_OLD] = 1.0; sc[SC_ALPHA] = 1.0; sc[SC_OMEGA] = 1.0; sc[SC_RR] = rr;
+            ctl[CTL_TOL2] = tol2; ctl[CTL_RED2] = red2; ctl[CTL_RR0] = rr; ctl[CTL_MAXIT] = (double)max_it; ctl[CTL_IT] = 0.0;
         }
     }
 }
@@ -128,11 +133,14 @@ __global__ void __launch_bounds__(256) k_bicg_fused_first(int64_t n, const doubl
     }
 }
 // omega = <t,s>/<t,t>; x += alpha ph + omega sh; r = s - omega t; reduce |r|^2 and <rh,r> (next rho).
-// ROLL: the block that finishes last also does the bookkeeping of k_bicg_roll (one launch less per iteration).
+// ROLL >= 1: the block that finishes last also does the bookkeeping of k_bicg_roll (one launch less per iteration).
+// ROLL == 2: ... and evaluates the ConvCheck on the device (same rule as the host loop of bicgstab_apply) and tells the
+//            conditional WHILE node of the solve graph whether to run another iteration (cudaGraphSetConditional).
 template <int ROLL>
 __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* sc, const double* ph, const double* sh,
                                                  const double* s, const double* t, const double* rh,
-                                                 double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2) {
+                                                 double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2,
+                                                 unsigned long long cond_handle, double* ctl, double* hist, int hist_cap) {
     pdl_prologue();
     const double rho = sc[SC_RHO];
     const double alpha = rho / sc[SC_RV];
@@ -150,11 +158,21 @@ __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* sc, const do
     if (ROLL && last) {          // every other block read the scalars before it took its ticket
         __syncthreads();
         if (threadIdx.x == 0) {
+            const double rr = out2[0], rho_new = out2[1];
             sc[SC_RHO_OLD] = rho;
             sc[SC_ALPHA] = alpha;
             sc[SC_OMEGA] = omega;
-            sc[SC_RR] = out2[0];
-            sc[SC_RHO] = out2[1];
+            sc[SC_RR] = rr;
+            sc[SC_RHO] = rho_new;
+            if (ROLL == 2) {
+                const int it = (int)ctl[CTL_IT] + 1;
+                ctl[CTL_IT] = (double)it;
+                if (hist && it < hist_cap) hist[it] = rr;
+                const bool finite = (rr == rr) && !isinf(rr);
+                const bool conv = rr < ctl[CTL_TOL2] || (ctl[CTL_RED2] > 0.0 && rr < ctl[CTL_RED2] * ctl[CTL_RR0]);
+                const bool stop = !finite || conv || it >= (int)ctl[CTL_MAXIT] || rho_new == 0.0 || omega == 0.0;
+                cudaGraphSetConditional((cudaGraphConditionalHandle)cond_handle, stop ? 0u : 1u);
+            }
         }
     }
 }

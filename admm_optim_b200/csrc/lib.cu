@@ -485,12 +485,17 @@ struct GmgLevel {
 // ONCE into an executable CUDA graph and replayed by all of them (x is copied in and out of the workspace).
 struct KrylovWs {
     DevBuf<double> r, rh, p, v, s, t, ph, sh, x, sc, out2;
+    DevBuf<double> ctl, hist;              // loop-control block and |r|^2 history of the device-side loop
+    cudaGraphExec_t exec_loop = nullptr;   // the WHOLE iteration loop: conditional WHILE node around one iteration + D2H of the result
+    std::vector<const void*> key_loop;
+    int64_t nodes_loop = 0;
+    bool loop_failed = false;              // the driver refused the conditional graph once: stay on per-iteration replay
     cudaGraphExec_t exec = nullptr;        // one full BiCGStab iteration (2 V-cycles, 2 SpMV, recurrences, D2H of the scalars)
     std::vector<const void*> key;          // every pointer baked into the captured launches
     int64_t nodes = 0;                     // kernel launches per replay
     KrylovWs() = default;
     KrylovWs(const KrylovWs&) = delete;
-    ~KrylovWs() { if (exec) cudaGraphExecDestroy(exec); }
+    ~KrylovWs() { if (exec) cudaGraphExecDestroy(exec); if (exec_loop) cudaGraphExecDestroy(exec_loop); }
 };
 
 struct Gmg {
@@ -991,7 +996,8 @@ static void solver_init(Solver* S, Operator* A) {
 // one full BiCGStab iteration on the workspace vectors; ends with the D2H copy of the scalars the ConvCheck reads.
 // The vector updates that feed a V-cycle are fused with that cycle's first smoothing step, the scalar bookkeeping
 // with the last reduction: 41 launches per iteration at three levels instead of 44.
-static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n, bool in_loop = false,
+                           unsigned long long cond_handle = 0) {
     double* sc = W.sc.p;
     double *fd = nullptr, *fx = nullptr;
     const bool fuse = G->first_step_targets(W.ph.p, &fd, &fx);
@@ -1013,19 +1019,87 @@ static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const doub
         G->apply(W.s.p, W.sh.p);
     }
     spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS, nullptr, nullptr, 1);
+    if (in_loop) {       // body of the conditional WHILE node: the ConvCheck runs on the device, nothing goes to the host
+        AB_LAUNCH_PDL(ctx, k_bicg_xr<2>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
+                      ctx->d_tickets, W.out2.p, cond_handle, W.ctl.p, W.hist.p, (int)W.hist.n);
+        return;
+    }
     AB_LAUNCH_PDL(ctx, k_bicg_xr<1>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
-                  ctx->d_tickets, W.out2.p);
+                  ctx->d_tickets, W.out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0);
     AB_CUDA(cudaMemcpyAsync(ctx->h_results, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 }
 
-// (re)capture the iteration when any pointer baked into its launches changed since the last capture
-static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+static std::vector<const void*> iteration_key(Context* ctx, const double* Av, Gmg* G) {
     std::vector<const void*> key;
     key.push_back(Av);
     key.push_back(G->Ainv.p);
     key.push_back(G->coefs.p);
     key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + (G->use_tail() ? 16 : 0) + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
+    return key;
+}
+
+// The whole iteration loop as ONE graph launch: a conditional WHILE node whose body is one BiCGStab iteration; the last kernel
+// of the body evaluates the ConvCheck on the device and sets the loop condition (cudaGraphSetConditional), so the host does not
+// see the solve again before it has ended (no launch + synchronisation per iteration).  The graph ends with the D2H copies of
+// the scalars and of the iteration count.  Returns false (once and for all for this workspace) if the driver refuses any step:
+// the caller then replays the per-iteration graph.
+static bool ensure_loop_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    if (W.loop_failed) return false;
+    std::vector<const void*> key = iteration_key(ctx, Av, G);
+    if (W.exec_loop && W.key_loop == key) return true;
+    TraceTimer tt(ctx->stream, "bicgstab: loop graph build");
+    if (W.exec_loop) { cudaGraphExecDestroy(W.exec_loop); W.exec_loop = nullptr; }
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+    cudaGraphConditionalHandle handle = 0;
+    ok = ok && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    cudaGraphNode_t wnode = nullptr;
+    cudaGraph_t body = nullptr;
+    if (ok) {
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        ok = cudaGraphAddNode(&wnode, graph, nullptr, 0, &cp) == cudaSuccess && cp.conditional.phGraph_out != nullptr;
+        if (ok) body = cp.conditional.phGraph_out[0];
+    }
+    const int64_t l0 = ctx->launches;
+    if (ok && cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        try {
+            bicg_iteration(ctx, dim, Lt, Av, G, W, n, true, (unsigned long long)handle);
+        } catch (...) {
+            ok = false;
+        }
+        cudaGraph_t ended = nullptr;
+        if (cudaStreamEndCapture(ctx->stream, &ended) != cudaSuccess) ok = false;
+    } else {
+        ok = false;
+    }
+    W.nodes_loop = ctx->launches - l0;
+    ctx->launches = l0;
+    if (ok) {
+        cudaGraphNode_t m1 = nullptr, m2 = nullptr;
+        ok = cudaGraphAddMemcpyNode1D(&m1, graph, &wnode, 1, ctx->h_results, W.sc.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaGraphAddMemcpyNode1D(&m2, graph, &m1, 1, ctx->h_results + 16, W.ctl.p, CTL_COUNT * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (ok) ok = cudaGraphInstantiate(&W.exec_loop, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        if (W.exec_loop) { cudaGraphExecDestroy(W.exec_loop); W.exec_loop = nullptr; }
+        W.loop_failed = true;
+        if (env_flag("ADMM_B200_TRACE")) fprintf(stderr, "[ab trace] conditional loop graph unavailable, per-iteration replay\n");
+        return false;
+    }
+    W.key_loop = key;
+    return true;
+}
+
+// (re)capture the iteration when any pointer baked into its launches changed since the last capture
+static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    std::vector<const void*> key = iteration_key(ctx, Av, G);
     if (W.exec && W.key == key) return;
     TraceTimer tt(ctx->stream, "bicgstab: graph capture");
     cudaGraph_t graph = nullptr;
@@ -1069,14 +1143,16 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     if (W.r.n != (size_t)n) {
         W.r.alloc(n); W.rh.alloc(n); W.p.alloc(n); W.v.alloc(n); W.s.alloc(n); W.t.alloc(n); W.ph.alloc(n); W.sh.alloc(n); W.x.alloc(n);
         W.sc.alloc(SC_COUNT + 3); W.out2.alloc(2);
-        W.key.clear();
+        W.ctl.alloc(CTL_COUNT + 1); W.hist.alloc(4097);
+        W.key.clear(); W.key_loop.clear();
     }
     double* sc = W.sc.p;
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
     // r = b - A x ; then in one pass: workspace x = x, rh = r, p = v = 0, rho = <r,r> and the other scalars
     spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, W.r.p);
-    AB_LAUNCH(ctx, k_bicg_init, red_grid(ctx, n), 256, 0, n, x->d.p, W.x.p, W.r.p, W.rh.p, W.p.p, W.v.p, sc, ctx->d_partials, ctx->d_tickets, W.out2.p);
+    AB_LAUNCH(ctx, k_bicg_init, red_grid(ctx, n), 256, 0, n, x->d.p, W.x.p, W.r.p, W.rh.p, W.p.p, W.v.p, sc, ctx->d_partials, ctx->d_tickets, W.out2.p,
+              W.ctl.p, tol2, S->desc.red_tol > 0 ? S->desc.red_tol * S->desc.red_tol : 0.0, S->desc.max_iterations);
     read_back(ctx, sc, SC_COUNT, h);
     const double rr0 = h[SC_RR];
     double rr = rr0;
@@ -1084,22 +1160,40 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     int it = 0;
     if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
     const bool graph = ctx->use_graph && ctx->stream != nullptr;
-    if (graph && !ok && S->desc.max_iterations > 0) ensure_iteration_graph(ctx, dim, Lt, Av, G, W, n);
-    while (!ok && it < S->desc.max_iterations) {
-        ++it;
-        if (graph) {
-            AB_CUDA(cudaGraphLaunch(W.exec, ctx->stream));
-            ctx->launches += W.nodes;
-        } else {
-            bicg_iteration(ctx, dim, Lt, Av, G, W, n);
-        }
+    const bool want_iter = !ok && S->desc.max_iterations > 0;
+    if (graph && want_iter && ctx->use_loop && ensure_loop_graph(ctx, dim, Lt, Av, G, W, n)) {
+        // the whole loop in one launch (conditional WHILE node); the device applied the same ConvCheck as the host loop below
+        AB_CUDA(cudaGraphLaunch(W.exec_loop, ctx->stream));
         AB_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int i = 0; i < SC_COUNT; ++i) h[i] = ctx->h_results[i];
+        it = (int)ctx->h_results[16 + CTL_IT];
+        ctx->launches += W.nodes_loop * it;
         rr = h[SC_RR];
-        if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
-        if (!(rr == rr) || std::isinf(rr)) break;                       // NaN/Inf: breakdown
-        if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
-        if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;               // breakdown
+        const bool finite = (rr == rr) && !std::isinf(rr);
+        ok = finite && (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0));
+        if (S->desc.verbose) {
+            std::vector<double> hh((size_t)std::min<int>(it + 1, (int)W.hist.n), 0.0);
+            AB_CUDA(cudaMemcpy(hh.data(), W.hist.p, hh.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t k = 1; k < hh.size(); ++k) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", (int)k, std::sqrt(hh[k]));
+        }
+    } else {
+        if (graph && want_iter) ensure_iteration_graph(ctx, dim, Lt, Av, G, W, n);
+        while (!ok && it < S->desc.max_iterations) {
+            ++it;
+            if (graph) {
+                AB_CUDA(cudaGraphLaunch(W.exec, ctx->stream));
+                ctx->launches += W.nodes;
+            } else {
+                bicg_iteration(ctx, dim, Lt, Av, G, W, n);
+            }
+            AB_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < SC_COUNT; ++i) h[i] = ctx->h_results[i];
+            rr = h[SC_RR];
+            if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
+            if (!(rr == rr) || std::isinf(rr)) break;                       // NaN/Inf: breakdown
+            if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
+            if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;               // breakdown
+        }
     }
     if (it > 0) dev_copy(ctx, n, W.x.p, x->d.p);
     x->touch();
@@ -1170,7 +1264,7 @@ static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_def
         exchange_sum(dom, top, S->t.p, dim);
         dot_owned(dom, n, S->s.p, S->t.p, S->t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
         AB_LAUNCH_PDL(ctx, k_bicg_xr<0>, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
-                  ctx->d_tickets, S->out2.p);                                    // local sums overwritten below
+                  ctx->d_tickets, S->out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0);   // local sums overwritten below
         dot_owned(dom, n, S->r.p, S->rh.p, S->r.p, 2, S->out2.p);               // <r,r>, <rh,r>
         AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
         read_back(ctx, sc, SC_COUNT, h);
@@ -1435,6 +1529,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (const char* v = getenv("ADMM_B200_GRAPH")) c->use_graph = atoi(v) != 0;
     if (env_flag("ADMM_B200_NO_CACHE")) c->use_cache = false;
     if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("ADMM_B200_LOOP")) c->use_loop = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_TAIL")) c->use_tail = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_L2_HINT")) c->l2_hint = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
@@ -1480,6 +1575,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "graph") ctx->use_graph = value != 0;
     else if (k == "coarse_variant") ctx->coarse_variant = value;
     else if (k == "pdl") ctx->use_pdl = value != 0;
+    else if (k == "loop") ctx->use_loop = value != 0;
     else if (k == "tail") ctx->use_tail = value != 0;
     else if (k == "l2_hint") ctx->l2_hint = value != 0;
     else if (k == "tma_small_ctas") ctx->tma_small_ctas = std::max(1, std::min(2, value));
