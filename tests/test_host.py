@@ -217,3 +217,23 @@ def test_pdl_kernels_wait_before_touching_chain_data():
     assert launched <= seen, launched - seen
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_pdl_sass.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_bench_algorithmic_byte_formulas_match_survey():
+    """bench.py computes `roofline.achieved` from the ALGORITHMIC bytes of SURVEY.md 8(d): B_spmv = nnzb(8 d^2 + 4) + nb(4 + 16 d),
+    B_V = sum_l [7 B_spmv(A_l) + 2 B_P(l)], with (nb, nnzb) = (V, V + 2E) from the refinement recurrences.  Pin the level
+    counts and the byte figures quoted in SURVEY / DESIGN (3D: L2 16.6 MB, L4 1.007 GB, L5 7.99 GB; V-cycle L4 8.18 GB,
+    L5 64.8 GB; 2D L3 2.57 MB)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    lv = bench.global_counts(5, 3)
+    assert [v for v, _ in lv] == [338, 2124, 14910, 111386, 860338, 6761314]
+    assert lv[2] == (14910, 14910 + 2 * 96476) and lv[4][1] == 12662290 and lv[5][1] == 100454946
+    assert abs(bench.spmv_bytes(3, *lv[2]) / 16.6e6 - 1) < 0.01
+    assert bench.spmv_bytes(3, *lv[4]) == 1007071616
+    assert bench.spmv_bytes(3, *lv[5]) == 7986164224
+    assert bench.vcycle_bytes(3, lv[:5]) == 8183626352
+    assert abs(bench.vcycle_bytes(3, lv) / 64.8e9 - 1) < 0.005
+    l2 = bench.global_counts(3, 2)
+    assert l2[3] == (9008, 9008 + 2 * 26672)
+    assert abs(bench.spmv_bytes(2, *l2[3]) / 2.57e6 - 1) < 0.01
