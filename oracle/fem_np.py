@@ -326,8 +326,96 @@ def c_kernels():
             lib.oracle_spmv.argtypes = [_C.c_int, ip, ip, dp, dp, dp, _C.c_int]
             lib.oracle_spmv.restype = None
             lib.oracle_max_threads.restype = _C.c_int
+            if hasattr(lib, "oracle_hessian_scatter"):
+                llp = _C.POINTER(_C.c_longlong)
+                lib.oracle_hessian_scatter.argtypes = [_C.c_int, _C.c_long, ip, dp, dp, _C.c_double, _C.c_double, dp, llp, dp]
+                lib.oracle_hessian_scatter.restype = None
+                lib.oracle_load_scatter.argtypes = [_C.c_int, _C.c_long, ip, dp, dp, dp, dp, _C.c_double, _C.c_int, dp, _C.c_int, _C.c_double, dp]
+                lib.oracle_load_scatter.restype = None
             _CLIB = lib
     return _CLIB or None
+
+
+# ------------------------------------------------------------------------------------------
+# compiled assembly (bench.py's CPU legs: ug4_np.Backend(fast_assembly=True)); the NumPy functions above stay the checker
+# ------------------------------------------------------------------------------------------
+_PLAN_CACHE = {}
+
+
+def _scatter_plan(mesh: Mesh):
+    """CSR structure of the P1 operator on `mesh` and, for every element-matrix entry (e,a,i,b,j) in K.ravel() order, its slot
+    in the CSR data array.  Built once per mesh (the pattern never changes)."""
+    hit = _PLAN_CACHE.get(id(mesh))
+    if hit is not None and hit["nv"] == mesh.nv and hit["ne"] == mesh.ne:
+        return hit
+    d, n = mesh.dim, mesh.nv * mesh.dim
+    dof = (mesh.elems[:, :, None].astype(np.int64) * d + np.arange(d)[None, None, :])   # (ne,a,i)
+    shape = (mesh.ne, d + 1, d, d + 1, d)
+    key = (np.broadcast_to(dof[:, :, :, None, None], shape) * n + np.broadcast_to(dof[:, None, None, :, :], shape)).ravel()
+    uniq, slot = np.unique(key, return_inverse=True)
+    rows, cols = uniq // n, uniq % n
+    indptr = np.searchsorted(rows, np.arange(n + 1)).astype(np.int32)
+    plan = dict(nv=mesh.nv, ne=mesh.ne, n=n, slot=np.ascontiguousarray(slot.ravel(), np.int64), rows=rows, indptr=indptr,
+                indices=cols.astype(np.int32), diag=np.flatnonzero(rows == cols), elems=np.ascontiguousarray(mesh.elems, np.int32), dmask={})
+    _PLAN_CACHE[id(mesh)] = plan
+    return plan
+
+
+def hessian_matrix_fast(mesh: Mesh, u, c=1.0, lam_vol=0.0, lam_bary=None, dmask=None):
+    """Same operator as hessian_matrix() (entries agree to rounding, tests/test_oracle.py), element loop and scatter in C.
+    Dirichlet rows / columns are zeroed in place (explicit zeros stay in the pattern), diagonal 1."""
+    lib = c_kernels()
+    if lib is None or not hasattr(lib, "oracle_hessian_scatter"):
+        return hessian_matrix(mesh, u, c, lam_vol, lam_bary, dmask)
+    d = mesh.dim
+    plan = _scatter_plan(mesh)
+    lb = np.zeros(3)
+    if lam_bary is not None:
+        lb[:d] = np.asarray(lam_bary, float)[:d]
+    data = np.zeros(len(plan["indices"]))
+    xyz = np.ascontiguousarray(mesh.xyz, np.float64)
+    uu = None if u is None else np.ascontiguousarray(u, np.float64)
+    dp, ip = _C.POINTER(_C.c_double), _C.POINTER(_C.c_int)
+    lib.oracle_hessian_scatter(d, mesh.ne, plan["elems"].ctypes.data_as(ip), xyz.ctypes.data_as(dp),
+                               uu.ctypes.data_as(dp) if uu is not None else None, float(c), float(lam_vol), lb.ctypes.data_as(dp),
+                               plan["slot"].ctypes.data_as(_C.POINTER(_C.c_longlong)), data.ctypes.data_as(dp))
+    if dmask is not None:
+        k = dmask.tobytes()
+        ent = plan["dmask"].get(k)
+        if ent is None:
+            ent = (np.flatnonzero(dmask[plan["rows"]] | dmask[plan["indices"]]), plan["diag"][dmask])
+            plan["dmask"] = {k: ent}
+        data[ent[0]] = 0.0
+        data[ent[1]] = 1.0
+    return sp.csr_matrix((data, plan["indices"], plan["indptr"]), shape=(plan["n"], plan["n"]))
+
+
+def load_vector_fast(mesh: Mesh, u, lam=None, q=None, tau=0.0, w=None, sign=1.0):
+    """load_vector() with S = lam + tau (grad u - q) formed inside the C element loop (S = 0 when lam is None)."""
+    lib = c_kernels()
+    d = mesh.dim
+    if lib is None or not hasattr(lib, "oracle_load_scatter"):
+        S = None
+        if lam is not None:
+            G, _, _ = geometry(mesh)
+            S = lam.reshape(-1, d, d) + tau * (grad_u(mesh, G, u) - q.reshape(-1, d, d))
+        return load_vector(mesh, u, S, w, sign)
+    plan = _scatter_plan(mesh)
+    out = np.zeros(mesh.nv * d)
+    xyz = np.ascontiguousarray(mesh.xyz, np.float64)
+    uu = None if u is None else np.ascontiguousarray(u, np.float64)
+    ww = np.zeros(4)
+    has_w = w is not None and bool(np.any(np.asarray(w) != 0.0))
+    if has_w:
+        ww[:d + 1] = np.asarray(w, float)[:d + 1]
+    use_S = lam is not None
+    la = np.ascontiguousarray(lam, np.float64).ravel() if use_S else None
+    qq = np.ascontiguousarray(q, np.float64).ravel() if use_S else None
+    dp, ip = _C.POINTER(_C.c_double), _C.POINTER(_C.c_int)
+    lib.oracle_load_scatter(d, mesh.ne, plan["elems"].ctypes.data_as(ip), xyz.ctypes.data_as(dp), uu.ctypes.data_as(dp) if uu is not None else None,
+                            la.ctypes.data_as(dp) if use_S else None, qq.ctypes.data_as(dp) if use_S else None, float(tau), int(use_S),
+                            ww.ctypes.data_as(dp), int(has_w), float(sign), out.ctypes.data_as(dp))
+    return out
 
 
 class CsrC:

@@ -173,8 +173,9 @@ class DomainDiscretization:
                 cache = self.ug._asm_cache
                 if cache.get("key") != key:
                     cache["key"] = key
-                    cache["mat"] = F.hessian_matrix(mesh, uu, c=disc.p["step_length"], lam_vol=disc.p["lambda_vol"],
-                                                    lam_bary=disc.p["lambda_bary"][:d], dmask=self.dmask(mesh) if self.dir else None)
+                    asm = F.hessian_matrix_fast if self.ug.fast_assembly else F.hessian_matrix
+                    cache["mat"] = asm(mesh, uu, c=disc.p["step_length"], lam_vol=disc.p["lambda_vol"],
+                                       lam_bary=disc.p["lambda_bary"][:d], dmask=self.dmask(mesh) if self.dir else None)
                 A.mat = cache["mat"]
                 A.diag = None
                 return
@@ -193,21 +194,28 @@ class DomainDiscretization:
             k = disc.kind
             if k == "DeformationEquation":
                 continue
+            fast = self.ug.fast_assembly
             if k in ("DeformationEquationRHS", "DeformationEquationLargeProblemRHS"):
-                lam = disc.imp["lam"].v.reshape(-1, d, d)
-                q = disc.imp["q"].v.reshape(-1, d, d)
-                G, _, _ = F.geometry(mesh)
-                S = lam + disc.p["tau"] * (F.grad_u(mesh, G, uu) - q)
                 w = np.array([disc.p["lambda_vol"]] + disc.p["lambda_bary"][:d])
                 if k == "DeformationEquationLargeProblemRHS":
                     w = w + np.array(disc.p["mult"][:d + 1])
-                out += F.load_vector(mesh, uu, S, w, 1.0 if d == 3 else -1.0)   # sign conventions: DESIGN.md 'Signs'
+                sgn = 1.0 if d == 3 else -1.0                                    # sign conventions: DESIGN.md 'Signs'
+                if fast:
+                    out += F.load_vector_fast(mesh, uu, disc.imp["lam"].v, disc.imp["q"].v, disc.p["tau"], w, sgn)
+                else:
+                    lam = disc.imp["lam"].v.reshape(-1, d, d)
+                    q = disc.imp["q"].v.reshape(-1, d, d)
+                    G, _, _ = F.geometry(mesh)
+                    S = lam + disc.p["tau"] * (F.grad_u(mesh, G, uu) - q)
+                    out += F.load_vector(mesh, uu, S, w, sgn)
             elif k in ("VolumeConstraintSecondDerivative", "SecondDerivativeVolume"):
                 w = np.zeros(d + 1); w[0] = 1.0
-                out += F.load_vector(mesh, uu, None, w, -1.0 if d == 3 else 1.0)
+                out += (F.load_vector_fast(mesh, uu, None, None, 0.0, w, -1.0 if d == 3 else 1.0) if fast
+                        else F.load_vector(mesh, uu, None, w, -1.0 if d == 3 else 1.0))
             elif k in ("SecondDerivativeBarycenter", "XBarycenterConstraintSecondDerivative"):
                 w = np.zeros(d + 1); w[disc.p["index"]] = 1.0
-                out += F.load_vector(mesh, uu, None, w, -1.0 if d == 3 else 1.0)
+                out += (F.load_vector_fast(mesh, uu, None, None, 0.0, w, -1.0 if d == 3 else 1.0) if fast
+                        else F.load_vector(mesh, uu, None, w, -1.0 if d == 3 else 1.0))
             elif k == "MassModel":
                 _, rhs = F.mass_model(mesh, uu, disc.imp["lam"].v)
                 out += rhs
@@ -330,9 +338,12 @@ class Backend:
     'gs' (lexicographic Gauss-Seidel, what the reference asks for -- iteration counts side by side)."""
     name = "oracle"
 
-    def __init__(self, smoother="cheb", cheb_ratio=6.0, threads=1):
+    def __init__(self, smoother="cheb", cheb_ratio=6.0, threads=1, fast_assembly=False):
+        """fast_assembly: element loops of the P1 assembly in C (oracle_kernels.c) instead of NumPy -- used by bench.py's CPU
+        legs so that the CPU baseline is not dominated by NumPy temporaries; the tests keep the NumPy path as the checker."""
         self.dim = None
         self.smoother, self.cheb_ratio, self.threads = smoother, cheb_ratio, threads
+        self.fast_assembly = bool(fast_assembly)
         self._gmg_cache = {}
         self._asm_cache = {}
         self.util = _NS()

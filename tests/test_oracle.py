@@ -213,3 +213,56 @@ def test_blocked_sweep_inversion_is_the_inverse(n, K):
         T[np.ix_(P, J)] = Dinv @ R
         T[np.ix_(P, P)] = Dinv
     assert np.allclose(T, np.linalg.inv(A), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("grid,refs", [(GRID3D, 1), (GRID2D, 2)])
+def test_compiled_assembly_matches_numpy_assembly(grid, refs):
+    """bench.py's CPU legs assemble with the C element kernels (oracle_kernels.c: oracle_hessian_scatter / oracle_load_scatter,
+    `ug4_np.Backend(fast_assembly=True)`); the NumPy functions remain the checker of every parity test.  Same formulas:
+    the matrices and load vectors must agree to rounding for every combination the drivers use."""
+    if F.c_kernels() is None or not hasattr(F.c_kernels(), "oracle_hessian_scatter"):
+        pytest.skip("oracle C library not built")
+    mesh = M.build_hierarchy(M.load_npz(grid), refs)[-1]
+    d = mesh.dim
+    rng = np.random.default_rng(7)
+    u = 0.02 * rng.standard_normal(mesh.nv * d)
+    dm = F.dirichlet_dofs(mesh)
+    for uu in (u, None):
+        for lamv, lb in ((0.0, [0.0, 0.0, 0.0]), (0.3, [-0.2, 0.1, 0.05])):
+            A = F.hessian_matrix(mesh, uu, 1.3, lamv, lb[:d], dm)
+            B = F.hessian_matrix_fast(mesh, uu, 1.3, lamv, lb[:d], dm)
+            assert abs(A - B).max() <= 1e-13 * abs(A).max()
+            A = F.hessian_matrix(mesh, uu, 0.7, lamv, lb[:d], None)
+            B = F.hessian_matrix_fast(mesh, uu, 0.7, lamv, lb[:d], None)
+            assert abs(A - B).max() <= 1e-13 * abs(A).max()
+    lam = 0.1 * rng.standard_normal(mesh.ne * d * d)
+    q = 0.1 * rng.standard_normal(mesh.ne * d * d)
+    G, _, _ = F.geometry(mesh)
+    w = np.array([0.3, -0.2, 0.1, 0.05][:d + 1])
+    for uu in (u, None):
+        S = lam.reshape(-1, d, d) + 0.7 * (F.grad_u(mesh, G, uu) - q.reshape(-1, d, d))
+        for ww in (w, None):
+            a = F.load_vector(mesh, uu, S, ww, -1.0)
+            b = F.load_vector_fast(mesh, uu, lam, q, 0.7, ww, -1.0)
+            assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
+        for k in range(d + 1):
+            e = np.zeros(d + 1); e[k] = 1.0
+            a = F.load_vector(mesh, uu, None, e, 1.0)
+            b = F.load_vector_fast(mesh, uu, None, None, 0.0, e, 1.0)
+            assert np.abs(a - b).max() <= 1e-13 * max(np.abs(a).max(), 1e-300)
+
+
+def test_fast_assembly_backend_reproduces_the_admm_iteration():
+    """The whole ADMM iteration with fast_assembly=True equals the NumPy-assembled one (3D, numRefs = 1)."""
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    recs = []
+    for fast in (False, True):
+        p = ObstacleOptim(ug4_np.Backend(smoother="gs", fast_assembly=fast), 3, numRefs=1, grid=GRID3D).setup()
+        p.set_sensitivity(p.synthetic_sensitivity(0.5))
+        p.begin_step()
+        recs.append(p.admm_iteration())
+    a, b = recs
+    assert len(a["newton"]) == len(b["newton"])
+    for k in ("u_diff", "lambda_inc", "max_norm"):
+        assert abs(a[k] - b[k]) <= 1e-11 * max(abs(a[k]), 1e-3), k
