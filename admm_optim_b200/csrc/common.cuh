@@ -45,7 +45,6 @@ struct Context {
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
     bool use_loop = true;   // ADMM_B200_LOOP: the whole BiCGStab loop as one graph launch (conditional WHILE node, device-side ConvCheck)
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
-    bool use_tail = false;  // ADMM_B200_TAIL=1: levels 1 and 0 of the V-cycle in one cluster kernel (kernels_tail.cuh; experimental, slower)
     int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals
@@ -60,31 +59,35 @@ struct Context {
 
 // Caching device allocator: per-Newton-iteration matrices / multigrid hierarchies come and go, and raw
 // cudaMalloc/cudaFree cost milliseconds each (and cudaFree synchronises the device).  Blocks are recycled by
-// size; reuse is safe because all work of a context is ordered on one stream.  Never returns memory to the
-// driver before process exit (sizes repeat every iteration).
+// (device, size): a block is only ever handed back to a context on the device it was allocated on.  Reuse across
+// streams of one device is safe because a block is released by host code that runs after the work using it was
+// enqueued, and every context synchronises its stream before it is destroyed; two contexts on the same device that
+// run concurrently on different streams must not share vectors (the C ABI never lets them).  trim() returns the
+// cached blocks of a device to the driver (ab_context_destroy calls it for its device).
 struct DevicePool {
-    std::multimap<size_t, void*> free_;
-    std::unordered_map<void*, size_t> size_;
+    std::multimap<std::pair<int, size_t>, void*> free_;
+    std::unordered_map<void*, std::pair<int, size_t>> size_;
     size_t bytes_allocated = 0;
     static DevicePool& get() { static DevicePool* p = new DevicePool(); return *p; }   // leaked on purpose (CUDA teardown order)
     void* alloc(size_t bytes) {
         bytes = (bytes + 511) & ~(size_t)511;
-        auto it = free_.lower_bound(bytes);
-        if (it != free_.end() && it->first <= bytes + bytes / 8 + 4096) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        auto it = free_.lower_bound({dev, bytes});
+        if (it != free_.end() && it->first.first == dev && it->first.second <= bytes + bytes / 8 + 4096) {
             void* p = it->second;
             free_.erase(it);
             return p;
         }
         void* p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) {   // out of memory: drop the cache and retry once
+        if (e != cudaSuccess) {   // out of memory: drop this device's cache and retry once
             cudaGetLastError();
-            for (auto& kv : free_) { cudaFree(kv.second); size_.erase(kv.second); bytes_allocated -= kv.first; }
-            free_.clear();
+            trim(dev);
             e = cudaMalloc(&p, bytes);
         }
         if (e != cudaSuccess) throw ab::Error(-2, std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
-        size_[p] = bytes;
+        size_[p] = {dev, bytes};
         bytes_allocated += bytes;
         return p;
     }
@@ -92,6 +95,16 @@ struct DevicePool {
         auto it = size_.find(p);
         if (it == size_.end()) { cudaFree(p); return; }
         free_.insert({it->second, p});
+    }
+    void trim(int dev) {
+        for (auto it = free_.begin(); it != free_.end();) {
+            if (it->first.first == dev) {
+                cudaFree(it->second);
+                size_.erase(it->second);
+                bytes_allocated -= it->first.second;
+                it = free_.erase(it);
+            } else ++it;
+        }
     }
 };
 

@@ -241,9 +241,7 @@ __global__ void k_coarse_scatter(int ndof, const int* __restrict__ dof2gfree, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// BSR SpMV family.  One group of LPR lanes per block row; the row's value array (len*D*D doubles,
-// contiguous) is streamed with unit-stride loads across the lanes, block-column indices are loaded
-// once per row and broadcast with shuffles, x is gathered through the read-only path.
+// BSR SpMV family (k_bsr_spmv_tma: default; k_bsr_spmv_warp: fallback when a row exceeds a tile).
 //   MODE 0: y = A x
 //   MODE 1: y = b - A x
 //   MODE 2: Chebyshev/Jacobi step  r = b - A xin ; d = c1*d + c2*dinv*r ; xout = xin + d
@@ -256,114 +254,14 @@ __device__ __forceinline__ double ld_stream(const double* p) {
     return v;
 }
 
-template <int D, int LPR, int MODE, int DOTS, int BATCH = D * D, int MINB = 3>
-__global__ void __launch_bounds__(256, MINB) k_bsr_spmv(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                                  const double* __restrict__ vals, const double* x,
-                                                  const double* b, double* __restrict__ y,
-                                                  const double* __restrict__ dinv, const double* dvec, double* dout, double c1, double c2,
-                                                  const double* w, double* partials, unsigned int* ticket, double* red, const double* __restrict__ cf, int prefetch) {
-    pdl_prologue();
-    if (cf) { c1 = cf[0]; c2 = cf[1]; }      // smoother coefficients from device memory (graph-replayable launches)
-    constexpr int DD = D * D;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane % LPR;                          // lane within group
-    const int gbase = lane - gl;                        // first lane of my group
-    const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
-    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-    const int64_t ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
-    double dot[2] = {0.0, 0.0};
-    // every lane of a warp iterates the same number of rounds (rows padded with idle groups)
-    const int64_t nrounds = (nb + ngroups - 1) / ngroups;
-    // software pipeline over rounds: the next row's extent and first column chunk are in flight while the
-    // current row's values stream in
-    int s_n = 0, e_n = 0, col_n = 0;
-    if (gid < nb) {
-        s_n = __ldg(rowptr + gid);
-        e_n = __ldg(rowptr + gid + 1);
-        if (s_n + gl < e_n) col_n = __ldg(colidx + s_n + gl);
-    }
-    for (int64_t round = 0; round < nrounds; ++round) {
-        const int64_t row = gid + round * ngroups;
-        const bool active = row < nb;
-        const int s = s_n, e = e_n;
-        int mycol = col_n;
-        {
-            const int64_t nrow = row + ngroups;
-            s_n = 0; e_n = 0; col_n = 0;
-            if (nrow < nb) {
-                s_n = __ldg(rowptr + nrow);
-                e_n = __ldg(rowptr + nrow + 1);
-                if (s_n + gl < e_n) col_n = __ldg(colidx + s_n + gl);
-            }
-        }
-        double acc[D];
-#pragma unroll
-        for (int r = 0; r < D; ++r) acc[r] = 0.0;
-        for (int cs = s; cs < e; cs += LPR) {           // chunks of LPR blocks (one chunk for most rows)
-            const int nent = min(LPR, e - cs) * DD;
-            int col_next = 0;
-            if (cs + LPR + gl < e) col_next = __ldg(colidx + cs + LPR + gl);
-            const double* vp = vals + (int64_t)cs * DD + gl;
-            // DD iterations cover the LPR*DD entries of a chunk; they are issued in phases of BATCH fully
-            // unrolled, independent loads (BATCH trades bytes in flight per lane against registers)
-#pragma unroll 1
-            for (int it0 = 0; it0 < DD; it0 += BATCH) {
-                if (it0 * LPR >= nent) break;            // group-uniform
-                double a[BATCH];
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j)
-                    a[j] = (it0 + j < DD && (it0 + j) * LPR + gl < nent) ? ld_stream(vp + (it0 + j) * LPR) : 0.0;
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j) {
-                    const int k = (it0 + j) * LPR + gl;
-                    const int blk = min(k / DD, LPR - 1);
-                    const int wq = k - (k / DD) * DD;
-                    const int r = wq / D;
-                    const int c = wq - r * D;
-                    const int col = __shfl_sync(gmask, mycol, gbase + blk);
-                    const double xv = (it0 + j < DD && k < nent) ? x[(unsigned)(col * D + c)] : 0.0;
-                    const double pr = a[j] * xv;
-#pragma unroll
-                    for (int rr = 0; rr < D; ++rr) acc[rr] += (rr == r) ? pr : 0.0;
-                }
-            }
-            mycol = col_next;
-        }
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(gmask, acc[r], o);
-        }
-        if (active && gl < D) {
-            double av = acc[0];
-#pragma unroll
-            for (int r = 1; r < D; ++r) av = (gl == r) ? acc[r] : av;
-            const int64_t i = row * D + gl;
-            if (MODE == 0) {
-                y[i] = av;
-                if (DOTS >= 1) dot[0] += w[i] * av;
-                if (DOTS >= 2) dot[1] += av * av;
-            } else if (MODE == 1) {
-                y[i] = b[i] - av;
-            } else {
-                const double res = b[i] - av;
-                const double dn = (c1 != 0.0 ? c1 * dvec[i] : 0.0) + c2 * dinv[i] * res;   // c1 == 0: dvec may be uninitialised
-                dout[i] = dn;
-                y[i] = x[i] + dn;
-            }
-        }
-    }
-    if (DOTS > 0) grid_reduce<2, 0>(dot, partials, ticket, red);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Warp-per-row BSR SpMV with a FIXED lane -> (block slot, r, c) map (default kernel).
+// Warp-per-row BSR SpMV with a FIXED lane -> (block slot, r, c) map (fallback kernel).
 // D*D lanes cover one block, 32/(D*D) blocks per step (3 for 3x3: 27 active lanes reading 216 contiguous
 // bytes; 8 for 2x2).  Because a lane's (r,c) never changes there is no index division, no select and a
 // single accumulator.  U steps are unrolled with all their loads in flight; the next row's extent is prefetched
 // while the current row streams.  32 registers -> 64 resident warps per SM (measured: occupancy beats deeper
 // per-warp pipelining for this kernel, profiles/r01_spmv_notes.md).
-// Same MODE / DOTS semantics as k_bsr_spmv.
+// Same MODE / DOTS semantics as above.
 // ---------------------------------------------------------------------------------------------
 template <int D, int MODE, int DOTS, int U>
 __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __restrict__ rowptr, const int* __restrict__ colidx,
@@ -451,7 +349,7 @@ __global__ void __launch_bounds__(256) k_bsr_spmv_warp(int nb, const int* __rest
 // the bytes in flight are set by the ring depth, not by the number of resident warps.  The consumer warps
 // take rows of a landed tile (warp per row, same fixed lane -> (block slot, r, c) map as k_bsr_spmv_warp),
 // read the matrix from shared memory, gather x through L1/L2 and apply the MODE epilogue.
-// Same MODE / DOTS semantics as k_bsr_spmv.
+// Same MODE / DOTS semantics as above.
 // ---------------------------------------------------------------------------------------------
 template <int D>
 struct SpmvTma {

@@ -13,13 +13,13 @@
 #include "common.cuh"
 #include "kernels_fe.cuh"
 #include "kernels_la.cuh"
-#include "kernels_tail.cuh"
 #include "mesh.hpp"
 
 namespace ab {
 
 static thread_local std::string g_last_error;
 static uint64_t g_version_counter = 1;
+static int g_live_contexts = 0, g_context_device = -1;   // one process drives one GPU (every entry point assumes the current device)
 struct TraceTimer {   // ADMM_B200_TRACE=1: wall-clock of setup phases (synchronising; diagnostics only)
     cudaStream_t st; const char* what; bool on; double t0;
     static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
@@ -43,7 +43,6 @@ struct LevelDev {
     int64_t nnzb = 0;
     DevBuf<int> rowptr, colidx, diagpos, mid;   // P1 vertex graph (BSR pattern) + midpoint ids on the next level
     DevBuf<int> tile_info;                       // TMA SpMV tiles: (first row, first block) per tile, ntiles+1 entries
-    std::vector<int> h_rowptr;                   // host copy on levels 0 and 1 (row partition of the cluster tail kernel)
     int ntiles = 0;
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
@@ -84,6 +83,14 @@ struct Domain {
     int dim() const { return mesh.dim; }
     int top() const { return (int)mesh.levels.size() - 1; }
     void finalize();
+    Domain() = default;
+    Domain(const Domain&) = delete;
+    ~Domain() {     // the peer-to-peer window and the opened CUDA IPC mappings are raw driver objects, not pool blocks
+        if (window || !peer_windows.empty()) cudaDeviceSynchronize();   // not ctx->stream: the context may already be gone
+        for (void* p : peer_windows) if (p) cudaIpcCloseMemHandle(p);
+        if (window) cudaFree(window);
+        cudaGetLastError();
+    }
 };
 
 template <int D>
@@ -141,7 +148,6 @@ void Domain::finalize() {
             L.tile_info.upload(ti, ctx->stream);
         }
         L.rowptr.upload(P.rowptr, ctx->stream);
-        if (l <= 1) L.h_rowptr = P.rowptr;
         L.colidx.upload(P.colidx, ctx->stream);
         L.diagpos.upload(P.diagpos, ctx->stream);
         if (l < nl - 1) L.mid.upload(P.mid, ctx->stream);
@@ -373,23 +379,6 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 }
 
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
-template <int D, int BATCH, int MINB>
-static void spmv_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
-                        const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
-    constexpr int LPR = D == 3 ? 16 : 8;
-    const int64_t groups_per_block = 256 / LPR;
-    const int grid = (int)std::min<int64_t>((L.nv + groups_per_block - 1) / groups_per_block, (int64_t)ctx->num_sms * MINB * ctx->spmv_waves);
-    const int g = std::min(std::max(grid, 1), (int)Context::kMaxBlocks);
-#define AB_SPMV(MODE, DOTS) \
-    AB_LAUNCH_PDL(ctx, (k_bsr_spmv<D, LPR, MODE, DOTS, BATCH, MINB>), g, 256, 0, L.nv, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch)
-    if (mode == 0) {
-        if (dots == 0) AB_SPMV(0, 0);
-        else if (dots == 1) AB_SPMV(0, 1);
-        else AB_SPMV(0, 2);
-    } else if (mode == 1) AB_SPMV(1, 0);
-    else AB_SPMV(2, 0);
-#undef AB_SPMV
-}
 template <int D, int U>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
@@ -448,17 +437,13 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
     // prefetch = 1 (solver / multigrid path only): the matrix and its pattern were final before the last stream
     // synchronisation, so the kernel may stream them before its programmatic-dependency wait (common.cuh, PDL)
     if (!dout) dout = dvec;
-    // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path,
-    // 2 = first-generation sub-warp row groups (kept for the comparisons in profiles/)
+    // tuning knob "spmv_variant": 0 = TMA-staged tiles (default), 1 = warp per row through the LSU path (the fallback when
+    // a row exceeds a tile)
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
             if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
-            return;
-        case 2:
-            if (dim == 2) spmv_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
-            else spmv_launch<3, 3, 5>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             return;
         default:
             if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
@@ -513,9 +498,6 @@ struct Gmg {
     int coef_stride = 0;              // doubles per (level, pre|post) slot
     std::unique_ptr<KrylovWs> ws;     // single-GPU BiCGStab workspace + iteration graph
     std::string pool_key;             // descriptor + Dirichlet set (Domain::gmg_pool)
-    // levels 1 and 0 in one cluster kernel (kernels_tail.cuh)
-    struct Tail { bool tried = false, ok = false; int nc = 0; DevBuf<int> part; size_t smem = 0; int max_rows = 0, max_blocks = 0; } tail;
-    bool use_tail() const { return tail.ok && dom->ctx->use_tail; }
     void setup(const std::shared_ptr<MatrixData>& A);
     void vcycle(int l, const double* b, double* x, bool first_done = false);
     void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
@@ -648,103 +630,6 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     }
 }
 
-// ---- cluster tail (levels 1 and 0 in one kernel) ----------------------------------------------------------------
-template <int D>
-static void tail_config(const Gmg& G, int nc, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr) {
-    Context* ctx = G.dom->ctx;
-    cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3((unsigned)nc);
-    cfg.blockDim = dim3(512);
-    cfg.dynamicSmemBytes = G.tail.smem;
-    cfg.stream = ctx->stream;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)nc;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = ctx->use_pdl ? 2 : 1;
-}
-// decide once per hierarchy whether the tail kernel applies: single GPU, at least three levels, both smoothers active,
-// the level-1 operator split over nc CTAs fits their shared memory and a cluster of nc such CTAs can be scheduled
-template <int D>
-static void tail_prepare(Gmg& G) {
-    G.tail.tried = true;
-    Domain* dom = G.dom;
-    Context* ctx = dom->ctx;
-    const int top = dom->top();
-    if (dom->distributed() || top < 2 || G.desc.pre_smooth < 1 || G.desc.post_smooth < 1 || G.n_free < 1) return;
-    const LevelDev& L1 = dom->dev[1];
-    const std::vector<int>& rp = L1.h_rowptr;
-    if ((int)rp.size() != L1.nv + 1) return;
-    const int n0 = dom->dev[0].nv * D;
-    for (int nc : {L1.nv >= 1024 ? 16 : 8, 8}) {
-        if (L1.nv < nc) continue;
-        std::vector<int> part(nc + 1, 0);
-        int row = 0;
-        for (int c = 1; c < nc; ++c) {                       // contiguous row slices balanced by blocks
-            const int64_t want = (int64_t)rp[L1.nv] * c / nc;
-            while (row < L1.nv && rp[row] < want) ++row;
-            part[c] = row;
-        }
-        part[nc] = L1.nv;
-        int max_rows = 0, max_blocks = 0;
-        for (int c = 0; c < nc; ++c) { max_rows = std::max(max_rows, part[c + 1] - part[c]); max_blocks = std::max(max_blocks, rp[part[c + 1]] - rp[part[c]]); }
-        TailSmem<D> lay(L1.nv, n0, G.n_free, max_rows, max_blocks);
-        if (lay.total > 227 * 1024) continue;
-        G.tail.smem = lay.total; G.tail.max_rows = max_rows; G.tail.max_blocks = max_blocks;
-        if (cudaFuncSetAttribute(k_vcycle_tail<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) { cudaGetLastError(); continue; }
-        if (nc > 8 && cudaFuncSetAttribute(k_vcycle_tail<D>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
-        cudaLaunchConfig_t cfg;
-        cudaLaunchAttribute attr[2];
-        tail_config<D>(G, nc, cfg, attr);
-        int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, k_vcycle_tail<D>, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
-        G.tail.part.upload(part, ctx->stream);
-        G.tail.nc = nc;
-        G.tail.ok = true;
-        return;
-    }
-}
-template <int D>
-static void tail_launch(Gmg& G, const double* b, double* x) {
-    Domain* dom = G.dom;
-    Context* ctx = dom->ctx;
-    const LevelDev& L1 = dom->dev[1];
-    const LevelDev& L0 = dom->dev[0];
-    TailArgs a;
-    a.nv1 = L1.nv; a.nvc = L0.nv;
-    a.rowptr1 = L1.rowptr.p; a.colidx1 = L1.colidx.p; a.vals1 = G.L[1].vals; a.dinv1 = G.L[1].dinv.p;
-    a.part = G.tail.part.p;
-    a.cf_pre = G.L[1].cf_pre; a.cf_post = G.L[1].cf_post;
-    a.nu_pre = G.desc.pre_smooth; a.nu_post = G.desc.post_smooth;
-    a.rowptr0 = L0.rowptr.p; a.mid0 = L0.mid.p; a.diagpos0 = L0.diagpos.p; a.mask0 = G.L[0].mask;
-    a.pa1 = L1.pa.p; a.pb1 = L1.pb.p;
-    a.n_free = G.n_free; a.n0 = G.n0;
-    a.Ainv = G.Ainv.p; a.free2dof = G.free2dof.p; a.dof2free = G.dof2free.p;
-    a.b = b; a.x = x;
-    a.max_rows = G.tail.max_rows; a.max_blocks = G.tail.max_blocks;
-    a.prof = nullptr;
-    if (env_flag("ADMM_B200_TAIL_PROF")) {      // diagnostics: phase time stamps of the LAST tail launch, printed by the next one
-        static unsigned long long* d_prof = nullptr;
-        static unsigned long long h_prof[16];
-        if (!d_prof) { AB_CUDA(cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long))); AB_CUDA(cudaMemset(d_prof, 0, 16 * sizeof(unsigned long long))); }
-        else {
-            AB_CUDA(cudaMemcpy(h_prof, d_prof, sizeof(h_prof), cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[tail prof ns]");
-            for (int i = 1; i <= 12; ++i) fprintf(stderr, " %lld", (long long)(h_prof[i] - h_prof[i - 1]));
-            fprintf(stderr, "  total %lld\n", (long long)(h_prof[12] - h_prof[0]));
-        }
-        a.prof = d_prof;
-    }
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[2];
-    tail_config<D>(G, G.tail.nc, cfg, attr);
-    AB_CUDA(cudaLaunchKernelEx(&cfg, k_vcycle_tail<D>, a));
-    ctx->launches++;
-}
-
 void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     Context* ctx = dom->ctx;
     TraceTimer tt(ctx->stream, "gmg: setup total");
@@ -833,7 +718,6 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
         AB_CUDA(cudaMemcpyAsync(coefs.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
-    if (!tail.tried) { if (dim == 2) tail_prepare<2>(*this); else tail_prepare<3>(*this); }
 }
 
 void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
@@ -903,10 +787,6 @@ void Gmg::vcycle(int l, const double* b, double* x, bool first_done) {
             AB_LAUNCH(ctx, k_dense_gemv, grid, 256, 0, n, Ainv.p, bg.p, xg.p);
             AB_LAUNCH(ctx, k_coarse_scatter, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, xg.p, x);
         }
-        return;
-    }
-    if (l == 1 && use_tail()) {          // levels 1 and 0: one cluster kernel
-        if (dim == 2) tail_launch<2>(*this, b, x); else tail_launch<3>(*this, b, x);
         return;
     }
     const LevelDev& Ld = dom->dev[l];
@@ -1034,7 +914,7 @@ static std::vector<const void*> iteration_key(Context* ctx, const double* Av, Gm
     key.push_back(Av);
     key.push_back(G->Ainv.p);
     key.push_back(G->coefs.p);
-    key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + (G->use_tail() ? 16 : 0) + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
+    key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
     return key;
 }
@@ -1369,7 +1249,11 @@ static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
         sig.lam_b[1] = jac->params[AB_PARAM_LAMBDA_BARY_Y];
         sig.lam_b[2] = dim == 3 ? jac->params[AB_PARAM_LAMBDA_BARY_Z] : 0.0;
         const bool has_lam = sig.lam_vol != 0 || sig.lam_b[0] != 0 || sig.lam_b[1] != 0 || sig.lam_b[2] != 0;
-        if (has_lam && u) { sig.u_id = u->id; sig.u_version = u->version; }
+        if (has_lam && u) {
+            // an aliased import (ab_vector_device_ptr) may change without a version bump: never matches a cached signature
+            if (u->aliased) u->touch();
+            sig.u_id = u->id; sig.u_version = u->version;
+        }
     } else {
         AB_REQUIRE(dd->sp->kind == AB_SPACE_P0 && dd->sp->ncomp == dim * dim, AB_ERR_ARG, "MassModel needs a P0 space with dim*dim components");
         sig.kind = 2;
@@ -1518,6 +1402,8 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     AB_REQUIRE(e == cudaSuccess && ndev > 0, AB_ERR_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
                                                             " (libadmm_b200 has no CPU fallback)");
     AB_REQUIRE(device >= 0 && device < ndev, AB_ERR_ARG, "device index out of range");
+    AB_REQUIRE(g_live_contexts == 0 || g_context_device == device, AB_ERR_UNSUPPORTED,
+               "a context on device " + std::to_string(g_context_device) + " is alive: one process drives one GPU (run one process per GPU)");
     AB_CUDA(cudaSetDevice(device));
     auto* c = new ab_context();
     c->device = device;
@@ -1530,7 +1416,6 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (env_flag("ADMM_B200_NO_CACHE")) c->use_cache = false;
     if (const char* v = getenv("ADMM_B200_PDL")) c->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_LOOP")) c->use_loop = atoi(v) != 0;
-    if (const char* v = getenv("ADMM_B200_TAIL")) c->use_tail = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_L2_HINT")) c->l2_hint = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
     spmv_prepare_kernels();
@@ -1544,6 +1429,8 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     AB_CUDA(cudaMemset(c->d_tickets, 0, sizeof(unsigned int) * 4));
     AB_CUDA(cudaMalloc((void**)&c->d_results, sizeof(double) * Context::kResultSlots));
     AB_CUDA(cudaMallocHost((void**)&c->h_results, sizeof(double) * Context::kResultSlots));
+    g_context_device = device;
+    ++g_live_contexts;
     *out = c;
     AB_CATCH
 }
@@ -1554,7 +1441,9 @@ int ab_context_destroy(ab_context* ctx) {
     g_dot_cache.erase(ctx);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_tickets); cudaFree(ctx->d_results); cudaFreeHost(ctx->h_results);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    const int dev = ctx->device;
     delete ctx;
+    if (--g_live_contexts <= 0) { g_live_contexts = 0; DevicePool::get().trim(dev); }   // last context gone: cached blocks go back to the driver
     AB_CATCH
 }
 int ab_context_synchronize(ab_context* ctx) {
@@ -1576,7 +1465,6 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "coarse_variant") ctx->coarse_variant = value;
     else if (k == "pdl") ctx->use_pdl = value != 0;
     else if (k == "loop") ctx->use_loop = value != 0;
-    else if (k == "tail") ctx->use_tail = value != 0;
     else if (k == "l2_hint") ctx->l2_hint = value != 0;
     else if (k == "tma_small_ctas") ctx->tma_small_ctas = std::max(1, std::min(2, value));
     else AB_REQUIRE(false, AB_ERR_ARG, "unknown tuning key '" + k + "'");

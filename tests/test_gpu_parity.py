@@ -348,42 +348,6 @@ def test_vecprod_and_l2norm_result_caches_are_transparent(gpu_backend):
     assert not np.allclose(c, b, rtol=1e-9)
 
 
-@pytest.mark.parametrize("dim,grid,refs", [(3, GRID3D, 2), (2, GRID2D, 3)])
-def test_cluster_tail_matches_separate_kernels(gpu_backend, monkeypatch, dim, grid, refs):
-    """Levels 1 and 0 of the V-cycle run as one thread-block-cluster kernel (kernels_tail.cuh).  It performs the same
-    arithmetic as the ten separate launches it replaces: the V-cycle and a full solve must agree to rounding."""
-    from admm_optim_b200.driver import ObstacleOptim
-    monkeypatch.setenv("ADMM_B200_NO_CACHE", "1")
-    g = ObstacleOptim(gpu_backend, dim, numRefs=refs, grid=grid).setup()
-    n = g.DeformationSpace_ApproxSpace.num_dofs()
-    rng = np.random.default_rng(3)
-    g.u.from_numpy(0.01 * rng.standard_normal(n))
-    DD = g.DeformationEquation_DomainDisc
-    DD.adjust_solution(g.u)
-    g.Hessian_ElemDisc.set_lambda_vol(0.15)
-    b = rng.standard_normal(n)
-    zs, sols, its = [], [], []
-    try:
-        for tail in (1, 0):
-            gpu_backend.set_tuning("tail", tail)
-            DD.assemble_jacobian(g.A_u_Hessian, g.u)
-            g.Lu.from_numpy(b, 2)
-            DD.adjust_solution(g.Lu)
-            s = g.SmallProblemRHS_Solver
-            s.init(g.A_u_Hessian, g.sigma)
-            s.vcycle(g.sigma, g.Lu)
-            zs.append(g.sigma.to_numpy())
-            g.sigma.set(0.0)
-            assert s.apply(g.sigma, g.Lu)
-            sols.append(g.sigma.to_numpy())
-            its.append(s.step())
-    finally:
-        gpu_backend.set_tuning("tail", 0)          # the default (the fused tail is an opt-in experiment, DESIGN.md)
-    assert _rel(zs[0], zs[1]) < 1e-12
-    assert its[0] == its[1]
-    assert _rel(sols[0], sols[1]) < 1e-10
-
-
 def test_multi_gpu_matches_single_gpu():
     """Domain decomposition over 2 GPUs reproduces the single-GPU ADMM iterates (tools/dist_check.py asserts 1e-9)."""
     import os

@@ -49,7 +49,6 @@ for g, pdl, cv, sv in CONFIGS:
     ug.set_tuning("loop", 0 if sv >= 1000 else 1)            # spmv_variant + 1000: device-side BiCGStab loop (conditional graph node) off
     sv = sv % 1000
     ug.set_tuning("spmv_variant", sv % 10)
-    ug.set_tuning("tail", 1 if sv % 100 >= 10 else 0)    # spmv_variant + 10: experimental cluster tail kernel on
     ug.set_tuning("tma_small_ctas", 1 if sv >= 100 else 2)   # spmv_variant + 100: one persistent SpMV CTA per SM on small levels
     p.admm_iteration()
     dt, launches, nn, its = timed_iterations()
