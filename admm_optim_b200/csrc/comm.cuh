@@ -56,12 +56,14 @@ struct Comm {
 // interface (shared-vertex) lists of one level: for every neighbour rank the local vertex ids of the shared
 // vertices in a canonical order both sides agree on (sorted by coordinates at setup)
 struct Interface {
-    std::vector<int> neigh, offset;   // neighbour ranks, offset[n]..offset[n+1] into idx
-    DevBuf<int> idx;                  // concatenated per-neighbour local vertex ids
-    DevBuf<int> iv;                   // unique interface vertices
+    std::vector<int> neigh, offset;   // neighbour ranks (ascending), offset[n]..offset[n+1] into idx
+    DevBuf<int> idx;                  // concatenated per-neighbour local vertex ids ("slots")
+    DevBuf<int> iv;                   // unique interface vertices, ordered by (first neighbour, slot): the stores into the first
+                                      // neighbour's window are then consecutive
+    DevBuf<int> iv_ptr, iv_slot, iv_nb;   // CSR unique vertex -> its slots and their neighbour index, neighbour ranks ascending
     DevBuf<unsigned char> owned;      // per local vertex: 1 when this rank is the lowest rank sharing it
-    DevBuf<double> send, recv, save;  // packed buffers (total * maxcomp), smoother scratch (niv * 2 * D)
-    int total = 0, niv = 0;
+    DevBuf<double> send, recv, save;  // NCCL fallback: packed buffers (total * maxcomp), smoother scratch (niv * 2 * D)
+    int total = 0, niv = 0, my_pos = 0;   // my_pos: number of neighbours with a rank below mine
     // peer-to-peer path (NVLink, CUDA IPC): neighbours write straight into this rank's window
     DevBuf<int> d_offset, d_neigh;                 // device copies of offset / neigh
     DevBuf<unsigned long long> d_peer_dst;          // per neighbour: address (in this process) of my slot in the neighbour's window, parity 0
@@ -69,105 +71,110 @@ struct Interface {
     DevBuf<unsigned long long> d_peer_flag;         // per neighbour: address of the neighbour's flag word for this rank
     double* win_recv = nullptr;                     // my two parity buffers inside the window (total*D doubles each)
     unsigned long long* win_flags = nullptr;        // my flag words (one per rank) for this level
-    unsigned long long epoch = 0;
+    DevBuf<unsigned long long> state;               // device side: [0] epoch of the last completed exchange, [1] arrive counter, [2] done counter
 };
 
-// Fused interface sum over NVLink peer memory: every rank stores its additive interface values directly into its
-// neighbours' receive windows, publishes a per-level epoch flag (system-scope release), waits for the neighbours'
-// flags and accumulates what they wrote -- pack, transfer, synchronisation and unpack in ONE launch, no NCCL call.
-// Double-buffered by epoch parity (a neighbour can be at most one exchange ahead).  Intra-grid ordering uses one
-// monotonic counter (never reset; the host passes the value it must reach).  A bounded spin turns a lost peer into
-// an error flag instead of a hang.
-//   SMOOTH = false: v <- v + sum over neighbours           (additive -> consistent)
+// Fused interface sum over NVLink peer memory -- pack, transfer, synchronisation and unpack in ONE launch, no NCCL call, no
+// grid-wide barrier.  One thread per (unique interface vertex, component):
+//   1. put   : the thread stores its additive value into the window of every neighbour that shares the vertex;
+//   2. signal: the CTA that arrives last publishes this exchange's epoch in every neighbour's flag word (st.release.sys);
+//   3. wait  : every CTA polls the neighbours' flags for the epoch (ld.acquire.sys; bounded spin -> error flag, never a hang);
+//   4. sum   : the thread adds what the neighbours wrote for ITS vertex, contributions taken in ascending rank order with its own
+//              value at its own rank's place -- every rank sharing a vertex performs the same additions in the same order, so the
+//              consistent copies are bitwise identical on all ranks, and the result is written by the thread that read the input
+//              (no intra-grid hazard, hence no co-residency assumption).
+// The epoch lives in device memory (state[0]) and is advanced by the CTA that finishes last, so the launch carries no
+// host-side counter and can be captured into a CUDA graph.  Windows are double-buffered by epoch parity (a neighbour is at
+// most one exchange ahead: it cannot finish exchange e+1 before this rank has published e+1, i.e. finished reading e).
+// On a timeout the sum phase is skipped (v keeps its additive value) and *err is set; the solvers read err with their scalars.
+//   SMOOTH = false: v <- sum over the sharing ranks of v                                  (additive -> consistent)
 //   SMOOTH = true : the Chebyshev/Jacobi interface fix-up fused around the sum (Gmg::smooth): the locally updated
-//                   d_out = c1 d_in + c2 D^-1 r_local is reduced to its additive increment, summed, and d_out, x_out
-//                   are rebuilt at the shared vertices:  d_out = c1 d_in + total,  x_out = x_in + d_out.
-__device__ __forceinline__ void p2p_grid_barrier(unsigned long long* counter, unsigned long long target, int* err) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1ull);
-        long long spins = 0;
-        while (*(volatile unsigned long long*)counter < target)
-            if (++spins > 400000000ll) { *err = 2; break; }
-        __threadfence();
-    }
-    __syncthreads();
-}
+//                   v = c1 d_in + c2 D^-1 r_local is reduced to its additive increment, summed, and d, x are rebuilt at the
+//                   shared vertices:  v = c1 d_in + total,  x_out = x_in + v.
+constexpr long long kP2PSpinLimit = 200000000ll;
 
 template <bool SMOOTH>
-__global__ void __launch_bounds__(256) k_iface_exchange_p2p(int total, int D, int nneigh, unsigned long long epoch, unsigned long long cnt_base,
-                                                            const int* __restrict__ idx, const int* __restrict__ offset,
-                                                            const int* __restrict__ neigh, const unsigned long long* __restrict__ peer_dst,
-                                                            const unsigned long long* __restrict__ peer_stride,
-                                                            const unsigned long long* __restrict__ peer_flag, double* my_recv,
-                                                            unsigned long long* my_flags, unsigned long long* counter, int* err, double* v,
-                                                            int niv, const int* __restrict__ iv, double c1, const double* din,
-                                                            const double* xin, double* xout) {
+__global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, int my_pos, const int* __restrict__ iv, const int* __restrict__ iv_ptr,
+                                                    const int* __restrict__ iv_slot, const int* __restrict__ iv_nb, const int* __restrict__ offset,
+                                                    const int* __restrict__ neigh, const unsigned long long* __restrict__ peer_dst,
+                                                    const unsigned long long* __restrict__ peer_stride, const unsigned long long* __restrict__ peer_flag,
+                                                    int total, const double* my_recv, unsigned long long* my_flags, unsigned long long* state,
+                                                    int* err, double* v, const double* cf, const double* din, const double* xin, double* xout) {
+    __shared__ int s_fail;
+    const unsigned long long epoch = *(volatile unsigned long long*)state + 1ull;   // stable until the last CTA of THIS launch is done
     const int parity = (int)(epoch & 1ull);
-    const int n_ent = total * D;
-    const unsigned long long g = gridDim.x;
-    unsigned long long stage = cnt_base;
-    if (SMOOTH) {
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < niv * D; t += gridDim.x * blockDim.x) {
-            const int k = t / D, c = t - k * D;
-            const int64_t i = (int64_t)iv[k] * D + c;
-            v[i] = v[i] - (c1 != 0.0 ? c1 * din[i] : 0.0);            // additive increment c2 D^-1 r_local
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = t < niv * D;
+    if (threadIdx.x == 0) s_fail = 0;
+    int k = 0, c = 0, e0 = 0, e1 = 0;
+    int64_t i = 0;
+    double own = 0.0, dold = 0.0;
+    if (on) {
+        k = t / D; c = t - k * D;
+        i = (int64_t)iv[k] * D + c;
+        e0 = iv_ptr[k]; e1 = iv_ptr[k + 1];
+        own = v[i];
+        if (SMOOTH) {
+            const double c1 = cf ? cf[0] : 0.0;
+            dold = (c1 != 0.0 && din) ? c1 * din[i] : 0.0;
+            own -= dold;                                              // additive increment c2 D^-1 r_local
         }
-        stage += g;
-        p2p_grid_barrier(counter, stage, err);
-    }
-    // 1. put: my additive values go straight into the neighbours' windows
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
-        const int k = t / D, c = t - k * D;
-        int n = 0;
-        while (n + 1 < nneigh && k >= offset[n + 1]) ++n;
-        double* dst = reinterpret_cast<double*>(peer_dst[n] + (unsigned long long)parity * peer_stride[n]) + (size_t)(k - offset[n]) * D + c;
-        *dst = v[(int64_t)idx[k] * D + c];
+        for (int e = e0; e < e1; ++e) {
+            const int nb = iv_nb[e];
+            double* dst = reinterpret_cast<double*>(peer_dst[nb] + (unsigned long long)parity * peer_stride[nb]) + (size_t)(iv_slot[e] - offset[nb]) * D + c;
+            *dst = own;
+        }
     }
     __threadfence_system();
     __syncthreads();
-    // grid-wide: every block has read v and issued its stores before anybody accumulates into v (a vertex shared with
-    // several neighbours is sent by one block and accumulated by another); the last block publishes the epoch
-    stage += g;
     if (threadIdx.x == 0) {
-        const unsigned long long old = atomicAdd(counter, 1ull);
-        if (old + 1 == stage) {
+        const unsigned long long old = atomicAdd(state + 1, 1ull);
+        if (old + 1 == gridDim.x) {                                   // every CTA's stores are out: publish the epoch
             __threadfence_system();
             for (int n = 0; n < nneigh; ++n) {
                 unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_flag[n]);
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
             }
         }
+    }
+    for (int n = threadIdx.x; n < nneigh; n += blockDim.x) {          // one polling thread per neighbour
         long long spins = 0;
-        while (*(volatile unsigned long long*)counter < stage)
-            if (++spins > 400000000ll) { *err = 2; break; }
-        // 2. wait for every neighbour's flag of this epoch
-        for (int n = 0; n < nneigh; ++n) {
-            spins = 0;
-            unsigned long long f;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(my_flags + neigh[n]) : "memory");
-                if (++spins > 400000000ll) { *err = 1; break; }
-            } while (f < epoch);
+        unsigned long long f;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(my_flags + neigh[n]) : "memory");
+            if (f >= epoch) break;
+            if (++spins > kP2PSpinLimit) { s_fail = 1; break; }
+        } while (true);
+    }
+    __syncthreads();
+    const bool fail = s_fail != 0;
+    if (fail && threadIdx.x == 0) *err = 1;
+    if (on && !fail) {
+        const double* buf = my_recv + (size_t)parity * total * D;
+        double tot = 0.0;
+        int e = e0;
+        for (int pos = 0; pos <= nneigh; ++pos) {                      // ascending rank order, own value at position my_pos
+            if (pos == my_pos) { tot += own; continue; }
+            const int nb = pos < my_pos ? pos : pos - 1;
+            if (e < e1 && iv_nb[e] == nb) { tot += __ldcg(buf + (size_t)iv_slot[e] * D + c); ++e; }
+        }
+        if (SMOOTH) {
+            const double dn = dold + tot;
+            v[i] = dn;
+            xout[i] = (xin ? xin[i] : 0.0) + dn;
+        } else {
+            v[i] = tot;
         }
     }
     __syncthreads();
-    // 3. accumulate what the neighbours wrote
-    const double* buf = my_recv + (size_t)parity * n_ent;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_ent; t += gridDim.x * blockDim.x) {
-        const int k = t / D, c = t - k * D;
-        atomicAdd(v + (int64_t)idx[k] * D + c, __ldcg(buf + t));
-    }
-    if (SMOOTH) {
-        stage += g;
-        p2p_grid_barrier(counter, stage, err);
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < niv * D; t += gridDim.x * blockDim.x) {
-            const int k = t / D, c = t - k * D;
-            const int64_t i = (int64_t)iv[k] * D + c;
-            const double dn = (c1 != 0.0 ? c1 * din[i] : 0.0) + v[i];
-            v[i] = dn;
-            xout[i] = (xin ? xin[i] : 0.0) + dn;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(state + 2, 1ull);
+        if (old + 1 == gridDim.x) {                                   // last CTA out: every CTA has read the epoch and arrived
+            state[1] = 0ull;
+            state[2] = 0ull;
+            __threadfence();
+            *(volatile unsigned long long*)state = epoch;
         }
     }
 }

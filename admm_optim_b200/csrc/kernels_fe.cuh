@@ -215,10 +215,12 @@ __global__ void __launch_bounds__(128) k_assemble_hessian(int64_t ne, const int*
 
 // unit diagonal for Dirichlet dofs (DirichletBoundary adjust_jacobian, 3d_admm.lua:445-462)
 template <int D>
-__global__ void k_dirichlet_diag(int nv, const unsigned char* __restrict__ dirmask, const int* __restrict__ diagpos, double* __restrict__ vals) {
+__global__ void k_dirichlet_diag(int nv, const unsigned char* __restrict__ dirmask, const unsigned char* __restrict__ owned,
+                                 const int* __restrict__ diagpos, double* __restrict__ vals) {
+    // multi-GPU (owned != null): the operator is additive over the ranks, so only the owner of a shared vertex sets the 1
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nv * D; t += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
-        if ((dirmask[v] >> c) & 1) vals[(int64_t)diagpos[v] * D * D + c * D + c] = 1.0;
+        if ((dirmask[v] >> c) & 1) vals[(int64_t)diagpos[v] * D * D + c * D + c] = (!owned || owned[v]) ? 1.0 : 0.0;
     }
 }
 // Dirichlet dofs of a vector -> 0 (adjust_defect / adjust_solution with value 0, 3d_admm.lua:465-466,971)

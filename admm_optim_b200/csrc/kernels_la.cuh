@@ -66,10 +66,12 @@ __global__ void k_bicg_update_p(int64_t n, const double* sc, const double* r, co
 enum { CTL_TOL2 = 0, CTL_RED2, CTL_RR0, CTL_MAXIT, CTL_IT, CTL_COUNT };
 
 // Start of a BiCGStab solve in one pass: x_ws = x ; rh = r ; p = v = 0 ; |r|^2 -> scalars {rho = |r|^2, rho_old = alpha = omega = 1}
-// and the loop-control block {tol^2, reduction^2, |r0|^2, max its, it = 0}
+// and the loop-control block {tol^2, reduction^2, |r0|^2, max its, it = 0}.  owned != null (multi-GPU): |r|^2 over the owned copies only;
+// the caller all-reduces out2[0] and lets k_bicg_init_fix put the global value in place.
 __global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in, double* __restrict__ x_ws, const double* r, double* __restrict__ rh,
                                                    double* __restrict__ p, double* __restrict__ v, double* sc, double* partials,
-                                                   unsigned int* ticket, double* out2, double* ctl, double tol2, double red2, int max_it) {
+                                                   unsigned int* ticket, double* out2, double* ctl, double tol2, double red2, int max_it,
+                                                   const unsigned char* __restrict__ owned, int D) {
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double ri = r[i];
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in
         rh[i] = ri;
         p[i] = 0.0;
         v[i] = 0.0;
-        acc[0] += ri * ri;
+        if (!owned || owned[i / D]) acc[0] += ri * ri;
     }
     const bool last = grid_reduce<1, 0>(acc, partials, ticket, out2);
     if (last) {
@@ -89,6 +91,10 @@ __global__ void __launch_bounds__(256) k_bicg_init(int64_t n, const double* x_in
             ctl[CTL_TOL2] = tol2; ctl[CTL_RED2] = red2; ctl[CTL_RR0] = rr; ctl[CTL_MAXIT] = (double)max_it; ctl[CTL_IT] = 0.0;
         }
     }
+}
+__global__ void k_bicg_init_fix(double* sc, double* ctl, const double* out2) {
+    const double rr = out2[0];
+    sc[SC_RHO] = rr; sc[SC_RR] = rr; ctl[CTL_RR0] = rr;
 }
 // alpha = rho / <rh,v>;  s = r - alpha v;  reduce |s|^2
 __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ sc, const double* r, const double* v,
@@ -109,7 +115,10 @@ __global__ void __launch_bounds__(256) k_bicg_s(int64_t n, double* __restrict__ 
 // identical arithmetic to k_bicg_update_p / k_bicg_s followed by k_smooth_first, one pass and one launch less each.
 template <int FIRST>
 __global__ void __launch_bounds__(256) k_bicg_fused_first(int64_t n, const double* sc, const double* r, const double* v, double* pv,
-                                                          const double* __restrict__ dinv, const double* __restrict__ cf, double* d, double* x) {
+                                                          const double* __restrict__ dinv, const double* __restrict__ cf, double* d, double* x,
+                                                          double* uq, const unsigned char* __restrict__ owned, int D) {
+    // uq != null (multi-GPU): the preconditioner input is the unique (owner-only) form of the vector, written to uq; the first
+    // smoothing step acts on it (its additive result is summed over the interfaces by the exchange kernel that follows)
     pdl_trigger();
     const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     const double c2 = ld_static(cf + 1);                       // static during a solve: fetched before the dependency wait
@@ -127,7 +136,12 @@ __global__ void __launch_bounds__(256) k_bicg_fused_first(int64_t n, const doubl
         if (i != i0) di = dinv[i];
         const double pn = FIRST == 0 ? r[i] + a * (pv[i] - b * v[i]) : r[i] - a * v[i];
         pv[i] = pn;
-        const double dn = c2 * di * pn;
+        double rhs = pn;
+        if (uq) {
+            rhs = owned[i / D] ? pn : 0.0;
+            uq[i] = rhs;
+        }
+        const double dn = c2 * di * rhs;
         d[i] = dn;
         x[i] = dn;
     }
@@ -140,7 +154,9 @@ template <int ROLL>
 __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* sc, const double* ph, const double* sh,
                                                  const double* s, const double* t, const double* rh,
                                                  double* __restrict__ x, double* __restrict__ r, double* partials, unsigned int* ticket, double* out2,
-                                                 unsigned long long cond_handle, double* ctl, double* hist, int hist_cap) {
+                                                 unsigned long long cond_handle, double* ctl, double* hist, int hist_cap,
+                                                 const unsigned char* __restrict__ owned, int D) {
+    // owned != null (multi-GPU, ROLL = 0): the two sums run over the owned copies only; the caller all-reduces out2
     pdl_prologue();
     const double rho = sc[SC_RHO];
     const double alpha = rho / sc[SC_RV];
@@ -151,8 +167,10 @@ __global__ void __launch_bounds__(256) k_bicg_xr(int64_t n, double* sc, const do
         x[i] += alpha * ph[i] + omega * sh[i];
         double ri = s[i] - omega * t[i];
         r[i] = ri;
-        acc[0] += ri * ri;
-        acc[1] += rh[i] * ri;
+        if (!owned || owned[i / D]) {
+            acc[0] += ri * ri;
+            acc[1] += rh[i] * ri;
+        }
     }
     const bool last = grid_reduce<2, 0>(acc, partials, ticket, out2);   // out2[0] = |r|^2, out2[1] = <rh,r>
     if (ROLL && last) {          // every other block read the scalars before it took its ticket
@@ -666,7 +684,8 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
                                              const int* __restrict__ cmid, const int* __restrict__ cdiag,
                                              const int* __restrict__ frowptr, const int* __restrict__ fcol, const double* __restrict__ fvals,
                                              const int* __restrict__ pa, const int* __restrict__ pb,
-                                             const unsigned char* __restrict__ dirmask, double* __restrict__ cvals) {
+                                             const unsigned char* __restrict__ dirmask, const unsigned char* __restrict__ owned,
+                                             double* __restrict__ cvals) {
     // one CTA per coarse block row, its warps take the children of the row in turn (the walk over one child's fine row is a
     // dependent chain of binary searches and shared-memory atomics: the children are the available parallelism)
     constexpr int DD = D * D;
@@ -711,11 +730,41 @@ __global__ void __launch_bounds__(256) k_rap(int nvc, int maxrow, const int* __r
             double val = acc[k];
             if (dirmask) {
                 const unsigned char mJ = dirmask[cols[blk]];
-                if (((mI >> r) & 1) || ((mJ >> c) & 1)) val = (cols[blk] == (int)I && r == c) ? 1.0 : 0.0;
+                // unit diagonal of an eliminated dof; multi-GPU (owned != null): set by the owner of the vertex only (additive operator)
+                if (((mI >> r) & 1) || ((mJ >> c) & 1)) val = (cols[blk] == (int)I && r == c && (!owned || owned[I])) ? 1.0 : 0.0;
             }
             cvals[(int64_t)cs * DD + k] = val;
         }
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertical interface of the agglomerated multigrid (multi-GPU, rank 0; lib.cu Gmg::vcycle_base_gathered / gmg_gather_operator)
+// ---------------------------------------------------------------------------------------------
+// dst[gpos[b]] += src[b] for DD-entry blocks; the positions of ONE rank are distinct, the ranks are added one launch after the other
+__global__ void k_scatter_add_blocks(int64_t n, int DD, const int* __restrict__ gpos, const double* __restrict__ src, double* __restrict__ dst) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / DD;
+        const int e = (int)(t - b * DD);
+        dst[(int64_t)gpos[b] * DD + e] += src[t];
+    }
+}
+// global additive -> summed right-hand side: bg[v] = sum of the staged local values of the ranks holding v, in rank order
+__global__ void k_vgather(int nvg, int D, const int* __restrict__ ptr, const int* __restrict__ idx, const double* stage, double* __restrict__ bg) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nvg * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / D), c = (int)(t - (int64_t)v * D);
+        double s = 0.0;
+        for (int e = ptr[v]; e < ptr[v + 1]; ++e) s += stage[(int64_t)idx[e] * D + c];
+        bg[t] = s;
+    }
+}
+// every rank's (consistent) part of the global coarse solution, packed rank by rank
+__global__ void k_vscatter(int64_t ntot, int D, const int* __restrict__ l2g, const double* xg, double* __restrict__ stage) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ntot * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = t / D;
+        const int c = (int)(t - k * D);
+        stage[t] = xg[(int64_t)l2g[k] * D + c];
     }
 }
 

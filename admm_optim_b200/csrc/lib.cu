@@ -64,22 +64,34 @@ struct Domain {
     // every ADMM iteration resets the multipliers (3d_admm.lua:884-894), so the first Newton iteration of each asks for the
     // SAME u-independent operator: the latest such matrix (and the hierarchies built on it) is kept alive for the signature cache
     std::shared_ptr<MatrixData> keep_lam0;
-    // multi-GPU: shared-vertex interfaces per level (host staging until finalize) and the replicated level-0 numbering
+    // multi-GPU: this domain is one part of a decomposed global grid once interfaces were set (ab_domain_set_interface); a domain
+    // without interfaces on a multi-rank context is a plain local (replicated) domain.  Shared-vertex interfaces per level
+    // (host staging until finalize):
+    bool dist_enabled = false;
     struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
     std::vector<HostIface> host_iface;
     std::vector<Interface> iface;
-    int nv0_global = 0;
-    std::vector<int> l0_gid, vsub0_global;
+    // Hierarchical agglomeration (the reference keeps level 0 on one process and widens the process set level by level,
+    // 3d_admm.lua:151-183): levels <= gather_level live on rank 0 as ONE global, non-distributed hierarchy (`cdom`, the global
+    // grid refined gather_level times); the level-`gather_level` Galerkin operators of all ranks are summed into it at every
+    // solver:init, each V-cycle crosses the vertical interface once down (additive right-hand sides) and once up (solution).
+    int gather_level = -1;
+    Domain* cdom = nullptr;                        // rank 0 only; owned by the caller (ab_domain handle)
+    std::vector<int> g_nv;                         // rank 0: vertices of every rank on the gather level
+    std::vector<int64_t> g_nblk;                   // rank 0: blocks of every rank on the gather level
+    DevBuf<int> g_l2g;                             // rank 0: concatenated local -> global vertex ids
+    DevBuf<int> g_csr_ptr, g_csr_idx;              // rank 0: global vertex -> positions in the staging buffer, rank order
+    DevBuf<int> g_gpos;                            // rank 0: concatenated local block -> global block position
+    DevBuf<double> g_vstage, g_mstage;             // rank 0: staging for the ranks' vectors / operators
+    int64_t g_nv_total = 0, g_nblk_total = 0;
     // P2P window (CUDA IPC): [flags: nlevels*nranks u64][level 0: 2 parity buffers][level 1: ...]
     unsigned char* window = nullptr;
     size_t window_bytes = 0;
     std::vector<size_t> win_level_base;
     std::vector<void*> peer_windows;        // opened IPC mappings, by rank
     bool p2p_connected = false;
-    DevBuf<unsigned long long> p2p_done;
-    unsigned long long p2p_done_total = 0;
     DevBuf<int> p2p_err;
-    bool distributed() const { return ctx && ctx->comm && ctx->comm->nranks > 1; }
+    bool distributed() const { return dist_enabled && ctx && ctx->comm && ctx->comm->nranks > 1; }
     int dim() const { return mesh.dim; }
     int top() const { return (int)mesh.levels.size() - 1; }
     void finalize();
@@ -163,25 +175,48 @@ void Domain::finalize() {
     }
     if (distributed()) {
         AB_REQUIRE((int)host_iface.size() == nl, AB_ERR_STATE, "multi-GPU: ab_domain_set_interface must be called for every level before the first ApproximationSpace");
-        AB_REQUIRE((int)l0_gid.size() == mesh.levels[0].nv, AB_ERR_STATE, "multi-GPU: ab_domain_set_global_coarse missing");
+        AB_REQUIRE(gather_level >= 0 && gather_level < nl - 1, AB_ERR_STATE, "multi-GPU: ab_domain_set_gather missing (the gather level must lie below the top level)");
         iface.resize(nl);
+        const int me = ctx->comm->rank;
         for (int l = 0; l < nl; ++l) {
             HostIface& H = host_iface[l];
             Interface& I = iface[l];
-            AB_REQUIRE((int)H.owned.size() == mesh.levels[l].nv, AB_ERR_ARG, "interface: owned mask size mismatch");
+            const int nv = mesh.levels[l].nv;
+            AB_REQUIRE((int)H.owned.size() == nv, AB_ERR_ARG, "interface: owned mask size mismatch");
             I.neigh = H.neigh; I.offset = H.offset;
             I.total = H.offset.empty() ? 0 : H.offset.back();
-            std::vector<int> iv(H.idx);
-            std::sort(iv.begin(), iv.end());
-            iv.erase(std::unique(iv.begin(), iv.end()), iv.end());
+            I.my_pos = 0;
+            for (size_t n = 0; n < H.neigh.size(); ++n) {
+                AB_REQUIRE(H.neigh[n] != me && (n == 0 || H.neigh[n] > H.neigh[n - 1]), AB_ERR_ARG, "interface: neighbour ranks must be ascending and exclude this rank");
+                if (H.neigh[n] < me) I.my_pos++;
+            }
+            // unique interface vertices ordered by (first neighbour, slot); CSR vertex -> (slot, neighbour index), neighbours ascending
+            std::vector<int> pos((size_t)nv, -1), iv;
+            for (size_t n = 0; n < H.neigh.size(); ++n)
+                for (int k = H.offset[n]; k < H.offset[n + 1]; ++k)
+                    if (pos[H.idx[k]] < 0) { pos[H.idx[k]] = (int)iv.size(); iv.push_back(H.idx[k]); }
+            std::vector<int> ptr(iv.size() + 1, 0);
+            for (int v : H.idx) ptr[pos[v] + 1]++;
+            for (size_t k = 0; k < iv.size(); ++k) ptr[k + 1] += ptr[k];
+            std::vector<int> fill(ptr.begin(), ptr.end() - 1), slot((size_t)I.total), nb((size_t)I.total);
+            for (size_t n = 0; n < H.neigh.size(); ++n)
+                for (int k = H.offset[n]; k < H.offset[n + 1]; ++k) {
+                    const int e = fill[pos[H.idx[k]]]++;
+                    slot[e] = k; nb[e] = (int)n;
+                }
             I.niv = (int)iv.size();
             I.idx.upload(H.idx, ctx->stream);
             I.iv.upload(iv, ctx->stream);
+            I.iv_ptr.upload(ptr, ctx->stream);
+            I.iv_slot.upload(slot, ctx->stream);
+            I.iv_nb.upload(nb, ctx->stream);
             I.owned.upload(H.owned, ctx->stream);
             const int maxc = mesh.dim;     // P1 vectors with dim components
             I.send.alloc((size_t)std::max(I.total, 1) * maxc);
             I.recv.alloc((size_t)std::max(I.total, 1) * maxc);
             I.save.alloc((size_t)std::max(I.niv, 1) * 2 * maxc);
+            I.state.alloc(4);
+            I.state.zero(ctx->stream);
         }
     }
     AB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -189,19 +224,23 @@ void Domain::finalize() {
 }
 
 // interface sum: additive -> consistent for a P1 vector with D components on `level`
+static void launch_xchg(Domain* dom, Interface& I, int D, bool smooth, double* v, const double* cf, const double* din, const double* xin, double* xout) {
+    Context* ctx = dom->ctx;
+    const int g = std::max(1, (I.niv * D + 255) / 256);
+    if (smooth)
+        AB_LAUNCH(ctx, (k_iface_xchg<true>), g, 256, 0, I.niv, D, (int)I.neigh.size(), I.my_pos, I.iv.p, I.iv_ptr.p, I.iv_slot.p, I.iv_nb.p, I.d_offset.p, I.d_neigh.p,
+                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.total, I.win_recv, I.win_flags, I.state.p, dom->p2p_err.p, v, cf, din, xin, xout);
+    else
+        AB_LAUNCH(ctx, (k_iface_xchg<false>), g, 256, 0, I.niv, D, (int)I.neigh.size(), I.my_pos, I.iv.p, I.iv_ptr.p, I.iv_slot.p, I.iv_nb.p, I.d_offset.p, I.d_neigh.p,
+                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.total, I.win_recv, I.win_flags, I.state.p, dom->p2p_err.p, v, cf, din, xin, xout);
+}
 static void exchange_sum(Domain* dom, int level, double* v, int D) {
     if (!dom->distributed()) return;
     Context* ctx = dom->ctx;
     Interface& I = dom->iface[level];
     if (I.total == 0) return;
     if (dom->p2p_connected) {   // one fused kernel over NVLink peer memory
-        I.epoch++;
-        const int g = std::max(1, std::min(grid_for((int64_t)I.total * D, 256, 64), ctx->num_sms));
-        const unsigned long long base = dom->p2p_done_total;
-        dom->p2p_done_total += (unsigned long long)g;
-        AB_LAUNCH(ctx, (k_iface_exchange_p2p<false>), g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, base, I.idx.p, I.d_offset.p, I.d_neigh.p,
-                  I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, v, 0,
-                  (const int*)nullptr, 0.0, (const double*)nullptr, (const double*)nullptr, (double*)nullptr);
+        launch_xchg(dom, I, D, false, v, nullptr, nullptr, nullptr, nullptr);
         return;
     }
     NcclApi& nc = NcclApi::get();
@@ -215,17 +254,12 @@ static void exchange_sum(Domain* dom, int level, double* v, int D) {
     AB_NCCL(nc.GroupEnd());
     AB_LAUNCH(ctx, k_iface_unpack_add, grid_for((int64_t)I.total * D, 256, ctx->num_sms * 4), 256, 0, I.total, D, I.idx.p, I.recv.p, v);
 }
-// smoother interface fix-up fused around the peer-to-peer sum (needs the P2P window): see k_iface_exchange_p2p<true>
-static void smooth_exchange_p2p(Domain* dom, int level, int D, double c1, const double* din, double* dout, const double* xin, double* xout) {
-    Context* ctx = dom->ctx;
+// smoother interface fix-up fused around the peer-to-peer sum (needs the P2P window): see k_iface_xchg<true>.  cf -> (c1, c2) of the
+// step in device memory (the launch stays valid when a new solver:init changes the coefficients: graph replay)
+static void smooth_exchange_p2p(Domain* dom, int level, int D, const double* cf, const double* din, double* dout, const double* xin, double* xout) {
     Interface& I = dom->iface[level];
-    I.epoch++;
-    const int g = std::max(1, std::min(grid_for((int64_t)I.total * D, 256, 64), ctx->num_sms));
-    const unsigned long long base = dom->p2p_done_total;
-    dom->p2p_done_total += 3ull * (unsigned long long)g;
-    AB_LAUNCH(ctx, (k_iface_exchange_p2p<true>), g, 256, 0, I.total, D, (int)I.neigh.size(), I.epoch, base, I.idx.p, I.d_offset.p, I.d_neigh.p,
-              I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.win_recv, I.win_flags, dom->p2p_done.p, dom->p2p_err.p, dout, I.niv, I.iv.p, c1,
-              din, xin, xout);
+    if (I.total == 0) return;
+    launch_xchg(dom, I, D, true, dout, cf, din, xin, xout);
 }
 // global sum / max of device scalars (no-op on one GPU)
 static void allreduce_dev(Context* ctx, double* d, int n, bool max_op = false) {
@@ -336,7 +370,6 @@ struct MatrixData {
     DevBuf<double> vals;
     Signature sig;
     bool assembled = false;
-    DomainDisc* dd = nullptr;                      // for Dirichlet masks on coarse levels
     std::map<std::string, std::shared_ptr<Gmg>> gmg;   // hierarchies built on this matrix, keyed by descriptor
 };
 
@@ -470,11 +503,13 @@ struct GmgLevel {
 // ONCE into an executable CUDA graph and replayed by all of them (x is copied in and out of the workspace).
 struct KrylovWs {
     DevBuf<double> r, rh, p, v, s, t, ph, sh, x, sc, out2;
+    DevBuf<double> uq, bq;                 // multi-GPU: unique (owner-only) form of the preconditioner input / of a consistent right-hand side
     DevBuf<double> ctl, hist;              // loop-control block and |r|^2 history of the device-side loop
     cudaGraphExec_t exec_loop = nullptr;   // the WHOLE iteration loop: conditional WHILE node around one iteration + D2H of the result
     std::vector<const void*> key_loop;
     int64_t nodes_loop = 0;
     bool loop_failed = false;              // the driver refused the conditional graph once: stay on per-iteration replay
+    bool graph_failed = false;             // multi-GPU: the capture (kernels + NCCL calls) was refused once: stay on stream launches
     cudaGraphExec_t exec = nullptr;        // one full BiCGStab iteration (2 V-cycles, 2 SpMV, recurrences, D2H of the scalars)
     std::vector<const void*> key;          // every pointer baked into the captured launches
     int64_t nodes = 0;                     // kernel launches per replay
@@ -487,28 +522,34 @@ struct Gmg {
     Domain* dom = nullptr;
     ab_gmg_desc desc;
     std::vector<GmgLevel> L;
+    // lowest level of THIS hierarchy: 0 on one GPU (dense inverse); distributed: the gather level, which is solved on rank 0 by
+    // `coarse`, a plain single-GPU hierarchy over the global coarse grid (Domain::cdom)
+    int base = 0;
+    std::vector<std::pair<int, int>> dir;               // Dirichlet set (subset, component), sorted
+    std::vector<DevBuf<unsigned char>> masks;           // per level
     // coarse level: dense inverse on the free dofs
     int n_free = 0, n0 = 0;
     DevBuf<double> Ainv, Mwork, gjpanel;
     DevBuf<int> free2dof, dof2free, pivrow, fail;
     bool force_pivoting = false;      // set when the unpivoted blocked elimination met a tiny pivot
-    DevBuf<int> dof2gfree;            // multi-GPU: local level-0 dof -> global free-dof index (-1: Dirichlet)
-    DevBuf<double> bg, xg;            // global coarse vectors (replicated solve)
+    std::shared_ptr<Gmg> coarse;      // multi-GPU, rank 0
+    DevBuf<double> gvals, bg, xg;     // multi-GPU, rank 0: summed operator of the gather level, global coarse right-hand side / solution
     DevBuf<double> coefs;             // smoother coefficients, [level][pre|post][step][c1,c2]
     int coef_stride = 0;              // doubles per (level, pre|post) slot
-    std::unique_ptr<KrylovWs> ws;     // single-GPU BiCGStab workspace + iteration graph
+    std::unique_ptr<KrylovWs> ws;     // BiCGStab workspace + iteration graph
     std::string pool_key;             // descriptor + Dirichlet set (Domain::gmg_pool)
-    void setup(const std::shared_ptr<MatrixData>& A);
+    void setup(const double* top_vals, const std::vector<std::pair<int, int>>& dir_sorted);
     void vcycle(int l, const double* b, double* x, bool first_done = false);
+    void vcycle_base_gathered(const double* b, double* x);
     void smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
                 bool first_done = false);
     // first_done: the caller already performed the first pre-smoothing step of the top level (fused into its own kernel)
     void apply(const double* r, double* z, bool first_done = false) { vcycle((int)L.size() - 1, r, z, first_done); }
     // where the first pre-smoothing step (zero initial guess) of a cycle writing its result to z puts d and x on the top level;
-    // false when that step cannot be fused by the caller (single level, no pre-smoothing, multi-GPU interface fix-ups)
+    // false when that step cannot be fused by the caller (single level, no pre-smoothing, NCCL-fallback interface fix-ups)
     bool first_step_targets(double* z, double** d, double** x) {
         const int top = (int)L.size() - 1;
-        if (top < 1 || desc.pre_smooth < 1 || dom->distributed() || !L[top].cf_pre) return false;
+        if (top <= base || desc.pre_smooth < 1 || (dom->distributed() && !dom->p2p_connected) || !L[top].cf_pre) return false;
         *d = L[top].d.p;
         *x = ((desc.pre_smooth - 1) % 2 == 0) ? z : L[top].x2.p;
         return true;
@@ -538,14 +579,46 @@ static void smoother_coefs(const ab_gmg_desc& desc, double lmax, int nu, std::ve
     }
 }
 
+// multi-GPU: the additive gather-level operators of all ranks are summed into the global operator on rank 0 (rank order:
+// reproducible), which then builds its single-GPU hierarchy below
 template <int D>
-static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
+static void gmg_gather_operator(Gmg& G) {
     Domain* dom = G.dom;
     Context* ctx = dom->ctx;
-    const int top = dom->top();
+    Comm& cm = *ctx->comm;
+    NcclApi& nc = NcclApi::get();
+    constexpr int DD = D * D;
+    const LevelDev& Lb = dom->dev[G.base];
+    const double* mine = G.L[G.base].vals;
+    if (cm.rank != 0) {
+        AB_NCCL(nc.Send(mine, (size_t)Lb.nnzb * DD, ncclFloat64, 0, cm.comm, ctx->stream));
+        return;
+    }
+    std::vector<int64_t> off((size_t)cm.nranks + 1, 0);
+    for (int r = 0; r < cm.nranks; ++r) off[r + 1] = off[r] + dom->g_nblk[r];
+    AB_REQUIRE(dom->g_nblk[0] == Lb.nnzb, AB_ERR_STATE, "gather maps do not match the local pattern");
+    AB_NCCL(nc.GroupStart());
+    for (int r = 1; r < cm.nranks; ++r)
+        AB_NCCL(nc.Recv(dom->g_mstage.p + (size_t)off[r] * DD, (size_t)dom->g_nblk[r] * DD, ncclFloat64, r, cm.comm, ctx->stream));
+    AB_NCCL(nc.GroupEnd());
+    AB_CUDA(cudaMemsetAsync(G.gvals.p, 0, G.gvals.n * sizeof(double), ctx->stream));
+    for (int r = 0; r < cm.nranks; ++r) {
+        const int64_t cnt = dom->g_nblk[r] * DD;
+        const double* src = r == 0 ? mine : dom->g_mstage.p + (size_t)off[r] * DD;
+        AB_LAUNCH(ctx, k_scatter_add_blocks, grid_for(cnt, 256, ctx->num_sms * 8), 256, 0, cnt, DD, dom->g_gpos.p + off[r], src, G.gvals.p);
+    }
+    G.coarse->setup(G.gvals.p, G.dir);
+}
+
+template <int D>
+static void gmg_setup_kernels(Gmg& G) {
+    Domain* dom = G.dom;
+    Context* ctx = dom->ctx;
+    const int top = dom->top(), base = G.base;
+    const bool dist = dom->distributed();
     constexpr int DD = D * D;
     // Galerkin coarse operators, top-down
-    for (int l = top; l > 0; --l) {
+    for (int l = top; l > base; --l) {
         TraceTimer tt(ctx->stream, "gmg: rap level");
         const LevelDev& F = dom->dev[l];
         const LevelDev& C = dom->dev[l - 1];
@@ -560,15 +633,16 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
         }
         AB_REQUIRE(smem <= 200 * 1024, AB_ERR_UNSUPPORTED, "coarse row too long for k_rap shared memory");
         const int grid = (int)std::min<int64_t>((int64_t)C.nv, (int64_t)ctx->num_sms * 8);
+        // distributed: the unit diagonal of an eliminated dof is set by the owner of the vertex only (additive operators)
         AB_LAUNCH(ctx, (k_rap<D>), std::max(grid, 1), 256, smem, C.nv, C.maxrow, C.rowptr.p, C.colidx.p, C.mid.p, C.diagpos.p, F.rowptr.p,
-                  F.colidx.p, G.L[l].vals, F.pa.p, F.pb.p, gc.mask, gc.vals_own.p);
+                  F.colidx.p, G.L[l].vals, F.pa.p, F.pb.p, gc.mask, dist ? dom->iface[l - 1].owned.p : (const unsigned char*)nullptr, gc.vals_own.p);
     }
-    // smoother data on levels >= 1
-    for (int l = 1; l <= top; ++l) {
+    // smoother data on the levels above the base
+    for (int l = base + 1; l <= top; ++l) {
         const LevelDev& Ld = dom->dev[l];
         GmgLevel& g = G.L[l];
         const int64_t n = (int64_t)Ld.nv * D;
-        if (!dom->distributed()) {
+        if (!dist) {
             AB_LAUNCH(ctx, (k_diag_gershgorin<D>), red_grid(ctx, n), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p,
                       ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
         } else {   // additive rows: diagonal and |row| sums are made consistent across the interfaces first
@@ -578,12 +652,19 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
             AB_LAUNCH(ctx, k_dinv_lmax, red_grid(ctx, n), 256, 0, n, g.dinv.p, g.r.p, ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
         }
     }
-    if (top >= 1) allreduce_dev(ctx, ctx->d_results + 1, top, true);
+    if (dist) {
+        if (top > base) allreduce_dev(ctx, ctx->d_results + base + 1, top - base, true);
+        AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
+        TraceTimer tt(ctx->stream, "gmg: gather + coarse setup");
+        gmg_gather_operator<D>(G);
+        return;
+    }
     // dense inverse of level 0 (free dofs)
     {
         TraceTimer tt(ctx->stream, "gmg: dense inverse");
         const LevelDev& L0 = dom->dev[0];
         const int n = G.n_free;
+        AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
         if (n > 0) {
             constexpr int KR = 16;                                 // pivots per barrier of the shared-memory-resident kernel
             const int grid_r = std::min(ctx->num_sms, n);
@@ -593,10 +674,7 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
             const int ld = resident ? n : 2 * n;                   // resident: A (n x n) in, A^-1 straight into Ainv; otherwise [A | I]
             AB_CUDA(cudaMemsetAsync(G.Mwork.p, 0, (size_t)n * ld * sizeof(double), ctx->stream));
             AB_LAUNCH(ctx, (k_bsr_to_dense<D>), grid_for(L0.nnzb * DD, 256, ctx->num_sms * 8), 256, 0, L0.nv, L0.rowptr.p, L0.colidx.p, G.L[0].vals,
-                      dom->distributed() ? G.dof2gfree.p : G.dof2free.p, ld, G.Mwork.p);
-            // multi-GPU: the additive level-0 operators are summed into the replicated global coarse matrix
-            if (dom->distributed()) { AB_REQUIRE((int64_t)n * ld < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "coarse matrix too large"); allreduce_dev(ctx, G.Mwork.p, n * ld); }
-            AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
+                      G.dof2free.p, ld, G.Mwork.p);
             int nn = n;
             double* M = G.Mwork.p;
             int* piv = G.pivrow.p;
@@ -630,63 +708,66 @@ static void gmg_setup_kernels(Gmg& G, const std::shared_ptr<MatrixData>& A) {
     }
 }
 
-void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
+void Gmg::setup(const double* top_vals, const std::vector<std::pair<int, int>>& dir_sorted) {
     Context* ctx = dom->ctx;
     TraceTimer tt(ctx->stream, "gmg: setup total");
+    dom->finalize();
     const int top = dom->top(), dim = dom->dim();
+    const bool dist = dom->distributed();
     const bool first = L.empty();
     if (first) {
+        dir = dir_sorted;
+        base = dist ? dom->gather_level : 0;
         L.resize(top + 1);
-        for (int l = 0; l <= top; ++l) {
+        masks.resize(top + 1);
+        for (int l = base; l <= top; ++l) {
             const int64_t n = (int64_t)dom->dev[l].nv * dim;
             GmgLevel& g = L[l];
             if (l < top) { g.x.alloc(n); g.b.alloc(n); }
-            if (l > 0) { g.r.alloc(n); g.d.alloc(n); g.x2.alloc(n); g.dinv.alloc(n); if (dom->distributed()) g.d2.alloc(n); }
+            if (l > base) { g.r.alloc(n); g.d.alloc(n); g.x2.alloc(n); g.dinv.alloc(n); if (dist) g.d2.alloc(n); }
+            if (!dir.empty()) {
+                const HostLevel& H = dom->mesh.levels[l];
+                std::vector<unsigned char> m((size_t)H.nv, 0);
+                for (auto& e : dir)
+                    for (int v = 0; v < H.nv; ++v)
+                        if (H.vsub[v] == e.first) m[v] |= (unsigned char)(1u << e.second);
+                masks[l].upload(m, ctx->stream);
+                g.mask = masks[l].p;
+            }
         }
-        // free-dof numbering of level 0
-        const HostLevel& H0 = dom->mesh.levels[0];
-        n0 = H0.nv * dim;
-        std::vector<unsigned char> m((size_t)H0.nv, 0);
-        if (A->dd)
-            for (auto& e : A->dd->dir)
+        fail.alloc(1);
+        if (!dist) {       // free-dof numbering of level 0 (dense base solver)
+            const HostLevel& H0 = dom->mesh.levels[0];
+            n0 = H0.nv * dim;
+            std::vector<unsigned char> m((size_t)H0.nv, 0);
+            for (auto& e : dir)
                 for (int v = 0; v < H0.nv; ++v)
                     if (H0.vsub[v] == e.first) m[v] |= (unsigned char)(1u << e.second);
-        std::vector<int> f2d, d2f((size_t)n0, -1);
-        for (int v = 0; v < H0.nv; ++v)
-            for (int c = 0; c < dim; ++c)
-                if (!((m[v] >> c) & 1)) { d2f[(size_t)v * dim + c] = (int)f2d.size(); f2d.push_back(v * dim + c); }
-        n_free = (int)f2d.size();
-        if (dom->distributed()) {   // replicated coarse solve on the GLOBAL level-0 mesh
-            const int nv0g = dom->nv0_global;
-            std::vector<unsigned char> mg((size_t)nv0g, 0);
-            if (A->dd)
-                for (auto& e : A->dd->dir)
-                    for (int v = 0; v < nv0g; ++v)
-                        if (dom->vsub0_global[v] == e.first) mg[v] |= (unsigned char)(1u << e.second);
-            std::vector<int> gfree((size_t)nv0g * dim, -1);
-            int cnt = 0;
-            for (int v = 0; v < nv0g; ++v)
-                for (int c = 0; c < dim; ++c)
-                    if (!((mg[v] >> c) & 1)) gfree[(size_t)v * dim + c] = cnt++;
-            std::vector<int> d2g((size_t)n0, -1);
+            std::vector<int> f2d, d2f((size_t)n0, -1);
             for (int v = 0; v < H0.nv; ++v)
-                for (int c = 0; c < dim; ++c) d2g[(size_t)v * dim + c] = gfree[(size_t)dom->l0_gid[v] * dim + c];
-            n_free = cnt;
-            dof2gfree.upload(d2g, ctx->stream);
-            bg.alloc(std::max(cnt, 1));
-            xg.alloc(std::max(cnt, 1));
+                for (int c = 0; c < dim; ++c)
+                    if (!((m[v] >> c) & 1)) { d2f[(size_t)v * dim + c] = (int)f2d.size(); f2d.push_back(v * dim + c); }
+            n_free = (int)f2d.size();
+            free2dof.upload(f2d, ctx->stream);
+            dof2free.upload(d2f, ctx->stream);
+            if (n_free) { Ainv.alloc((size_t)n_free * n_free); Mwork.alloc((size_t)n_free * 2 * n_free); }
+            pivrow.alloc(std::max(n_free, 1));
+        } else if (ctx->comm->rank == 0) {   // the global coarse hierarchy below the gather level
+            AB_REQUIRE(dom->cdom, AB_ERR_STATE, "multi-GPU: rank 0 has no coarse domain (ab_domain_set_gather)");
+            dom->cdom->finalize();
+            const LevelDev& Cg = dom->cdom->dev[dom->cdom->top()];
+            gvals.alloc((size_t)Cg.nnzb * dim * dim);
+            bg.alloc((size_t)Cg.nv * dim);
+            xg.alloc((size_t)Cg.nv * dim);
+            coarse = std::make_shared<Gmg>();
+            coarse->dom = dom->cdom;
+            coarse->desc = desc;
         }
-        free2dof.upload(f2d, ctx->stream);
-        dof2free.upload(d2f, ctx->stream);
-        if (n_free) { Ainv.alloc((size_t)n_free * n_free); Mwork.alloc((size_t)n_free * 2 * n_free); }
-        pivrow.alloc(std::max(n_free, 1));
-        fail.alloc(1);
         coef_stride = 2 * std::max(1, std::max(desc.pre_smooth, desc.post_smooth));
         coefs.alloc((size_t)(top + 1) * 2 * coef_stride);
     }
-    for (int l = 0; l <= top; ++l) L[l].mask = A->dd ? A->dd->mask(l) : nullptr;
-    L[top].vals = A->vals.p;
-    if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
+    L[top].vals = top_vals;
+    if (dim == 2) gmg_setup_kernels<2>(*this); else gmg_setup_kernels<3>(*this);
     // ONE synchronisation per setup: Gershgorin bounds and the singularity flag come back together (pinned memory)
     int* h_fail = reinterpret_cast<int*>(ctx->h_results + Context::kResultSlots - 1);
     auto fetch = [&]() {
@@ -698,12 +779,12 @@ void Gmg::setup(const std::shared_ptr<MatrixData>& A) {
     int hfail = fetch();
     if (hfail == 2 && !force_pivoting) {          // tiny pivot without row exchanges: redo everything with partial pivoting
         force_pivoting = true;
-        if (dim == 2) gmg_setup_kernels<2>(*this, A); else gmg_setup_kernels<3>(*this, A);
+        if (dim == 2) gmg_setup_kernels<2>(*this); else gmg_setup_kernels<3>(*this);
         hfail = fetch();
     }
-    if (top >= 1) {
+    if (top > base) {
         std::vector<double> hc((size_t)(top + 1) * 2 * coef_stride, 0.0);
-        for (int l = 1; l <= top; ++l) {
+        for (int l = base + 1; l <= top; ++l) {
             L[l].lmax = ctx->h_results[l - 1];
             smoother_coefs(desc, L[l].lmax, desc.pre_smooth, L[l].coef_pre);
             smoother_coefs(desc, L[l].lmax, desc.post_smooth, L[l].coef_post);
@@ -739,8 +820,8 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     if (zero_guess) {
         cur = ((nu - 1) % 2 == 0) ? 0 : 1;
         if (!first_done) AB_LAUNCH_PDL(ctx, k_smooth_first, ew_grid(ctx, n), 256, 0, n, coef[0].second, g.dinv.p, b, dbuf[dcur], bufs[cur], cf);
-        if (p2p) {          // d = c2 D^-1 b is additive at the interfaces: sum it, x = d there -- one fused launch
-            smooth_exchange_p2p(dom, l, D, 0.0, nullptr, dbuf[dcur], nullptr, bufs[cur]);
+        if (p2p) {          // d = c2 D^-1 b is additive at the interfaces: sum it, x = d there -- one fused launch (c1 = 0 in cf[0])
+            smooth_exchange_p2p(dom, l, D, cf, nullptr, dbuf[dcur], nullptr, bufs[cur]);
         } else if (dist) {
             AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, (const double*)nullptr, (const double*)nullptr, I->save.p);
             exchange_sum(dom, l, g.d.p, D);
@@ -755,13 +836,14 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
         // multi-GPU: the local step yields d_new = c1 d_old + c2 D^-1 r_local at shared vertices; the increment
         // c2 D^-1 r_local is additive -> sum it over the interfaces and rebuild d, x there (comm.cuh)
         const double c1 = coef[k].first, c2 = coef[k].second;
+        const double* cfk = cf ? cf + 2 * k : nullptr;
         if (p2p) {
-            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, dbuf[dcur], c1, c2, nullptr, nullptr, dbuf[1 - dcur], nullptr, 1);
-            smooth_exchange_p2p(dom, l, D, c1, dbuf[dcur], dbuf[1 - dcur], bufs[cur], bufs[1 - cur]);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, dbuf[dcur], c1, c2, nullptr, nullptr, dbuf[1 - dcur], cfk, 1);
+            smooth_exchange_p2p(dom, l, D, cfk, dbuf[dcur], dbuf[1 - dcur], bufs[cur], bufs[1 - cur]);
             dcur = 1 - dcur;
         } else {
             if (dist) AB_LAUNCH(ctx, k_iface_save, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1 != 0.0 ? g.d.p : (const double*)nullptr, (const double*)bufs[cur], I->save.p);
-            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2, nullptr, nullptr, nullptr, cf ? cf + 2 * k : nullptr, 1);
+            spmv(ctx, dom->dim(), Ld, g.vals, 2, 0, bufs[cur], b, bufs[1 - cur], g.dinv.p, g.d.p, c1, c2, nullptr, nullptr, nullptr, cfk, 1);
             if (dist) {
                 AB_LAUNCH(ctx, k_iface_inc, grid_for((int64_t)I->niv * D, 256, ctx->num_sms), 256, 0, I->niv, D, I->iv.p, c1, I->save.p, g.d.p);
                 exchange_sum(dom, l, g.d.p, D);
@@ -772,28 +854,51 @@ void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, con
     }
 }
 
+// multi-GPU base level: the additive right-hand sides of all ranks cross the vertical interface to rank 0, which runs the
+// single-GPU cycle of the global coarse hierarchy and hands every rank its (consistent) part of the solution
+void Gmg::vcycle_base_gathered(const double* b, double* x) {
+    Context* ctx = dom->ctx;
+    Comm& cm = *ctx->comm;
+    NcclApi& nc = NcclApi::get();
+    const int D = dom->dim();
+    const size_t n_loc = (size_t)dom->dev[base].nv * D;
+    if (cm.rank != 0) {
+        AB_NCCL(nc.Send(b, n_loc, ncclFloat64, 0, cm.comm, ctx->stream));
+        AB_NCCL(nc.Recv(x, n_loc, ncclFloat64, 0, cm.comm, ctx->stream));
+        return;
+    }
+    std::vector<int64_t> off((size_t)cm.nranks + 1, 0);
+    for (int r = 0; r < cm.nranks; ++r) off[r + 1] = off[r] + dom->g_nv[r];
+    double* st = dom->g_vstage.p;
+    dev_copy(ctx, (int64_t)n_loc, b, st);
+    AB_NCCL(nc.GroupStart());
+    for (int r = 1; r < cm.nranks; ++r) AB_NCCL(nc.Recv(st + (size_t)off[r] * D, (size_t)dom->g_nv[r] * D, ncclFloat64, r, cm.comm, ctx->stream));
+    AB_NCCL(nc.GroupEnd());
+    const int nvg = dom->cdom->dev[dom->cdom->top()].nv;
+    AB_LAUNCH(ctx, k_vgather, ew_grid(ctx, (int64_t)nvg * D), 256, 0, nvg, D, dom->g_csr_ptr.p, dom->g_csr_idx.p, st, bg.p);
+    coarse->apply(bg.p, xg.p);
+    AB_LAUNCH(ctx, k_vscatter, ew_grid(ctx, dom->g_nv_total * D), 256, 0, dom->g_nv_total, D, dom->g_l2g.p, xg.p, st);
+    AB_NCCL(nc.GroupStart());
+    for (int r = 1; r < cm.nranks; ++r) AB_NCCL(nc.Send(st + (size_t)off[r] * D, (size_t)dom->g_nv[r] * D, ncclFloat64, r, cm.comm, ctx->stream));
+    AB_NCCL(nc.GroupEnd());
+    dev_copy(ctx, (int64_t)n_loc, st, x);
+}
+
 void Gmg::vcycle(int l, const double* b, double* x, bool first_done) {
     Context* ctx = dom->ctx;
     const int dim = dom->dim();
-    if (l == 0) {
+    if (l == base) {
+        if (dom->distributed()) { vcycle_base_gathered(b, x); return; }
         const int n = n_free;
         const int grid = std::max(1, std::min((n + 7) / 8, ctx->num_sms * 8));
-        if (!dom->distributed()) {
-            AB_LAUNCH_PDL(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x, 1);
-        } else {   // replicated solve of the global level-0 system (the reference keeps level 0 on one process, 3d_admm.lua:158-161)
-            AB_CUDA(cudaMemsetAsync(bg.p, 0, (size_t)n * sizeof(double), ctx->stream));
-            AB_LAUNCH(ctx, k_coarse_gather, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, b, bg.p);
-            allreduce_dev(ctx, bg.p, n);
-            AB_LAUNCH(ctx, k_dense_gemv, grid, 256, 0, n, Ainv.p, bg.p, xg.p);
-            AB_LAUNCH(ctx, k_coarse_scatter, grid_for(n0, 256, ctx->num_sms), 256, 0, n0, dof2gfree.p, xg.p, x);
-        }
+        AB_LAUNCH_PDL(ctx, k_coarse_solve, grid, 256, (size_t)n * sizeof(double), n, n0, Ainv.p, free2dof.p, dof2free.p, b, x, 1);
         return;
     }
     const LevelDev& Ld = dom->dev[l];
     const LevelDev& Lc = dom->dev[l - 1];
     GmgLevel& g = L[l];
     GmgLevel& gc = L[l - 1];
-    const int64_t n = (int64_t)Ld.nv * dim, nc = (int64_t)Lc.nv * dim;
+    const int64_t n = (int64_t)Ld.nv * dim;
     smooth(l, b, x, desc.pre_smooth, true, g.coef_pre, g.cf_pre, first_done);
     spmv(ctx, dim, Ld, g.vals, 1, 0, x, b, g.r.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
     const int rg = grid_for((int64_t)Lc.nv * 16, 256, ctx->num_sms * 8);
@@ -817,8 +922,7 @@ struct Solver {
     double damp = 0.66;
     std::shared_ptr<MatrixData> A;
     std::shared_ptr<Gmg> gmg;
-    DevBuf<double> r, rh, p, v, s, t, ph, sh, sc, out2;
-    DevBuf<double> rc;                  // multi-GPU: scratch for the unique (owner-only) form of the preconditioner input
+    DevBuf<double> r, p, v, s, sc, out2;   // CG + Jacobi work vectors (BiCGStab: the workspace lives in the shared hierarchy, KrylovWs)
     int last_steps = 0;
     double last_defect = 0;
     void ensure_vectors();
@@ -827,10 +931,6 @@ struct Solver {
 void Solver::ensure_vectors() {
     const int64_t n = sp->ndofs;
     if (sc.n == 0) { sc.alloc(SC_COUNT + 3); out2.alloc(2); }
-    if (type == 1 && r.n == 0 && sp->dom->distributed()) {   // single GPU: the work vectors live in the shared hierarchy (KrylovWs)
-        r.alloc(n); rh.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); t.alloc(n); ph.alloc(n); sh.alloc(n);
-        rc.alloc(n);
-    }
     if (type == 2 && r.n == 0) { r.alloc(n); p.alloc(n); v.alloc(n); s.alloc(n); }
 }
 
@@ -846,11 +946,7 @@ static void solver_init(Solver* S, Operator* A) {
         // recycle an idle hierarchy of this domain (same descriptor and Dirichlet set): its level buffers, BiCGStab workspace
         // and captured iteration graph keep their addresses, so in steady state nothing is reallocated or re-instantiated
         std::string pool_key = key + "|";
-        if (A->data->dd) {
-            auto dir = A->data->dd->dir;
-            std::sort(dir.begin(), dir.end());
-            for (auto& e : dir) pool_key += std::to_string(e.first) + "." + std::to_string(e.second) + ",";
-        }
+        for (auto& e : A->data->sig.dir) pool_key += std::to_string(e.first) + "." + std::to_string(e.second) + ",";
         Domain* dom = S->sp->dom;
         S->gmg.reset();
         std::shared_ptr<Gmg> G;
@@ -865,7 +961,7 @@ static void solver_init(Solver* S, Operator* A) {
         }
         G->dom = dom;
         G->desc = S->desc;
-        G->setup(A->data);
+        G->setup(A->data->vals.p, A->data->sig.dir);
         A->data->gmg[key] = G;
         S->gmg = G;
     } else {
@@ -873,39 +969,82 @@ static void solver_init(Solver* S, Operator* A) {
     }
 }
 
+// Multi-GPU BiCGStab.  The matrix is additive, so every SpMV result is made consistent by one interface sum; the Krylov
+// vectors (r, p, v, s, t) are then all CONSISTENT -- bitwise identical on every rank sharing a vertex, because the
+// interface sum adds the ranks' contributions in rank order -- and every inner product is taken over the owned copies only
+// (owner mask): mathematically the global dot product, free of the large cancelling per-rank parts an additive residual
+// carries at shared vertices.  The preconditioner input is the unique (owner-only) form, a valid additive representation.
+// 2 interface sums + 3 all-reduces per iteration on top of the single-GPU sequence.
+static void dot_owned(Domain* dom, int64_t n, const double* x0, const double* x1, const double* y, int nx, double* out) {
+    Context* ctx = dom->ctx;
+    const unsigned char* owned = dom->iface[dom->top()].owned.p;
+    if (nx == 1) AB_LAUNCH(ctx, (k_dot_owned<1>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x0, y, ctx->d_partials, ctx->d_tickets, out);
+    else AB_LAUNCH(ctx, (k_dot_owned<2>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x1, y, ctx->d_partials, ctx->d_tickets, out);
+    allreduce_dev(ctx, out, nx);
+}
+static void to_unique(Domain* dom, int64_t n, const double* src, double* dst) {
+    dev_copy(dom->ctx, n, src, dst);
+    AB_LAUNCH(dom->ctx, k_zero_not_owned, ew_grid(dom->ctx, n), 256, 0, n, dom->dim(), dom->iface[dom->top()].owned.p, dst);
+}
+
 // one full BiCGStab iteration on the workspace vectors; ends with the D2H copy of the scalars the ConvCheck reads.
 // The vector updates that feed a V-cycle are fused with that cycle's first smoothing step, the scalar bookkeeping
 // with the last reduction: 41 launches per iteration at three levels instead of 44.
-static void bicg_iteration(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n, bool in_loop = false,
-                           unsigned long long cond_handle = 0) {
+static void bicg_iteration(Domain* dom, const double* Av, Gmg* G, KrylovWs& W, int64_t n, bool in_loop = false, unsigned long long cond_handle = 0) {
+    Context* ctx = dom->ctx;
+    const int dim = dom->dim(), top = dom->top();
+    const LevelDev& Lt = dom->dev[top];
+    const bool dist = dom->distributed();
+    const unsigned char* owned = dist ? dom->iface[top].owned.p : nullptr;
+    double* uq = dist ? W.uq.p : nullptr;
     double* sc = W.sc.p;
     double *fd = nullptr, *fx = nullptr;
     const bool fuse = G->first_step_targets(W.ph.p, &fd, &fx);
     const GmgLevel& gt = G->L.back();
     if (fuse) {
-        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<0>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p, gt.dinv.p, gt.cf_pre, fd, fx);
-        G->apply(W.p.p, W.ph.p, true);
+        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<0>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p, gt.dinv.p, gt.cf_pre, fd, fx, uq, owned, dim);
+        G->apply(dist ? uq : W.p.p, W.ph.p, true);
     } else {
         AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.p.p);
-        G->apply(W.p.p, W.ph.p);
+        if (dist) to_unique(dom, n, W.p.p, uq);
+        G->apply(dist ? uq : W.p.p, W.ph.p);
     }
-    spmv(ctx, dim, Lt, Av, 0, 1, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, W.rh.p, sc + SC_RV, nullptr, nullptr, 1);
+    if (!dist) {
+        spmv(ctx, dim, Lt, Av, 0, 1, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, W.rh.p, sc + SC_RV, nullptr, nullptr, 1);
+    } else {
+        spmv(ctx, dim, Lt, Av, 0, 0, W.ph.p, nullptr, W.v.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
+        exchange_sum(dom, top, W.v.p, dim);
+        dot_owned(dom, n, W.rh.p, nullptr, W.v.p, 1, sc + SC_RV);
+    }
     if (fuse) {
         G->first_step_targets(W.sh.p, &fd, &fx);
-        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<1>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, gt.dinv.p, gt.cf_pre, fd, fx);
-        G->apply(W.s.p, W.sh.p, true);
+        AB_LAUNCH_PDL(ctx, k_bicg_fused_first<1>, ew_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, gt.dinv.p, gt.cf_pre, fd, fx, uq, owned, dim);
+        G->apply(dist ? uq : W.s.p, W.sh.p, true);
     } else {
-        AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, ctx->d_partials, ctx->d_tickets);
-        G->apply(W.s.p, W.sh.p);
+        AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, W.r.p, W.v.p, W.s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
+        if (dist) to_unique(dom, n, W.s.p, uq);
+        G->apply(dist ? uq : W.s.p, W.sh.p);
     }
-    spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS, nullptr, nullptr, 1);
-    if (in_loop) {       // body of the conditional WHILE node: the ConvCheck runs on the device, nothing goes to the host
+    if (!dist) {
+        spmv(ctx, dim, Lt, Av, 0, 2, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, W.s.p, sc + SC_TS, nullptr, nullptr, 1);
+    } else {
+        spmv(ctx, dim, Lt, Av, 0, 0, W.sh.p, nullptr, W.t.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
+        exchange_sum(dom, top, W.t.p, dim);
+        dot_owned(dom, n, W.s.p, W.t.p, W.t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
+    }
+    if (dist) {      // owner-masked local sums, one all-reduce, then the scalar bookkeeping
+        AB_LAUNCH_PDL(ctx, k_bicg_xr<0>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
+                      ctx->d_tickets, W.out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0, owned, dim);
+        allreduce_dev(ctx, W.out2.p, 2);
+        AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, W.out2.p);
+    } else if (in_loop) {       // body of the conditional WHILE node: the ConvCheck runs on the device, nothing goes to the host
         AB_LAUNCH_PDL(ctx, k_bicg_xr<2>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
-                      ctx->d_tickets, W.out2.p, cond_handle, W.ctl.p, W.hist.p, (int)W.hist.n);
+                      ctx->d_tickets, W.out2.p, cond_handle, W.ctl.p, W.hist.p, (int)W.hist.n, owned, dim);
         return;
+    } else {
+        AB_LAUNCH_PDL(ctx, k_bicg_xr<1>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
+                      ctx->d_tickets, W.out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0, owned, dim);
     }
-    AB_LAUNCH_PDL(ctx, k_bicg_xr<1>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
-                  ctx->d_tickets, W.out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0);
     AB_CUDA(cudaMemcpyAsync(ctx->h_results, sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 }
 
@@ -916,6 +1055,11 @@ static std::vector<const void*> iteration_key(Context* ctx, const double* Av, Gm
     key.push_back(G->coefs.p);
     key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
+    if (G->coarse) {
+        key.push_back(G->coarse->Ainv.p);
+        key.push_back(G->coarse->coefs.p);
+        for (const GmgLevel& g : G->coarse->L) { key.push_back(g.vals); key.push_back(g.dinv.p); key.push_back(g.x.p); }
+    }
     return key;
 }
 
@@ -923,8 +1067,10 @@ static std::vector<const void*> iteration_key(Context* ctx, const double* Av, Gm
 // of the body evaluates the ConvCheck on the device and sets the loop condition (cudaGraphSetConditional), so the host does not
 // see the solve again before it has ended (no launch + synchronisation per iteration).  The graph ends with the D2H copies of
 // the scalars and of the iteration count.  Returns false (once and for all for this workspace) if the driver refuses any step:
-// the caller then replays the per-iteration graph.
-static bool ensure_loop_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+// the caller then replays the per-iteration graph.  Single GPU only (distributed solves are not launch-bound: small problems
+// are not decomposed at all, see ug4.Backend).
+static bool ensure_loop_graph(Domain* dom, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    Context* ctx = dom->ctx;
     if (W.loop_failed) return false;
     std::vector<const void*> key = iteration_key(ctx, Av, G);
     if (W.exec_loop && W.key_loop == key) return true;
@@ -948,7 +1094,7 @@ static bool ensure_loop_graph(Context* ctx, int dim, const LevelDev& Lt, const d
     const int64_t l0 = ctx->launches;
     if (ok && cudaStreamBeginCaptureToGraph(ctx->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
         try {
-            bicg_iteration(ctx, dim, Lt, Av, G, W, n, true, (unsigned long long)handle);
+            bicg_iteration(dom, Av, G, W, n, true, (unsigned long long)handle);
         } catch (...) {
             ok = false;
         }
@@ -977,23 +1123,41 @@ static bool ensure_loop_graph(Context* ctx, int dim, const LevelDev& Lt, const d
     return true;
 }
 
-// (re)capture the iteration when any pointer baked into its launches changed since the last capture
-static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+// (re)capture the iteration when any pointer baked into its launches changed since the last capture.  Multi-GPU: the capture
+// holds the interface-exchange kernels (device-side epochs) and the NCCL calls of the iteration; if the driver or NCCL refuses
+// it, the workspace stays on stream launches (returns false).
+static bool ensure_iteration_graph(Domain* dom, const double* Av, Gmg* G, KrylovWs& W, int64_t n) {
+    Context* ctx = dom->ctx;
+    if (W.graph_failed) return false;
     std::vector<const void*> key = iteration_key(ctx, Av, G);
-    if (W.exec && W.key == key) return;
+    if (W.exec && W.key == key) return true;
     TraceTimer tt(ctx->stream, "bicgstab: graph capture");
+    const bool dist = dom->distributed();
     cudaGraph_t graph = nullptr;
     const int64_t l0 = ctx->launches;
     AB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+    bool ok = true;
     try {
-        bicg_iteration(ctx, dim, Lt, Av, G, W, n);
+        bicg_iteration(dom, Av, G, W, n);
     } catch (...) {
         cudaStreamEndCapture(ctx->stream, &graph);
         if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
         ctx->launches = l0;
-        throw;
+        if (!dist) throw;
+        ok = false;
+        graph = nullptr;
     }
-    AB_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+    if (ok && cudaStreamEndCapture(ctx->stream, &graph) != cudaSuccess) {
+        cudaGetLastError();
+        if (!dist) throw ab::Error(-2, "cudaStreamEndCapture failed for the BiCGStab iteration");
+        ok = false;
+    }
+    if (!ok) {
+        W.graph_failed = true;
+        if (env_flag("ADMM_B200_TRACE")) fprintf(stderr, "[ab trace] multi-GPU iteration graph unavailable, stream launches\n");
+        return false;
+    }
     if (const char* dot = getenv("ADMM_B200_GRAPH_DOT")) cudaGraphDebugDotPrint(graph, dot, cudaGraphDebugDotFlagsVerbose);   // diagnostics
     W.nodes = ctx->launches - l0;
     ctx->launches = l0;                      // capturing launches nothing
@@ -1005,23 +1169,34 @@ static void ensure_iteration_graph(Context* ctx, int dim, const LevelDev& Lt, co
             W.exec = nullptr;
         }
     }
-    if (!W.exec) AB_CUDA(cudaGraphInstantiate(&W.exec, graph, 0));
+    if (!W.exec && cudaGraphInstantiate(&W.exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        W.exec = nullptr;
+        cudaGraphDestroy(graph);
+        if (!dist) throw ab::Error(-2, "cudaGraphInstantiate failed for the BiCGStab iteration");
+        W.graph_failed = true;
+        return false;
+    }
     AB_CUDA(cudaGraphDestroy(graph));
     W.key = key;
+    return true;
 }
 
 static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) {
     Domain* dom = S->sp->dom;
     Context* ctx = dom->ctx;
-    const int dim = dom->dim();
-    const LevelDev& Lt = dom->dev[dom->top()];
+    const int dim = dom->dim(), top = dom->top();
+    const LevelDev& Lt = dom->dev[top];
     const int64_t n = S->sp->ndofs;
     const double* Av = S->A->vals.p;
+    const bool dist = dom->distributed();
+    const unsigned char* owned = dist ? dom->iface[top].owned.p : nullptr;
     Gmg* G = S->gmg.get();
     if (!G->ws) G->ws = std::make_unique<KrylovWs>();
     KrylovWs& W = *G->ws;
     if (W.r.n != (size_t)n) {
         W.r.alloc(n); W.rh.alloc(n); W.p.alloc(n); W.v.alloc(n); W.s.alloc(n); W.t.alloc(n); W.ph.alloc(n); W.sh.alloc(n); W.x.alloc(n);
+        if (dist) { W.uq.alloc(n); W.bq.alloc(n); }
         W.sc.alloc(SC_COUNT + 3); W.out2.alloc(2);
         W.ctl.alloc(CTL_COUNT + 1); W.hist.alloc(4097);
         W.key.clear(); W.key_loop.clear();
@@ -1029,19 +1204,32 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     double* sc = W.sc.p;
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
+    const double* bp = b->d.p;
+    if (dist) {
+        // storage types at the solver boundary (UG4 converts here; 3d_admm.lua:978 only guards one call): the right-hand side
+        // must be additive (a consistent one would be counted once per sharing rank), the start iterate consistent
+        if (!(b->storage & (AB_PST_ADDITIVE | AB_PST_UNIQUE))) { to_unique(dom, n, b->d.p, W.bq.p); bp = W.bq.p; }
+        if (!(x->storage & AB_PST_CONSISTENT)) { exchange_sum(dom, top, x->d.p, dim); x->storage = AB_PST_CONSISTENT; }
+    }
     // r = b - A x ; then in one pass: workspace x = x, rh = r, p = v = 0, rho = <r,r> and the other scalars
-    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, W.r.p);
+    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, bp, W.r.p);
+    if (dist) exchange_sum(dom, top, W.r.p, dim);                              // additive -> consistent
     AB_LAUNCH(ctx, k_bicg_init, red_grid(ctx, n), 256, 0, n, x->d.p, W.x.p, W.r.p, W.rh.p, W.p.p, W.v.p, sc, ctx->d_partials, ctx->d_tickets, W.out2.p,
-              W.ctl.p, tol2, S->desc.red_tol > 0 ? S->desc.red_tol * S->desc.red_tol : 0.0, S->desc.max_iterations);
+              W.ctl.p, tol2, S->desc.red_tol > 0 ? S->desc.red_tol * S->desc.red_tol : 0.0, S->desc.max_iterations, owned, dim);
+    if (dist) {
+        allreduce_dev(ctx, W.out2.p, 1);
+        AB_LAUNCH(ctx, k_bicg_init_fix, 1, 1, 0, sc, W.ctl.p, W.out2.p);
+    }
     read_back(ctx, sc, SC_COUNT, h);
     const double rr0 = h[SC_RR];
     double rr = rr0;
     bool ok = rr < tol2;
     int it = 0;
-    if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
-    const bool graph = ctx->use_graph && ctx->stream != nullptr;
+    const bool verbose = S->desc.verbose && (!dist || ctx->comm->rank == 0);
+    if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
+    bool graph = ctx->use_graph && ctx->stream != nullptr && (!dist || dom->p2p_connected);
     const bool want_iter = !ok && S->desc.max_iterations > 0;
-    if (graph && want_iter && ctx->use_loop && ensure_loop_graph(ctx, dim, Lt, Av, G, W, n)) {
+    if (graph && want_iter && !dist && ctx->use_loop && ensure_loop_graph(dom, Av, G, W, n)) {
         // the whole loop in one launch (conditional WHILE node); the device applied the same ConvCheck as the host loop below
         AB_CUDA(cudaGraphLaunch(W.exec_loop, ctx->stream));
         AB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1051,25 +1239,25 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
         rr = h[SC_RR];
         const bool finite = (rr == rr) && !std::isinf(rr);
         ok = finite && (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0));
-        if (S->desc.verbose) {
+        if (verbose) {
             std::vector<double> hh((size_t)std::min<int>(it + 1, (int)W.hist.n), 0.0);
             AB_CUDA(cudaMemcpy(hh.data(), W.hist.p, hh.size() * sizeof(double), cudaMemcpyDeviceToHost));
             for (size_t k = 1; k < hh.size(); ++k) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", (int)k, std::sqrt(hh[k]));
         }
     } else {
-        if (graph && want_iter) ensure_iteration_graph(ctx, dim, Lt, Av, G, W, n);
+        if (graph && want_iter) graph = ensure_iteration_graph(dom, Av, G, W, n);
         while (!ok && it < S->desc.max_iterations) {
             ++it;
             if (graph) {
                 AB_CUDA(cudaGraphLaunch(W.exec, ctx->stream));
                 ctx->launches += W.nodes;
             } else {
-                bicg_iteration(ctx, dim, Lt, Av, G, W, n);
+                bicg_iteration(dom, Av, G, W, n);
             }
             AB_CUDA(cudaStreamSynchronize(ctx->stream));
             for (int i = 0; i < SC_COUNT; ++i) h[i] = ctx->h_results[i];
             rr = h[SC_RR];
-            if (S->desc.verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
+            if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
             if (!(rr == rr) || std::isinf(rr)) break;                       // NaN/Inf: breakdown
             if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
             if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;               // breakdown
@@ -1078,86 +1266,18 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     if (it > 0) dev_copy(ctx, n, W.x.p, x->d.p);
     x->touch();
     S->last_steps = it;
-    S->last_defect = std::sqrt(rr);
-    if (return_defect) { dev_copy(ctx, n, W.r.p, b->d.p); b->touch(); }
-    return ok;
-}
-
-// Multi-GPU BiCGStab.  The matrix is additive, so every SpMV result is made consistent by one interface sum; the
-// Krylov vectors (r, p, v, s, t) are then all CONSISTENT and every inner product is taken over the owned copies only
-// (owner mask) -- mathematically the global dot product, and free of the large cancelling per-rank parts an additive
-// residual carries at shared vertices (<consistent, additive> stagnates at ~1e-8 once copies differ in the last bit,
-// which they do as soon as three ranks share a vertex).  The preconditioner input is the unique (owner-only) form,
-// a valid additive representation.  2 interface sums + 3 all-reduces per iteration.
-static void dot_owned(Domain* dom, int64_t n, const double* x0, const double* x1, const double* y, int nx, double* out) {
-    Context* ctx = dom->ctx;
-    const unsigned char* owned = dom->iface[dom->top()].owned.p;
-    if (nx == 1) AB_LAUNCH(ctx, (k_dot_owned<1>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x0, y, ctx->d_partials, ctx->d_tickets, out);
-    else AB_LAUNCH(ctx, (k_dot_owned<2>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x1, y, ctx->d_partials, ctx->d_tickets, out);
-    allreduce_dev(ctx, out, nx);
-}
-static void to_unique(Domain* dom, int64_t n, const double* src, double* dst) {
-    dev_copy(dom->ctx, n, src, dst);
-    AB_LAUNCH(dom->ctx, k_zero_not_owned, ew_grid(dom->ctx, n), 256, 0, n, dom->dim(), dom->iface[dom->top()].owned.p, dst);
-}
-static bool bicgstab_apply_dist(Solver* S, Vector* x, Vector* b, bool return_defect) {
-    Domain* dom = S->sp->dom;
-    Context* ctx = dom->ctx;
-    const int dim = dom->dim(), top = dom->top();
-    const LevelDev& Lt = dom->dev[top];
-    const int64_t n = S->sp->ndofs;
-    const double* Av = S->A->vals.p;
-    double* sc = S->sc.p;
-    double* uniq = S->rc.p;                                                     // scratch: unique form of the preconditioner input
-    const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
-    double h[SC_COUNT];
-    spmv(ctx, dim, Lt, Av, 1, 0, x->d.p, b->d.p, S->r.p);                       // r = b_additive - A x  (additive)
-    exchange_sum(dom, top, S->r.p, dim);                                        // -> consistent
-    dev_copy(ctx, n, S->r.p, S->rh.p);
-    {
-        const double init[SC_COUNT] = {0, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        AB_CUDA(cudaMemcpyAsync(sc, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        dot_owned(dom, n, S->r.p, nullptr, S->r.p, 1, sc + SC_RR);
-        AB_CUDA(cudaMemcpyAsync(sc + SC_RHO, sc + SC_RR, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    dev_fill(ctx, S->p.p, n, 0.0);
-    dev_fill(ctx, S->v.p, n, 0.0);
-    read_back(ctx, sc, SC_COUNT, h);
-    const double rr0 = h[SC_RR];
-    double rr = rr0;
-    bool ok = rr < tol2;
-    int it = 0;
-    const bool verbose = S->desc.verbose && ctx->comm->rank == 0;
-    if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", 0, std::sqrt(rr));
-    while (!ok && it < S->desc.max_iterations) {
-        ++it;
-        AB_LAUNCH_PDL(ctx, k_bicg_update_p, ew_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->p.p);
-        to_unique(dom, n, S->p.p, uniq);
-        S->gmg->apply(uniq, S->ph.p);
-        spmv(ctx, dim, Lt, Av, 0, 0, S->ph.p, nullptr, S->v.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
-        exchange_sum(dom, top, S->v.p, dim);
-        dot_owned(dom, n, S->rh.p, nullptr, S->v.p, 1, sc + SC_RV);
-        AB_LAUNCH_PDL(ctx, k_bicg_s, red_grid(ctx, n), 256, 0, n, sc, S->r.p, S->v.p, S->s.p, ctx->d_partials, ctx->d_tickets);   // its local |s|^2 is not used
-        to_unique(dom, n, S->s.p, uniq);
-        S->gmg->apply(uniq, S->sh.p);
-        spmv(ctx, dim, Lt, Av, 0, 0, S->sh.p, nullptr, S->t.p, nullptr, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 1);
-        exchange_sum(dom, top, S->t.p, dim);
-        dot_owned(dom, n, S->s.p, S->t.p, S->t.p, 2, sc + SC_TS);               // <s,t>, <t,t>
-        AB_LAUNCH_PDL(ctx, k_bicg_xr<0>, red_grid(ctx, n), 256, 0, n, sc, S->ph.p, S->sh.p, S->s.p, S->t.p, S->rh.p, x->d.p, S->r.p, ctx->d_partials,
-                  ctx->d_tickets, S->out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0);   // local sums overwritten below
-        dot_owned(dom, n, S->r.p, S->rh.p, S->r.p, 2, S->out2.p);               // <r,r>, <rh,r>
-        AB_LAUNCH_PDL(ctx, k_bicg_roll, 1, 1, 0, sc, S->out2.p);
-        read_back(ctx, sc, SC_COUNT, h);
-        rr = h[SC_RR];
-        if (verbose) printf("  BiCGStab+GMG: iter %4d  defect %.6e\n", it, std::sqrt(rr));
-        if (!(rr == rr) || std::isinf(rr)) break;
-        if (rr < tol2 || (S->desc.red_tol > 0 && rr < S->desc.red_tol * S->desc.red_tol * rr0)) { ok = true; break; }
-        if (h[SC_RHO] == 0.0 || h[SC_OMEGA] == 0.0) break;
-    }
-    x->touch();
-    S->last_steps = it;
     S->last_defect = std::sqrt(std::max(rr, 0.0));
-    if (return_defect) { to_unique(dom, n, S->r.p, b->d.p); b->storage = AB_PST_ADDITIVE; b->touch(); }   // unique = additive form of the defect
+    if (return_defect) {
+        if (dist) { to_unique(dom, n, W.r.p, b->d.p); b->storage = AB_PST_ADDITIVE; }   // unique = additive form of the defect
+        else dev_copy(ctx, n, W.r.p, b->d.p);
+        b->touch();
+    }
+    if (dist && dom->p2p_connected) {      // a lost or stalled peer shows up as an error flag of the exchange kernels, never as a wrong sum
+        int herr = 0;
+        AB_CUDA(cudaMemcpyAsync(&herr, dom->p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));
+        AB_REQUIRE(herr == 0, AB_ERR_CUDA, "peer-to-peer interface exchange timed out (a neighbour rank did not arrive)");
+    }
     return ok;
 }
 
@@ -1218,7 +1338,8 @@ static void assemble_hessian_kernels(Domain* dom, DomainDisc* dd, ElemDisc* h, c
     AB_CUDA(cudaMemsetAsync(vals, 0, (size_t)L.nnzb * D * D * sizeof(double), ctx->stream));
     const unsigned char* mask = dd->mask(dom->top());
     AB_LAUNCH(ctx, (k_assemble_hessian<D>), grid_for(L.ne, 128, ctx->num_sms * 16), 128, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u, L.elem_pos.p, mask, P, vals);
-    if (mask) AB_LAUNCH(ctx, (k_dirichlet_diag<D>), ew_grid(ctx, (int64_t)L.nv * D), 256, 0, L.nv, mask, L.diagpos.p, vals);
+    if (mask) AB_LAUNCH(ctx, (k_dirichlet_diag<D>), ew_grid(ctx, (int64_t)L.nv * D), 256, 0, L.nv, mask,
+                        dom->distributed() ? dom->iface[dom->top()].owned.p : (const unsigned char*)nullptr, L.diagpos.p, vals);
 }
 
 static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
@@ -1280,7 +1401,6 @@ static void assemble_jacobian(DomainDisc* dd, Operator* A, Vector* uarg) {
     MatrixData& M = *A->data;
     M.assembled = false;
     M.gmg.clear();
-    M.dd = dd;
     if (sig.kind == 1) {
         const double* up = u ? u->d.p : nullptr;
         if (dim == 2) assemble_hessian_kernels<2>(dom, dd, jac, up, M.vals.p);
@@ -1570,16 +1690,57 @@ int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t
     const int nv = dom->mesh.levels[level].nv;
     H.owned.assign(owned, owned + nv);
     for (int v : H.idx) AB_REQUIRE(v >= 0 && v < nv, AB_ERR_ARG, "interface vertex index out of range");
+    dom->dist_enabled = true;
     AB_CATCH
 }
-int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l0_gid, const int32_t* vsub0_global) {
+int ab_domain_set_gather(ab_domain* dom, int gather_level, ab_domain* coarse, const int32_t* nv_per_rank, const int32_t* l2g_cat,
+                         const int64_t* nblk_per_rank, const int32_t* gpos_cat) {
     AB_TRY
     AB_REQUIRE(dom && !dom->finalized, AB_ERR_STATE, "must be set before the first ApproximationSpace");
-    const int nv0 = dom->mesh.levels[0].nv;
-    dom->nv0_global = nv0_global;
-    dom->l0_gid.assign(l0_gid, l0_gid + nv0);
-    dom->vsub0_global.assign(vsub0_global, vsub0_global + nv0_global);
-    for (int g : dom->l0_gid) AB_REQUIRE(g >= 0 && g < nv0_global, AB_ERR_ARG, "global vertex id out of range");
+    AB_REQUIRE(dom->ctx && dom->ctx->comm && dom->ctx->comm->nranks > 1, AB_ERR_STATE, "ab_domain_set_gather needs a multi-rank context");
+    AB_REQUIRE(gather_level >= 0 && gather_level < (int)dom->mesh.levels.size() - 1, AB_ERR_ARG, "the gather level must lie below the top level");
+    dom->gather_level = gather_level;
+    Context* ctx = dom->ctx;
+    if (ctx->comm->rank != 0) return AB_OK;
+    const int nr = ctx->comm->nranks, D = dom->dim();
+    AB_REQUIRE(coarse && nv_per_rank && l2g_cat && nblk_per_rank && gpos_cat, AB_ERR_ARG, "rank 0 needs the coarse domain and the gather maps");
+    AB_REQUIRE(coarse->ctx == ctx && (int)coarse->mesh.levels.size() == gather_level + 1 && coarse->dim() == D, AB_ERR_ARG,
+               "the coarse domain must be the global grid refined gather_level times on the same context");
+    dom->cdom = coarse;
+    dom->g_nv.assign(nv_per_rank, nv_per_rank + nr);
+    dom->g_nblk.assign(nblk_per_rank, nblk_per_rank + nr);
+    AB_REQUIRE(dom->g_nv[0] == dom->mesh.levels[gather_level].nv, AB_ERR_ARG, "gather maps: rank 0's own vertex count does not match");
+    int64_t nvt = 0, nbt = 0;
+    for (int r = 0; r < nr; ++r) { nvt += dom->g_nv[r]; nbt += dom->g_nblk[r]; }
+    dom->g_nv_total = nvt; dom->g_nblk_total = nbt;
+    const int nvg = coarse->mesh.levels[gather_level].nv;
+    std::vector<int> ptr((size_t)nvg + 1, 0);
+    for (int64_t k = 0; k < nvt; ++k) {
+        AB_REQUIRE(l2g_cat[k] >= 0 && l2g_cat[k] < nvg, AB_ERR_ARG, "gather maps: global vertex id out of range");
+        ptr[l2g_cat[k] + 1]++;
+    }
+    for (int v = 0; v < nvg; ++v) {
+        AB_REQUIRE(ptr[v + 1] > 0, AB_ERR_ARG, "gather maps: a global coarse vertex belongs to no rank");
+        ptr[v + 1] += ptr[v];
+    }
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1), idx((size_t)nvt);
+    for (int64_t k = 0; k < nvt; ++k) idx[fill[l2g_cat[k]]++] = (int)k;     // k ascends rank by rank: every list is in rank order
+    dom->g_l2g.upload(std::vector<int>(l2g_cat, l2g_cat + nvt), ctx->stream);
+    dom->g_csr_ptr.upload(ptr, ctx->stream);
+    dom->g_csr_idx.upload(idx, ctx->stream);
+    dom->g_gpos.upload(std::vector<int>(gpos_cat, gpos_cat + nbt), ctx->stream);
+    dom->g_vstage.alloc((size_t)nvt * D);
+    dom->g_mstage.alloc((size_t)nbt * D * D);
+    AB_CATCH
+}
+int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* rowptr, int32_t* colidx) {
+    AB_TRY
+    AB_REQUIRE(dom && level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    HostPattern P;
+    build_pattern(dom->mesh.levels[level], P);
+    if (nnzb) *nnzb = (int64_t)P.colidx.size();
+    if (rowptr) memcpy(rowptr, P.rowptr.data(), P.rowptr.size() * sizeof(int32_t));
+    if (colidx) memcpy(colidx, P.colidx.data(), P.colidx.size() * sizeof(int32_t));
     AB_CATCH
 }
 int ab_domain_p2p_export(ab_domain* dom, void* handle64, int64_t* level_base /* nlevels */, int32_t* totals /* nlevels */) {
@@ -1598,7 +1759,6 @@ int ab_domain_p2p_export(ab_domain* dom, void* handle64, int64_t* level_base /* 
         dom->window_bytes = std::max<size_t>(off, 256);
         AB_CUDA(cudaMalloc((void**)&dom->window, dom->window_bytes));      // a plain allocation: exported whole through CUDA IPC
         AB_CUDA(cudaMemset(dom->window, 0, dom->window_bytes));
-        dom->p2p_done.alloc(1); dom->p2p_done.zero(dom->ctx->stream);
         dom->p2p_err.alloc(1); dom->p2p_err.zero(dom->ctx->stream);
         AB_CUDA(cudaStreamSynchronize(dom->ctx->stream));
     }
@@ -2172,8 +2332,7 @@ static int solver_apply_impl(ab_solver* s, ab_vector* x, ab_vector* b, int* conv
     AB_TRY
     AB_REQUIRE(s->A, AB_ERR_STATE, "solver:apply before solver:init");
     AB_REQUIRE(x->n() == s->sp->ndofs && b->n() == s->sp->ndofs, AB_ERR_ARG, "solver:apply: vector size mismatch");
-    const bool ok = s->type == 1 ? (s->sp->dom->distributed() ? bicgstab_apply_dist(s, x, b, ret_def) : bicgstab_apply(s, x, b, ret_def))
-                                 : cg_jacobi_apply(s, x, b, ret_def);
+    const bool ok = s->type == 1 ? bicgstab_apply(s, x, b, ret_def) : cg_jacobi_apply(s, x, b, ret_def);
     x->storage = AB_PST_CONSISTENT;
     if (converged) *converged = ok ? 1 : 0;
     AB_CHECK_LAUNCH(s->sp->dom->ctx);

@@ -8,6 +8,12 @@ level by exact coordinate matching of candidate lists (both sides run the same r
 shared vertices have bit-identical coordinates); the matched lists are sorted lexicographically, which gives
 both sides the same canonical order without any further negotiation.
 
+Hierarchical agglomeration (3d_admm.lua:151-183 keeps level 0 on one process and widens the process set level by
+level): grid levels whose GLOBAL size is below a threshold are not decomposed at all -- rank 0 holds them as one global
+hierarchy; the helpers at the end of this file compute the vertical-interface maps (local -> global vertex ids and
+local -> global matrix-block positions on the gather level).  A problem whose top level is below the threshold is
+not decomposed in the first place (ug4.Backend).
+
 Pure NumPy + a tiny `gather` callable (torch.distributed.all_gather_object in production, gloo in the CPU tests).
 """
 from __future__ import annotations
@@ -128,3 +134,71 @@ def match_level(xyz: np.ndarray, mask: np.ndarray, rank: int, nranks: int, gathe
             owned[loc] = 0
     idx = np.concatenate(idx).astype(np.int32) if idx else np.zeros(0, np.int32)
     return np.array(neigh, np.int32), np.array(offsets, np.int32), idx, owned
+
+
+# ------------------------------------------------------------------------------------------------
+# hierarchical agglomeration: which levels are gathered, and the vertical-interface maps
+# ------------------------------------------------------------------------------------------------
+def global_level_counts(g: dict, refs: int):
+    """Vertices per level of the GLOBAL hierarchy from the regular-refinement recurrences V' = V+E, E' = 2E+3F(+T),
+    F' = 4F(+8T), T' = 8T, seeded with the level-0 entity counts of the grid."""
+    el = np.asarray(g["elems"])
+    dim = int(g["dim"])
+    V = len(g["xyz"])
+    E = len(np.unique(np.sort(np.concatenate([el[:, [i, j]] for i, j in _LOCAL_EDGES[dim]]), axis=1), axis=0))
+    if dim == 3:
+        T = len(el)
+        F = len(np.unique(np.sort(np.concatenate([el[:, list(f)] for f in _LOCAL_FACES]), axis=1), axis=0))
+    else:
+        T, F = 0, len(el)
+    out = [V]
+    for _ in range(refs):
+        V, E, F, T = V + E, 2 * E + 3 * F + T, 4 * F + 8 * T, 8 * T
+        out.append(V)
+    return out
+
+
+def gather_level(nv_levels, dim: int, max_dofs: int) -> int:
+    """Highest level whose global P1 deformation space has at most max_dofs unknowns (level 0 always qualifies):
+    levels 0..gather_level are held undivided by rank 0, the levels above are decomposed over all ranks."""
+    lg = 0
+    for l, nv in enumerate(nv_levels):
+        if nv * dim <= max_dofs:
+            lg = l
+    return lg
+
+
+def propagate_l2g(l2g_coarse, nvc_global, gpa, gpb, lpa, lpb):
+    """local -> global vertex ids one level up.  Copies keep their ids (coarse vertices are a prefix of the fine ones on
+    both sides); a local midpoint is the global midpoint of the global edge between the images of its parents."""
+    l2g_coarse = np.asarray(l2g_coarse, np.int64)
+    nvg = int(nvc_global)
+    gkey = np.minimum(gpa, gpb).astype(np.int64) * nvg + np.maximum(gpa, gpb)
+    order = np.argsort(gkey, kind="stable")
+    a, b = l2g_coarse[lpa], l2g_coarse[lpb]
+    lkey = np.minimum(a, b) * nvg + np.maximum(a, b)
+    pos = np.searchsorted(gkey[order], lkey)
+    if len(lkey) and (pos.max(initial=0) >= len(gkey) or not np.array_equal(gkey[order][pos], lkey)):
+        raise ValueError("a local edge has no global counterpart")
+    return np.concatenate([l2g_coarse, nvg + order[pos]]).astype(np.int64)
+
+
+def pattern_keys(elems, nv: int):
+    """Sorted keys i*nv + j of the P1 block pattern (vertex pairs sharing an element, diagonal included) = the BSR order of
+    ab_domain_level_pattern: rows ascending, columns ascending."""
+    el = np.asarray(elems, np.int64)
+    n = el.shape[1]
+    keys = np.concatenate([el[:, a] * nv + el[:, b] for a in range(n) for b in range(n)])
+    return np.unique(keys)
+
+
+def block_positions(local_elems, nv_local: int, l2g, global_keys, nv_global: int):
+    """Position in the global BSR pattern of every block of the local pattern (local BSR order)."""
+    lk = pattern_keys(local_elems, nv_local)
+    i, j = lk // nv_local, lk % nv_local
+    l2g = np.asarray(l2g, np.int64)
+    gk = l2g[i] * nv_global + l2g[j]
+    pos = np.searchsorted(global_keys, gk)
+    if len(gk) and (pos.max(initial=0) >= len(global_keys) or not np.array_equal(global_keys[pos], gk)):
+        raise ValueError("a local matrix block has no global counterpart")
+    return pos.astype(np.int32)

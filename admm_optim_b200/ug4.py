@@ -61,6 +61,12 @@ class Domain(_Handle):
         self.ug = ug
         self.dim = None
         self.subset_names = []
+        self._dist = None          # multi-GPU: set when this rank holds one part of a decomposed grid (CreateRegularHierarchy)
+
+    @property
+    def decomposed(self):
+        """True when this rank holds one part of a domain-decomposed grid (False: the whole grid lives on this rank)."""
+        return self._dist is not None
 
     def _loaded(self):
         d = C.c_int()
@@ -158,7 +164,7 @@ class ApproximationSpace(_Handle):
     def _ensure(self):
         if not self.h:
             call("ab_space_create", self.dom.h, self.kind, len(self.names), C.byref(self.h))
-            if self.ug.nranks > 1 and not getattr(self.dom, "_p2p_done", False):
+            if self.ug.nranks > 1 and getattr(self.dom, "_dist", None) is not None and not getattr(self.dom, "_p2p_done", False):
                 self.dom._p2p_done = True
                 self.ug._connect_p2p(self.dom)
 
@@ -596,18 +602,12 @@ class Backend:
     def LoadDomain(self, dom, grid_name):
         """LoadDomain(dom, gridName)  3d_admm.lua:109. `.ugx` is parsed natively; `.npz` is the converted
         fixture format of tools/convert_ugx.py (same content, travels to machines without the reference tree).
-        Multi-GPU: the grid is partitioned here (level-0 elements, RCB) and this rank keeps its own sub-grid."""
+        Multi-GPU: see CreateRegularHierarchy (the decomposition needs the number of refinements)."""
         if self.nranks > 1:
-            g = self._read_global_grid(grid_name)
-            from . import partition as P
-            cent = g["xyz"][g["elems"]].mean(axis=1)
-            part = P.rcb_partition(cent, self.nranks)
-            sub = P.extract_submesh(g, part, self.rank)
-            if len(sub["elems"]) == 0:
-                raise AdmmB200Error("rank %d received no elements" % self.rank)
-            self._create_from_dict(dom, dict(sub, subset_names=g["subset_names"]))
-            dom._dist = dict(l2g=sub["l2g"], mask0=P.vertex_rank_masks(g["elems"], part, len(g["xyz"]))[sub["l2g"]],
-                             vsub_global=np.ascontiguousarray(g["vsub"], np.int32), nv0_global=len(g["xyz"]), part=part)
+            # provisional: the whole level-0 grid on every rank; whether and how it is decomposed is decided when the
+            # number of refinements is known (CreateRegularHierarchy)
+            dom._global = self._read_global_grid(grid_name)
+            self._create_from_dict(dom, dom._global)
         elif grid_name.endswith(".npz"):
             self._create_from_dict(dom, self._read_global_grid(grid_name))
         else:
@@ -629,7 +629,7 @@ class Backend:
         call("ab_domain_load_ugx", None, grid_name.encode(), C.byref(tmp.h))
         return tmp.get_grid_dict(0)
 
-    def _create_from_dict(self, dom, g):
+    def _create_from_dict(self, dom, g, host_only=False):
         names = list(g["subset_names"])
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         xyz = np.ascontiguousarray(g["xyz"], np.float64)
@@ -640,30 +640,83 @@ class Backend:
         ses = np.ascontiguousarray(g["sp_edges_sub"], np.int32)
         sf = np.ascontiguousarray(g["sp_faces"], np.int32)
         sfs = np.ascontiguousarray(g["sp_faces_sub"], np.int32)
-        call("ab_domain_create", self.ctx, int(g["dim"]), xyz.shape[0], _dp(xyz), elems.shape[0], _ip(elems), len(names), arr,
+        call("ab_domain_create", None if host_only else self.ctx, int(g["dim"]), xyz.shape[0], _dp(xyz), elems.shape[0], _ip(elems), len(names), arr,
              _ip(vsub), _ip(esub), len(ses), _ip(se) if len(ses) else None, _ip(ses) if len(ses) else None,
              len(sfs), _ip(sf) if len(sfs) else None, _ip(sfs) if len(sfs) else None, C.byref(dom.h))
         dom.subset_names = names
+        dom.dim = int(g["dim"])
 
     def _create_regular_hierarchy(self, dom, num_refs, verbose=False, balancer_desc=None):
         """util.refinement.CreateRegularHierarchy(dom, numRefs, false, balancerDesc)  3d_admm.lua:186.
-        Multi-GPU: every rank refines its own sub-grid; the shared-vertex interfaces of all levels are then matched."""
+
+        Multi-GPU (balancerDesc.hierarchy of 3d_admm.lua:151-183, with GPU-sized thresholds): grid levels whose global
+        deformation space has at most ADMM_B200_GATHER_DOFS unknowns (default 400 000) are not worth decomposing --
+          * if that includes the top level, the problem runs UNDIVIDED: every rank keeps the whole grid and computes the same
+            answers without any communication (what the reference's scalars look like on every MPI rank);
+          * otherwise the level-0 elements are partitioned (RCB), every rank refines its own sub-grid, the shared-vertex
+            interfaces of all levels are matched, and the levels up to the gather level are additionally held by rank 0 as ONE
+            global hierarchy (the vertical interface of the multigrid cycle, lib.cu Gmg::vcycle_base_gathered)."""
+        g = getattr(dom, "_global", None)
+        if self.nranks == 1 or g is None:
+            call("ab_domain_refine", dom.h, int(num_refs))
+            return
+        from . import partition as P
+        dim = int(g["dim"])
+        nv_levels = P.global_level_counts(g, int(num_refs))
+        lg = P.gather_level(nv_levels, dim, int(os.environ.get("ADMM_B200_GATHER_DOFS", "400000")))
+        if lg >= num_refs:
+            call("ab_domain_refine", dom.h, int(num_refs))
+            dom._dist = None
+            return
+        # ---- decomposed levels ---------------------------------------------------------------------------------
+        cent = g["xyz"][g["elems"]].mean(axis=1)
+        part = P.rcb_partition(cent, self.nranks)
+        sub = P.extract_submesh(g, part, self.rank)
+        if len(sub["elems"]) == 0:
+            raise AdmmB200Error("rank %d received no elements" % self.rank)
+        call("ab_domain_destroy", dom.h)                       # the provisional whole grid
+        dom.h = C.c_void_p()
+        self._create_from_dict(dom, dict(sub, subset_names=g["subset_names"]), host_only=not self.ctx)
+        dom._dist = dict(l2g=sub["l2g"], part=part, gather_level=lg)
         call("ab_domain_refine", dom.h, int(num_refs))
-        if self.nranks > 1:
-            from . import partition as P
-            info = dom._dist
-            mask = info["mask0"]
-            dom._iface = []
-            for level in range(dom.num_levels()):
-                lv = dom.get_level(level, elems=False)
-                if level > 0:
-                    mask = P.refine_masks(mask, lv["parent_a"], lv["parent_b"])
-                neigh, offsets, idx, owned = P.match_level(lv["xyz"], mask, self.rank, self.nranks, self._gather)
-                call("ab_domain_set_interface", dom.h, level, len(neigh), _ip(neigh) if len(neigh) else None, _ip(offsets),
-                     _ip(idx) if len(idx) else None, owned.ctypes.data_as(C.POINTER(C.c_ubyte)))
-                dom._iface.append(dict(neigh=neigh, offsets=offsets, idx=idx, owned=owned))
-            l2g = np.ascontiguousarray(info["l2g"], np.int32)
-            call("ab_domain_set_global_coarse", dom.h, int(info["nv0_global"]), _ip(l2g), _ip(info["vsub_global"]))
+        mask = P.vertex_rank_masks(g["elems"], part, len(g["xyz"]))[sub["l2g"]]
+        dom._iface = []
+        for level in range(dom.num_levels()):
+            lv = dom.get_level(level, elems=False)
+            if level > 0:
+                mask = P.refine_masks(mask, lv["parent_a"], lv["parent_b"])
+            neigh, offsets, idx, owned = P.match_level(lv["xyz"], mask, self.rank, self.nranks, self._gather)
+            call("ab_domain_set_interface", dom.h, level, len(neigh), _ip(neigh) if len(neigh) else None, _ip(offsets),
+                 _ip(idx) if len(idx) else None, owned.ctypes.data_as(C.POINTER(C.c_ubyte)))
+            dom._iface.append(dict(neigh=neigh, offsets=offsets, idx=idx, owned=owned))
+        # ---- gathered levels: the global grid refined lg times (every rank builds it on the host for the maps; rank 0 keeps it) ----
+        cdom = Domain(self)
+        self._create_from_dict(cdom, g, host_only=(self.rank != 0 or not self.ctx))
+        call("ab_domain_refine", cdom.h, lg)
+        l2g = np.asarray(sub["l2g"], np.int64)
+        for level in range(1, lg + 1):
+            gl, ll = cdom.get_level(level, elems=False), dom.get_level(level, elems=False)
+            l2g = P.propagate_l2g(l2g, gl["nv_coarse"], gl["parent_a"], gl["parent_b"], ll["parent_a"], ll["parent_b"])
+        glev, llev = cdom.get_level(lg), dom.get_level(lg)
+        if not np.array_equal(glev["xyz"][l2g], llev["xyz"]):
+            raise AdmmB200Error("vertical interface: local and global refinement disagree on level %d" % lg)
+        nvg = len(glev["xyz"])
+        gpos = P.block_positions(llev["elems"], len(llev["xyz"]), l2g, P.pattern_keys(glev["elems"], nvg), nvg)
+        mine = (np.ascontiguousarray(l2g, np.int32), gpos)
+        everyone = self._gather(mine)
+        dom._gather = dict(level=lg, l2g=mine[0], gpos=gpos, nv_global=nvg)
+        if not self.ctx:                                       # host-only instance (CPU tests of this logic)
+            dom._cdom = cdom
+            return
+        if self.rank == 0:
+            nvr = np.array([len(e[0]) for e in everyone], np.int32)
+            nbr = np.array([len(e[1]) for e in everyone], np.int64)
+            l2g_cat = np.ascontiguousarray(np.concatenate([e[0] for e in everyone]), np.int32)
+            gpos_cat = np.ascontiguousarray(np.concatenate([e[1] for e in everyone]), np.int32)
+            call("ab_domain_set_gather", dom.h, lg, cdom.h, _ip(nvr), _ip(l2g_cat), nbr.ctypes.data_as(C.POINTER(C.c_int64)), _ip(gpos_cat))
+            dom._cdom = cdom                                   # rank 0 keeps the global coarse grid alive as long as the domain
+        else:
+            call("ab_domain_set_gather", dom.h, lg, None, None, None, None, None)
 
     def _connect_p2p(self, dom):
         """Wire the NVLink peer-to-peer interface sums (collective over all ranks): exchange the CUDA IPC handles and the

@@ -72,11 +72,22 @@ int ab_domain_destroy(ab_domain* dom);
 int ab_domain_refine(ab_domain* dom, int num_refs);
 /* Multi-GPU (replaces the ParMETIS/pcl distribution of 3d_admm.lua:124-186): this rank's domain is its element
  * partition of the level-0 grid; after refinement the host program supplies, per level, the vertices shared with
- * each neighbour rank (same canonical order on both sides) and the owner mask, plus the global level-0 numbering
- * for the replicated coarse solve.  Must be called before the first ApproximationSpace.                        */
+ * each neighbour rank (neighbour ranks ascending, same canonical vertex order on both sides) and the owner mask.
+ * A domain on a multi-rank context for which no interface is set stays a plain local domain (a problem too small
+ * to be decomposed runs undivided).  Must be called before the first ApproximationSpace.                       */
 int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets,
                             const int32_t* idx, const unsigned char* owned);
-int ab_domain_set_global_coarse(ab_domain* dom, int nv0_global, const int32_t* l0_gid, const int32_t* vsub0_global);
+/* Hierarchical agglomeration of the coarse grid levels (the reference keeps level 0 on one process and widens the
+ * process set level by level: balancerDesc.hierarchy, 3d_admm.lua:151-183): levels <= gather_level are held by rank 0
+ * as one global hierarchy.  Every rank states the level; rank 0 also passes `coarse` (the GLOBAL grid refined
+ * gather_level times, same context) and, concatenated over the ranks 0..nranks-1: the number of level-`gather_level`
+ * vertices / matrix blocks of each rank, the local -> global vertex ids and the local block -> global block positions
+ * (BSR order of ab_domain_level_pattern).  Other ranks pass NULL for all of them.                                 */
+int ab_domain_set_gather(ab_domain* dom, int gather_level, ab_domain* coarse, const int32_t* nv_per_rank, const int32_t* l2g_cat,
+                         const int64_t* nblk_per_rank, const int32_t* gpos_cat);
+/* P1 block pattern of a level (host side, no GPU needed): block rows = vertices, columns ascending, diagonal included;
+ * nnzb = V + 2E.  rowptr (nv+1) / colidx (nnzb) may be NULL to query the size only.                              */
+int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* rowptr, int32_t* colidx);
 /* NVLink peer-to-peer interface sums (CUDA IPC; optional -- without it the exchanges use ncclSend/ncclRecv):
  * export this rank's receive window after the first ApproximationSpace exists, gather all handles / layouts on the
  * host, then connect.  remote_dst / remote_stride: one entry per (level, neighbour) in level-major, neighbour order. */

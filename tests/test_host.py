@@ -151,12 +151,9 @@ def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
     assert outs[1] == ""
 
 
-@pytest.mark.parametrize("grid,refs,counts", [(GRID3D, 2, [338, 2124, 14910]), (GRID2D, 2, [160, 596, 2296])])
-def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts):
-    """Host side of the multi-GPU path on 2 gloo ranks: every global vertex is owned exactly once on every level,
-    both sides of an interface list the same coordinates in the same order."""
+def _run_dist_host_workers(grid, refs, gather_dofs, port):
     import json
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", ADMM_B200_GATHER_DOFS=str(gather_dofs))
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_host_worker.py"), grid, str(refs)],
                               env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
     outs = []
@@ -164,12 +161,43 @@ def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts):
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0, err[-2000:]
         outs.append(out)
-    res = json.loads(outs[0].strip().splitlines()[-1])
+    return json.loads(outs[0].strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("grid,refs,counts,gather_dofs,lg", [(GRID3D, 2, [338, 2124, 14910], 7000, 1), (GRID3D, 2, [338, 2124, 14910], 100, 0),
+                                                            (GRID2D, 2, [160, 596, 2296], 1500, 1)])
+def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts, gather_dofs, lg):
+    """Host side of the multi-GPU path on 2 gloo ranks: every global vertex is owned exactly once on every level,
+    both sides of an interface list the same coordinates in the same order; the levels up to the gather level have exact
+    local -> global vertex and matrix-block maps (the per-rank element-incidence counts add up to the global ones)."""
+    res = _run_dist_host_workers(grid, refs, gather_dofs, 29613)
+    assert all(r["decomposed"] and r["gather_level"] == lg for r in res)
+    assert res[0]["blocks_ok"]
+    lv = [r["levels"] for r in res]
     for level in range(refs + 1):
-        assert sum(r[level]["owned"] for r in res) == counts[level]
-        a, b = res[0][level]["shared"].get("1"), res[1][level]["shared"].get("0")
+        assert sum(r[level]["owned"] for r in lv) == counts[level]
+        a, b = lv[0][level]["shared"].get("1"), lv[1][level]["shared"].get("0")
         assert a is not None and a == b and len(a) > 0
-        assert res[0][level]["nv"] + res[1][level]["nv"] - len(a) == counts[level]
+        assert lv[0][level]["nv"] + lv[1][level]["nv"] - len(a) == counts[level]
+
+
+def test_small_problem_is_not_decomposed_gloo_world_size_2():
+    """A hierarchy whose top level is below the agglomeration threshold runs undivided: every rank keeps the whole grid
+    (3d_admm.lua's default refinement has 44 730 unknowns -- decomposing it only adds latency)."""
+    res = _run_dist_host_workers(GRID3D, 2, 400000, 29614)
+    assert all(not r["decomposed"] and r["levels"] == [338, 2124, 14910] for r in res)
+
+
+def test_agglomeration_level_choice():
+    from admm_optim_b200 import partition as P
+    z = np.load(GRID3D)
+    g = {k: z[k] for k in z.files}
+    nv = P.global_level_counts(g, 6)
+    assert nv == [338, 2124, 14910, 111386, 860338, 6761314, 53608130]              # SURVEY.md 8(d)
+    assert P.gather_level(nv, 3, 400000) == 3 and P.gather_level(nv[:3], 3, 400000) == 2 and P.gather_level(nv, 3, 10) == 0
+    z2 = np.load(GRID2D)
+    nv2 = P.global_level_counts({k: z2[k] for k in z2.files}, 7)
+    assert nv2[3] == 9008 and nv2[7] == 2263808 and P.gather_level(nv2, 2, 400000) == 5
 
 
 def test_rcb_partition_is_balanced_and_deterministic():
