@@ -1896,7 +1896,16 @@ int ab_transform_domain_by_displacement(ab_domain* dom, ab_vector* u) {
     AB_REQUIRE(dom->finalized, AB_ERR_STATE, "domain has no ApproximationSpace yet");
     AB_REQUIRE(u->sp->kind == AB_SPACE_P1 && u->sp->ncomp == dom->dim() && u->sp->dom == dom, AB_ERR_ARG, "displacement must be a P1 dim-vector on this domain");
     LevelDev& L = dom->dev[dom->top()];
-    dev_axpby(dom->ctx, u->n(), 1.0, L.xyz.p, 1.0, u->d.p, L.xyz.p);
+    if (dom->distributed() && !(u->storage & AB_PST_CONSISTENT)) {
+        // every rank must move its copy of a shared vertex by the same (summed) displacement
+        DevBuf<double> tmp((size_t)u->n());
+        dev_copy(dom->ctx, u->n(), u->d.p, tmp.p);
+        exchange_sum(dom, dom->top(), tmp.p, dom->dim());
+        dev_axpby(dom->ctx, u->n(), 1.0, L.xyz.p, 1.0, tmp.p, L.xyz.p);
+        AB_CUDA(cudaStreamSynchronize(dom->ctx->stream));   // tmp is released below
+    } else {
+        dev_axpby(dom->ctx, u->n(), 1.0, L.xyz.p, 1.0, u->d.p, L.xyz.p);
+    }
     dom->coords_version = ++g_version_counter;
     dom->host_xyz_stale = true;
     AB_CHECK_LAUNCH(dom->ctx);

@@ -325,11 +325,13 @@ def run_b200(args):
             t_solve = time.perf_counter() - t0
         extra = {"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / (peak * world),
                  "vcycle_bytes": bv, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(), "solve_converged": bool(ok)}
+        if world > 1:
+            st = big.dom.p2p_status()
+            assert st["error"] == 0, "peer-to-peer interface exchange timed out (error %d)" % st["error"]
+            extra["decomposed"] = bool(big.dom.decomposed)
+            extra["gather_level"] = big.dom._dist["gather_level"] if big.dom.decomposed else None
         del big
 
-    if world > 1:
-        st = prob.dom.p2p_status()
-        assert st["error"] == 0, "peer-to-peer interface exchange timed out (error %d)" % st["error"]
     if rank != 0:
         return
     value = args.steps / (ms_dev * 1e-3)

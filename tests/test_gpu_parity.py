@@ -349,7 +349,9 @@ def test_vecprod_and_l2norm_result_caches_are_transparent(gpu_backend):
 
 
 def test_multi_gpu_matches_single_gpu():
-    """Domain decomposition over 2 GPUs reproduces the single-GPU ADMM iterates (tools/dist_check.py asserts 1e-9)."""
+    """Domain decomposition over 2 GPUs reproduces the single-GPU ADMM iterates (tools/dist_check.py asserts 1e-9 on u, 1e-8 on
+    the per-iteration scalars, equal Newton counts, BiCGStab counts within 1, bitwise-identical copies of shared vertices):
+    with only level 0 agglomerated on rank 0, and with levels 0..1 agglomerated (3D)."""
     import os
     import subprocess
     import sys
@@ -357,11 +359,27 @@ def test_multi_gpu_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for dim, refs in ((3, 1), (2, 2)):
+    for dim, refs, gather in ((3, 2, 100), (3, 2, 7000), (2, 3, 100)):
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                              "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), str(refs), str(dim)],
+                              "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), str(refs), str(dim), str(gather)],
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_undivided_run_on_a_multi_rank_context():
+    """A problem below the agglomeration threshold is not decomposed: with 2 ranks each holds the whole grid, nothing is
+    exchanged and the iterates equal the single-GPU ones bit for bit in iteration counts (tools/dist_check.py, default threshold)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29618", os.path.join(root, "tools", "dist_check.py"), "1", "3", "400000"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
 @pytest.mark.parametrize("name", ["3d_refs1", "2d_refs2", "3d_refs2", "2d_refs3"])   # the last two: the scripts' default refinements
