@@ -15,6 +15,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -29,7 +30,7 @@ struct NcclApi {
             if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
             AB_REQUIRE(h, -4, std::string("cannot load libnccl.so.2: ") + dlerror());
 #define AB_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "nccl" #name)); AB_REQUIRE(api.name, -4, "libnccl.so.2 lacks nccl" #name)
-            AB_SYM(GetUniqueId); AB_SYM(CommInitRank); AB_SYM(CommDestroy); AB_SYM(AllReduce); AB_SYM(Send); AB_SYM(Recv);
+            AB_SYM(GetUniqueId); AB_SYM(CommInitRank); AB_SYM(CommDestroy); AB_SYM(CommAbort); AB_SYM(AllReduce); AB_SYM(Send); AB_SYM(Recv);
             AB_SYM(GroupStart); AB_SYM(GroupEnd); AB_SYM(GetErrorString);
 #undef AB_SYM
             loaded = true;
@@ -47,7 +48,11 @@ struct NcclApi {
 struct Comm {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
-    ~Comm() { if (comm) NcclApi::get().CommDestroy(comm); }
+    // ncclCommDestroy is an intra-node collective (it blocks until every rank of the node calls it); a context may be torn down
+    // by a garbage collector at a different time on every rank, or not at all on a rank that is exiting.  All work of the
+    // context has been synchronised by then (ab_context_destroy), so the communicator is released with ncclCommAbort, which
+    // frees the local resources without waiting for the peers.
+    ~Comm() { if (comm) NcclApi::get().CommAbort(comm); }
     void allreduce(double* d, int n, bool max_op, cudaStream_t s) {
         AB_NCCL(NcclApi::get().AllReduce(d, d, (size_t)n, ncclFloat64, max_op ? ncclMax : ncclSum, comm, s));
     }
@@ -91,7 +96,7 @@ struct Interface {
 //   SMOOTH = true : the Chebyshev/Jacobi interface fix-up fused around the sum (Gmg::smooth): the locally updated
 //                   v = c1 d_in + c2 D^-1 r_local is reduced to its additive increment, summed, and d, x are rebuilt at the
 //                   shared vertices:  v = c1 d_in + total,  x_out = x_in + v.
-constexpr long long kP2PSpinLimit = 200000000ll;
+constexpr long long kP2PSpinLimit = 20000000ll;   // ~10-20 s of polling
 
 template <bool SMOOTH>
 __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, int my_pos, const int* __restrict__ iv, const int* __restrict__ iv_ptr,

@@ -362,7 +362,7 @@ def test_multi_gpu_matches_single_gpu():
     for dim, refs, gather in ((3, 2, 100), (3, 2, 7000), (2, 3, 100)):
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                               "--master-port", "29617", os.path.join(root, "tools", "dist_check.py"), str(refs), str(dim), str(gather)],
-                             capture_output=True, text=True, timeout=600)
+                             capture_output=True, text=True, timeout=240)
         assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
@@ -378,7 +378,7 @@ def test_undivided_run_on_a_multi_rank_context():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29618", os.path.join(root, "tools", "dist_check.py"), "1", "3", "400000"],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "DIST CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 

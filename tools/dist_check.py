@@ -6,7 +6,8 @@ and the SAME Newton / BiCGStab iteration counts (+-1 per solve: the partition ch
   torchrun ... tools/dist_check.py <numRefs> <dim> [gather_dofs]
 gather_dofs overrides ADMM_B200_GATHER_DOFS so that small test grids are decomposed at all (default here: 100 -> only level 0
 is agglomerated)."""
-import os, sys, time
+import faulthandler, os, sys, time
+faulthandler.dump_traceback_later(int(os.environ.get("DIST_CHECK_WATCHDOG_S", "180")), exit=True)   # a hang prints where, then ends the rank
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 refs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dim = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -80,5 +81,7 @@ if rank == 0:
     assert worst <= 1
     assert rel < 1e-9
     print("DIST CHECK OK")
+sys.stdout.flush()
 dist.barrier()
 dist.destroy_process_group()
+faulthandler.cancel_dump_traceback_later()
