@@ -45,6 +45,7 @@ struct Context {
     bool use_cache = true;  // result caches (VecProd batches, L2Norm components); ADMM_B200_NO_CACHE=1 disables
     bool use_loop = true;   // ADMM_B200_LOOP: the whole BiCGStab loop as one graph launch (conditional WHILE node, device-side ConvCheck)
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
+    int assembly_variant = 0; // ADMM_B200_ASSEMBLY: 0 = row-owner gather (no atomics, reproducible), 1 / "atomic" = per-element atomic scatter
     int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals

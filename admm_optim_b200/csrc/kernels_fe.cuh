@@ -213,6 +213,157 @@ __global__ void __launch_bounds__(128) k_assemble_hessian(int64_t ne, const int*
     }
 }
 
+// Row-owner assembly of the same operator without atomics (default): a group of LPR lanes owns one block row.
+//   phase 1: lane i computes the geometry (and, with multipliers, F, cof F G_b, the weight wc) of the i-th element incident to the
+//            row's vertex and parks the record in shared memory -- every element is evaluated once per incident vertex;
+//   phase 2: lane j owns the j-th block (v, w_j) of the row: it walks the parked elements, picks those that contain w_j and adds
+//            their (a, b) contribution to nine accumulators in a fixed order, then writes its block: the row is written once, fully
+//            coalesced, never read -- no memset, no atomics, bitwise reproducible.
+// Needs the vertex -> element incidence (v2e, elements ascending) instead of the per-element block positions of the scatter kernel.
+template <int D>
+struct HessRec {
+    double G[D + 1][D];
+    double CG[D + 1][D];
+    double F[D][D];
+    double vol, wc;
+    int v[D + 1];
+};
+
+template <int D, int LPR>
+__global__ void __launch_bounds__(128) k_assemble_hessian_rows(int nv, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                                               const int* __restrict__ v2e_ptr, const int* __restrict__ v2e_idx,
+                                                               const int* __restrict__ elems, const double* __restrict__ xyz,
+                                                               const double* __restrict__ u, const unsigned char* __restrict__ dirmask,
+                                                               HessParams P, double* __restrict__ vals) {
+    constexpr int N = D + 1, DD = D * D;
+    extern __shared__ __align__(16) unsigned char sm_hess[];
+    HessRec<D>* recs = reinterpret_cast<HessRec<D>*>(sm_hess) + (threadIdx.x / LPR) * LPR;       // this group's LPR records
+    const int gl = threadIdx.x % LPR;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR, ngroups = (int64_t)gridDim.x * blockDim.x / LPR;
+    const int64_t rounds = (nv + ngroups - 1) / ngroups;                 // every lane of a warp runs the same number of rounds
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+        const int64_t row = gid + rd * ngroups;
+        const bool row_on = row < nv;
+        const int es = row_on ? v2e_ptr[row] : 0, ee = row_on ? v2e_ptr[row + 1] : 0;
+        const int bs = row_on ? rowptr[row] : 0, be = row_on ? rowptr[row + 1] : 0;
+        int nel = ee - es, nbl = be - bs;
+        // warp-uniform trip counts (groups of one warp own different rows)
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) { nel = max(nel, __shfl_xor_sync(0xffffffffu, nel, o)); nbl = max(nbl, __shfl_xor_sync(0xffffffffu, nbl, o)); }
+        const unsigned char mrow = (row_on && dirmask) ? dirmask[row] : 0;
+        for (int b0 = 0; b0 < nbl; b0 += LPR) {
+            const int blk = bs + b0 + gl;
+            const bool blk_on = blk < be;
+            const int w = blk_on ? colidx[blk] : -1;
+            double acc[DD];
+#pragma unroll
+            for (int k = 0; k < DD; ++k) acc[k] = 0.0;
+            for (int e0 = 0; e0 < nel; e0 += LPR) {
+                __syncwarp();                                            // the previous chunk's records have been consumed
+                if (es + e0 + gl < ee) {
+                    const int64_t e = v2e_idx[es + e0 + gl];
+                    Elem<D> E;
+                    elem_load<D>(elems, xyz, e, E);
+                    HessRec<D>& R = recs[gl];
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        R.v[a] = E.v[a];
+#pragma unroll
+                        for (int c = 0; c < D; ++c) R.G[a][c] = E.G[a][c];
+                    }
+                    R.vol = E.vol;
+                    R.wc = 0.0;
+                    if (P.has_lam) {
+                        double gu[D][D], ubar[D], F[D][D], C[D][D];
+                        elem_gradu<D>(E, u, gu, ubar);
+                        cof_det<D>(gu, F, C);
+                        double wc = P.lam_vol;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) wc += P.lam_b[k] * (E.xbar[k] + ubar[k]);
+                        R.wc = wc;
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = 0; j < D; ++j) R.F[i][j] = F[i][j];
+#pragma unroll
+                        for (int a = 0; a < N; ++a)
+#pragma unroll
+                            for (int i = 0; i < D; ++i) {
+                                double sC = 0.0;
+#pragma unroll
+                                for (int j = 0; j < D; ++j) sC += C[i][j] * E.G[a][j];
+                                R.CG[a][i] = sC;
+                            }
+                    }
+                }
+                __syncwarp();
+                const int cnt = min(LPR, ee - es - e0);                  // records of this group (<= 0: none)
+                if (blk_on) {
+                    for (int r = 0; r < cnt; ++r) {
+                        const HessRec<D>& R = recs[r];
+                        int a = -1, b = -1;
+#pragma unroll
+                        for (int q = 0; q < N; ++q) { if (R.v[q] == (int)row) a = q; if (R.v[q] == w) b = q; }
+                        if (b < 0) continue;                             // the element does not contain w (a >= 0 always: it is incident to the row)
+                        double Ga[D], Gb[D];
+#pragma unroll
+                        for (int c = 0; c < D; ++c) { Ga[c] = R.G[a][c]; Gb[c] = R.G[b][c]; }
+                        double gg = 0.0;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) gg += Ga[c] * Gb[c];
+                        double B[D][D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = 0; j < D; ++j) B[i][j] = (i == j) ? P.c * gg : 0.0;
+                        if (P.has_lam) {
+                            const double wc = R.wc;
+                            if constexpr (D == 2) {
+                                const double dt = wc * (Ga[0] * Gb[1] - Ga[1] * Gb[0]);
+                                B[0][1] += dt;
+                                B[1][0] -= dt;
+                            } else {
+                                const double w0 = Ga[1] * Gb[D - 1] - Ga[D - 1] * Gb[1];
+                                const double w1 = Ga[D - 1] * Gb[0] - Ga[0] * Gb[D - 1];
+                                const double w2 = Ga[0] * Gb[1] - Ga[1] * Gb[0];
+                                double t[3];
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) t[k] = wc * (w0 * R.F[k % D][0] + w1 * R.F[k % D][1] + w2 * R.F[k % D][D - 1]);
+                                B[0][1] += t[2];     B[0][D - 1] -= t[1];
+                                B[1][0] -= t[2];     B[1][D - 1] += t[0];
+                                B[D - 1][0] += t[1]; B[D - 1][1] -= t[0];
+                            }
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                const double lk = P.lam_b[k] * (1.0 / (D + 1));
+#pragma unroll
+                                for (int j = 0; j < D; ++j) B[k][j] += lk * R.CG[b][j];
+#pragma unroll
+                                for (int i = 0; i < D; ++i) B[i][k] += lk * R.CG[a][i];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = 0; j < D; ++j) acc[i * D + j] += R.vol * B[i][j];
+                    }
+                }
+            }
+            if (blk_on) {
+                const unsigned char mw = dirmask ? dirmask[w] : 0;
+                double* dst = vals + (int64_t)blk * DD;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        const bool dead = ((mrow >> i) & 1) || ((mw >> j) & 1);      // Dirichlet rows / columns (unit diagonal: k_dirichlet_diag)
+                        dst[i * D + j] = dead ? 0.0 : acc[i * D + j];
+                    }
+            }
+        }
+    }
+}
+
 // unit diagonal for Dirichlet dofs (DirichletBoundary adjust_jacobian, 3d_admm.lua:445-462)
 template <int D>
 __global__ void k_dirichlet_diag(int nv, const unsigned char* __restrict__ dirmask, const unsigned char* __restrict__ owned,

@@ -47,7 +47,9 @@ struct LevelDev {
     DevBuf<int> pa, pb;                          // parents of vertices nvc..nv-1
     DevBuf<int> vsub;
     DevBuf<double> xyz;                          // top level only
-    DevBuf<int> elems, elem_pos;                 // top level only
+    DevBuf<int> elems;                           // top level only
+    DevBuf<int> v2e_ptr, v2e_idx;                // top level only: vertex -> incident elements (ascending), row-owner assembly
+    DevBuf<int> elem_pos;                        // top level, built on demand: block positions per element (atomic-scatter assembly variant)
 };
 
 struct MatrixData;
@@ -168,8 +170,18 @@ void Domain::finalize() {
         if (l == nl - 1) {
             L.xyz.upload(H.xyz, ctx->stream);
             L.elems.upload(H.elems, ctx->stream);
-            L.elem_pos.alloc((size_t)H.ne * (H.dim + 1) * (H.dim + 1));
-            if (H.dim == 2) launch_elem_pos<2>(ctx, L); else launch_elem_pos<3>(ctx, L);
+            {   // vertex -> element incidence, elements ascending (fixed summation order of the row-owner assembly)
+                const int N = H.dim + 1;
+                AB_REQUIRE((int64_t)H.ne * N < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "level exceeds int32 incidence entries");
+                std::vector<int> vp((size_t)H.nv + 1, 0), vi((size_t)H.ne * N);
+                for (size_t k = 0; k < (size_t)H.ne * N; ++k) vp[H.elems[k] + 1]++;
+                for (int v = 0; v < H.nv; ++v) vp[v + 1] += vp[v];
+                std::vector<int> fill(vp.begin(), vp.end() - 1);
+                for (int e = 0; e < H.ne; ++e)
+                    for (int a = 0; a < N; ++a) vi[fill[H.elems[(size_t)e * N + a]]++] = e;
+                L.v2e_ptr.upload(vp, ctx->stream);
+                L.v2e_idx.upload(vi, ctx->stream);
+            }
         }
         if (l < nl - 1) { H.edges.clear(); H.edges.shrink_to_fit(); H.have_edges = false; }
     }
@@ -1335,9 +1347,21 @@ static void assemble_hessian_kernels(Domain* dom, DomainDisc* dd, ElemDisc* h, c
     P.lam_b[1] = h->params[AB_PARAM_LAMBDA_BARY_Y];
     P.lam_b[2] = D == 3 ? h->params[AB_PARAM_LAMBDA_BARY_Z] : 0.0;
     P.has_lam = (P.lam_vol != 0.0 || P.lam_b[0] != 0.0 || P.lam_b[1] != 0.0 || P.lam_b[2] != 0.0) ? 1 : 0;
-    AB_CUDA(cudaMemsetAsync(vals, 0, (size_t)L.nnzb * D * D * sizeof(double), ctx->stream));
     const unsigned char* mask = dd->mask(dom->top());
-    AB_LAUNCH(ctx, (k_assemble_hessian<D>), grid_for(L.ne, 128, ctx->num_sms * 16), 128, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u, L.elem_pos.p, mask, P, vals);
+    if (ctx->assembly_variant == 0) {      // row-owner gather: every block row is written once, no memset, no atomics
+        constexpr int LPR = D == 3 ? 32 : 8;
+        const int64_t threads = (int64_t)L.nv * LPR;
+        AB_LAUNCH(ctx, (k_assemble_hessian_rows<D, LPR>), grid_for(threads, 128, ctx->num_sms * 16), 128, 128 * sizeof(HessRec<D>), L.nv, L.rowptr.p, L.colidx.p,
+                  L.v2e_ptr.p, L.v2e_idx.p, L.elems.p, L.xyz.p, u, mask, P, vals);
+    } else {                               // atomic scatter per element (ADMM_B200_ASSEMBLY=atomic; kept for the A/B measurement)
+        LevelDev& Lm = dom->dev[dom->top()];
+        if (Lm.elem_pos.n == 0) {
+            Lm.elem_pos.alloc((size_t)L.ne * (D + 1) * (D + 1));
+            launch_elem_pos<D>(ctx, Lm);
+        }
+        AB_CUDA(cudaMemsetAsync(vals, 0, (size_t)L.nnzb * D * D * sizeof(double), ctx->stream));
+        AB_LAUNCH(ctx, (k_assemble_hessian<D>), grid_for(L.ne, 128, ctx->num_sms * 16), 128, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u, L.elem_pos.p, mask, P, vals);
+    }
     if (mask) AB_LAUNCH(ctx, (k_dirichlet_diag<D>), ew_grid(ctx, (int64_t)L.nv * D), 256, 0, L.nv, mask,
                         dom->distributed() ? dom->iface[dom->top()].owned.p : (const unsigned char*)nullptr, L.diagpos.p, vals);
 }
@@ -1538,6 +1562,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (const char* v = getenv("ADMM_B200_LOOP")) c->use_loop = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_L2_HINT")) c->l2_hint = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
+    if (const char* v = getenv("ADMM_B200_ASSEMBLY")) c->assembly_variant = (strcmp(v, "atomic") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
     spmv_prepare_kernels();
     cudaDeviceProp prop;
     AB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1583,6 +1608,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "spmv_waves") ctx->spmv_waves = std::max(1, value);
     else if (k == "graph") ctx->use_graph = value != 0;
     else if (k == "coarse_variant") ctx->coarse_variant = value;
+    else if (k == "assembly_variant") ctx->assembly_variant = value != 0 ? 1 : 0;
     else if (k == "pdl") ctx->use_pdl = value != 0;
     else if (k == "loop") ctx->use_loop = value != 0;
     else if (k == "l2_hint") ctx->l2_hint = value != 0;
