@@ -12,6 +12,17 @@ Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: J' uploa
 and u downloaded every step through the public API.  `roofline`: the dominant kernel (k_bsr_spmv family)
 timed with CUDA events on a level whose matrix exceeds L2.  `cpu_baseline` / `--impl reference`: the CPU
 oracle port of the same algorithm timed on this box's host cores (the only places oracle/ is executed).
+
+Further keys of the line (every N):
+  parity             first two ADMM iterations at the golden tolerance against tests/golden/admm_trace_3d_refs2.json (asserted:
+                     scalars 1e-8, |u| 1e-9); at N > 1 also `decomposed`: the domain-decomposed numRefs-4 iteration against the
+                     undivided run of the same problem on rank 0's GPU
+  admm_refs4         BASELINE.json configs[2]: one ADMM iteration at numRefs = 4 (2.58 M DoFs), strong scaling over the N GPUs
+  admm_2d_refs7      BASELINE.json configs[3]: 2d_admm.lua on refined.ugx, numRefs = 7 (4.53 M DoFs): ADMM iteration, SpMV, V-cycle
+  vcycle_frac_effective / vcycle_frac_dram   V-cycle bandwidth by the SURVEY 8(d) formula (7 matrix passes per level) and by the
+                     bytes the kernels really stream (6 passes: the first pre-smoothing step needs no matrix)
+At N > 1 the 44 730-DoF headline problem is below the agglomeration threshold and runs UNDIVIDED (every rank holds the whole
+grid, no communication; ug4.Backend._create_regular_hierarchy); the larger legs are domain-decomposed over the N ranks.
 """
 from __future__ import annotations
 
@@ -117,28 +128,33 @@ def vcycle_bytes(dim, levels):
     return tot
 
 
+def vcycle_dram_bytes(dim, levels, pre=3, post=3):
+    """Bytes the V(pre,post) kernels of this library really stream per cycle (what ncu's dram__bytes should show on levels
+    larger than L2), per level l >= 1 with n = nb*dim unknowns and M = nnzb*(8 dim^2 + 4) + 4 nb matrix bytes:
+      first pre-smoothing step from a zero guess  (k_smooth_first, NO matrix pass): read dinv, b; write d, x          4 * 8n
+      every other smoothing step (SpMV mode 2)    M + x gathered (8n) + slices b, dinv, x (+ d unless c1 = 0) + write d, y
+      residual (mode 1)                           M + x (8n) + b (8n) + write r (8n)
+      restriction                                 fine r (8 n) + mid table (4 nnzb_c) + row extents, diagonal positions (8 nb_c) + write (8 n_c)
+      prolongation + correction                   parents (8 (nb - nb_c)) + xc (8 n_c) + x in, x out (16 n)
+    i.e. pre + post matrix passes per level instead of the pre + post + 1 of the SURVEY 8(d) formula."""
+    tot = 0
+    for l in range(1, len(levels)):
+        nb, nnzb = levels[l]
+        nbc, nnzbc = levels[l - 1]
+        n, nc = nb * dim, nbc * dim
+        M = nnzb * (8 * dim * dim + 4) + 4 * nb
+        step = lambda with_d: M + 8 * n + (4 if with_d else 3) * 8 * n + 2 * 8 * n
+        tot += 4 * 8 * n + (pre - 1) * step(True)                    # pre-smoothing
+        tot += M + 3 * 8 * n                                          # residual
+        tot += 8 * n + 4 * nnzbc + 8 * nbc + 8 * nc                   # restriction
+        tot += 8 * (nb - nbc) + 8 * nc + 16 * n                       # prolongation
+        tot += step(False) + (post - 1) * step(True)                  # post-smoothing (first step: c1 = 0)
+    return tot
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU oracle legs (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------
-def oracle_threads(refs):
-    """Host threads the CPU port uses: the C kernels (GS sweep, SpMV) fork per call, which only pays off on big levels."""
-    return 1 if refs <= 2 else max(1, min(cpu_cores(), 16))
-
-
-def oracle_problem(refs):
-    from admm_optim_b200.driver import ObstacleOptim
-    from oracle import ug4_np
-    # Gauss-Seidel is what the reference's descriptor asks for (u3:16): sequential lexicographic on one thread,
-    # block-Jacobi across threads otherwise (UG4's behaviour under mpirun, SURVEY App. C5)
-    # fast_assembly: the element loops of the P1 assembly run in C (oracle/oracle_kernels.c) -- with NumPy assembly two thirds of
-    # the CPU iteration were temporaries, which no compiled reference would pay
-    ug = ug4_np.Backend(smoother="gs", threads=oracle_threads(refs), fast_assembly=True)
-    p = ObstacleOptim(ug, 3, numRefs=refs, grid=GRID3D).setup()
-    p.set_sensitivity(p.synthetic_sensitivity(0.5))
-    p.begin_step()
-    return p
-
-
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -146,49 +162,108 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+CPU_NOTE = ("UG4 cannot be built or run here (no UG4 / plugins / Lua in the image; /root/reference holds only the Lua drivers), so this arm is the "
+            "CPU port of the same algorithm: scalar CRS fp64, P1 assembly in C, Galerkin RAP + V(3,3) Gauss-Seidel GMG (GS inside each thread's "
+            "row block, Jacobi between blocks = UG4 under mpirun) + dense-LU base solve + BiCGStab in C/OpenMP (oracle/solver_c.c) on all host "
+            "cores, driven by the same script replay. The GPU arm smooths with Chebyshev(3)-Jacobi instead of GS (stated equivalent, DESIGN.md): "
+            "the ratio of the two arms is 'B200 path vs this CPU port', not 'vs UG4'")
+
+
+def oracle_problem(refs, threads=None):
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    # Gauss-Seidel is what the reference's descriptor asks for (u3:16): sequential lexicographic on one thread, block-Jacobi across
+    # threads otherwise (UG4's behaviour under mpirun).  fast_assembly / c_solver: element loops and the whole
+    # solver:init + solver:apply path run compiled (oracle_kernels.c, solver_c.c); what stays in NumPy is vector algebra and the norms
+    threads = cpu_cores() if threads is None else threads
+    ug = ug4_np.Backend(smoother="gs", threads=threads, fast_assembly=True, c_solver=True)
+    p = ObstacleOptim(ug, 3, numRefs=refs, grid=GRID3D).setup()
+    p.set_sensitivity(p.synthetic_sensitivity(0.5))
+    p.begin_step()
+    return p
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np  # noqa: F401
-    p = oracle_problem(args.refs)
+    cores = cpu_cores()
+    p = oracle_problem(args.refs, cores)
     for _ in range(args.warmup):
         p.admm_iteration()
     t0 = time.perf_counter()
+    its = 0
     for _ in range(args.steps):
         rec = p.admm_iteration()
         assert rec is not None, "oracle ADMM iteration failed"
+        its += sum(n["its"]["rhs"] + n["its"]["large"] + sum(n["its"]["B"]) for n in rec["newton"])
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    cores = oracle_threads(args.refs)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "3d_admm.lua ADMM loop on box_3D_elongated.ugx, numRefs=%d, synthetic J'" % args.refs, "numRefs": args.refs,
-                       "note": "UG4 is not installable here; this is the CPU oracle port (NumPy/SciPy + C kernels for the P1 assembly, the Gauss-Seidel sweep and SpMV, V(3,3), SuperLU base solve)",
-                       "host_cores_available": cpu_cores()},
+            "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, global_counts(args.refs)[-1][0] * 3),
+                       "numRefs": args.refs, "dofs": global_counts(args.refs)[-1][0] * 3, "note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % cores,
+                       "host_cores_available": cores, "bicgstab_its_per_step": its / args.steps},
             "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port",
-                             "sample": "%d full ADMM iterations (NumPy/SciPy oracle with C kernels for assembly / GS / SpMV, %d thread(s))" % (args.steps, cores)},
+                             "sample": "%d full ADMM iterations of the same workload (C/OpenMP solve path + C assembly on %d threads, NumPy vector algebra)" % (args.steps, cores)},
             "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_sample(refs):
-    p = oracle_problem(refs)
-    t0 = time.perf_counter()
-    rec = p.admm_iteration()
-    dt = time.perf_counter() - t0
-    assert rec is not None
-    return {"value": 1.0 / dt, "unit": "iters/s", "cores": oracle_threads(refs), "kind": "port", "host_cores_available": cpu_cores(),
-            "sample": "1 ADMM iteration (first of the loop, %d Newton its) of the same workload, NumPy/SciPy oracle with C kernels for the P1 assembly, "
-                      "the lexicographic GS sweep and the SpMV" % len(rec["newton"]),
+    cores = cpu_cores()
+    out = {}
+    for label, threads in (("all", cores), ("one", 1)):
+        p = oracle_problem(refs, threads)
+        p.admm_iteration()                                            # first iteration: static solver data, C library load
+        t0 = time.perf_counter()
+        rec = p.admm_iteration()
+        dt = time.perf_counter() - t0
+        assert rec is not None
+        out[label] = (1.0 / dt, rec)
+    v, rec = out["all"]
+    return {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "host_cores_available": cores,
+            "value_1_thread": out["one"][0],
+            "sample": "1 ADMM iteration (second of the loop, %d Newton its) of the same workload: CPU port with the C/OpenMP solve path "
+                      "(RAP, V(3,3) Gauss-Seidel GMG, dense-LU base solve, BiCGStab) and C assembly on %d threads; value_1_thread = the same on one thread "
+                      "(sequential lexicographic Gauss-Seidel)" % (len(rec["newton"]), cores),
+            "note": CPU_NOTE,
             "newton_iterations": len(rec["newton"]),
-            "bicgstab_iterations_first_newton": rec["newton"][0]["its"]}
+            "bicgstab_iterations_first_newton": rec["newton"][0]["its"],
+            "bicgstab_iterations_first_newton_1_thread": out["one"][1]["newton"][0]["its"]}
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def golden_parity(ug, name="3d_refs2"):
+    """First two ADMM iterations at the golden tolerance against the committed golden trace (tests/golden, made by
+    tools/make_golden.py from the CPU oracle).  north_star: per-iteration scalars within 1e-8 relative, u within 1e-9."""
+    import numpy as np
+    from admm_optim_b200.driver import ObstacleOptim
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "admm_trace_%s.json" % name)))
+    p = ObstacleOptim(ug, gold["dim"], numRefs=gold["numRefs"], grid=os.path.join(ROOT, "grids", gold["grid"]), admmSteps=2).setup()
+    for s in [p.SmallProblemRHS_Solver, p.LargeProblem_Solver] + p.B_Solver:
+        s.desc.abs_tol = gold["abs_tol"]
+    p.set_sensitivity(p.synthetic_sensitivity(gold["amplitude"]))
+    tr = p.run_admm()
+    assert len(tr) == len(gold["admm"]) and not p.p_solver_failure, "ADMM replay failed"
+    rel = lambda a, b, floor: abs(a - b) / max(abs(b), floor)
+    out = {"golden": "tests/golden/admm_trace_%s.json" % name,
+           "u_diff_rel": max(rel(a["u_diff"], g["u_diff"], 1e-3) for a, g in zip(tr, gold["admm"])),
+           "lambda_inc_rel": max(rel(a["lambda_inc"], g["lambda_inc"], 1e-3) for a, g in zip(tr, gold["admm"])),
+           "max_norm_rel": max(rel(a["max_norm"], g["max_norm"], 1e-3) for a, g in zip(tr, gold["admm"])),
+           "Lambda_rel": max(rel(x, y, 1e-2) for a, g in zip(tr, gold["admm"]) for x, y in zip(a["Lambda"], g["Lambda"])),
+           "newton_its": [len(a["newton"]) for a in tr], "newton_its_golden": [g["newton_its"] for g in gold["admm"]]}
+    u = p.u.to_numpy()
+    out["u_l2_rel"] = abs(float(np.linalg.norm(u)) - gold["u_l2"]) / gold["u_l2"]
+    out["ok"] = bool(max(out["u_diff_rel"], out["lambda_inc_rel"], out["max_norm_rel"], out["Lambda_rel"]) <= 1e-8 and out["u_l2_rel"] <= 1e-9
+                     and all(abs(a - b) <= 1 for a, b in zip(out["newton_its"], out["newton_its_golden"])))
+    return out
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -209,19 +284,44 @@ def run_b200(args):
     stream = torch.cuda.Stream()
     ug = ug4.Backend(device=local, stream=stream.cuda_stream, distributed=world > 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    peak, peak_src = measured_peak()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # multi-GPU: the SAME global problem is domain-decomposed over the ranks (strong scaling): level-0 elements are
-    # partitioned (RCB), every rank refines its sub-grid, interface sums + all-reduces run on NCCL
+    def maxtime(t):
+        x = torch.tensor([t], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return float(x.item())
+
+    def timeit(fn, reps):
+        """seconds per call: CUDA events on the launching stream, max over ranks"""
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return maxtime(e0.elapsed_time(e1) / reps * 1e-3)
+
+    # ---- parity before anything is timed ------------------------------------------------------------------
+    parity = golden_parity(ug)
+    assert parity["ok"], "parity against the golden trace failed: %s" % parity
+
+    # ---- headline: ADMM iterations at the script's default refinement ---------------------------------------
+    # multi-GPU: 44 730 unknowns are far below the agglomeration threshold -> the problem runs undivided on every rank (no
+    # communication); the decomposed path is measured by the legs below
     prob = ObstacleOptim(ug, 3, numRefs=args.refs, grid=GRID3D).setup()
     ndofs_local = prob.DeformationSpace_ApproxSpace.num_dofs()
     J_host = torch.from_numpy(prob.synthetic_sensitivity(0.5)).pin_memory()
     u_host = torch.empty(ndofs_local, dtype=torch.float64).pin_memory()
-    ndofs = global_counts(args.refs)[-1][0] * 3 if world > 1 else ndofs_local
+    ndofs = global_counts(args.refs)[-1][0] * 3
 
     def timed_leg(e2e):
         prob.set_sensitivity(J_host.numpy())
@@ -254,51 +354,120 @@ def run_b200(args):
             its += sum(n["its"]["rhs"] + n["its"]["large"] + sum(n["its"]["B"]) for n in rec["newton"])
         barrier()
         launches = ug.launch_count() - launches0
-        t = torch.tensor([total_ms, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tm = t.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            t[0] = tm[0]
-        return float(t[0].item()), launches, newton, its, rec, int(t[1].item()), int(t[2].item())
+        return maxtime(total_ms), launches, newton, its, rec, h2d, d2h
 
     clocks = ClockSampler(local)
     clocks.start()
     ms_dev, launches, newton, its, rec, _, _ = timed_leg(False)
     ms_e2e, _, _, _, _, h2d_bytes, d2h_bytes = timed_leg(True)
     clk = clocks.stop()
+    headline_decomposed = bool(prob.dom.decomposed)
+    del prob
 
-    # ---- roofline leg: SpMV / V-cycle on a level larger than L2 ---------------------------------
-    roof, extra = None, {}
-    if args.roofline_refs > 0:
-        big = ObstacleOptim(ug, 3, numRefs=args.roofline_refs, grid=GRID3D).setup()
-        DD = big.DeformationEquation_DomainDisc
-        DD.assemble_jacobian(big.A_u_Hessian, big.u)
-        levels = global_counts(args.roofline_refs) if world > 1 else None
-        _, nb_loc, nnzb_loc = big.A_u_Hessian.info()
-        nb, nnzb = (levels[-1] if world > 1 else (nb_loc, nnzb_loc))
-        x = np.random.default_rng(1 + rank).standard_normal(nb_loc * 3)
-        big.sigma.from_numpy(x)
-        DD.adjust_solution(big.sigma)
+    # ---- one ADMM iteration of a larger configuration (BASELINE.json configs[2] / configs[3]) -------------------
+    def admm_leg(ug, dim, refs, grid, steps=2, collective=True):
+        bar = barrier if collective else torch.cuda.synchronize
+        mx = maxtime if collective else (lambda t: t)
+        p = ObstacleOptim(ug, dim, numRefs=refs, grid=grid).setup()
+        p.set_sensitivity(p.synthetic_sensitivity(0.5))
+        p.begin_step()
+        assert p.admm_iteration() is not None                     # warm-up (captures the solver graphs, fills the pools)
+        ug.synchronize(); bar()
+        t0 = time.perf_counter()
+        recs = []
+        for _ in range(steps):
+            r = p.admm_iteration()
+            assert r is not None and not p.p_solver_failure
+            recs.append(r)
+        ug.synchronize()
+        dt = mx(time.perf_counter() - t0) / steps
+        levels = global_counts(refs, dim)
+        cm = p.ucmps.split(",")
+        u_l2 = float(np.sqrt(sum(ug.L2Norm(p.u, c, 4, "outer") ** 2 for c in cm)))
+        out = {"numRefs": refs, "dofs": levels[-1][0] * dim, "iters_per_s": 1.0 / dt, "ms_per_step": dt * 1e3,
+               "newton_its": [len(r["newton"]) for r in recs],
+               "bicgstab_its": [sum(n["its"]["rhs"] + n["its"]["large"] + sum(n["its"]["B"]) for n in r["newton"]) for r in recs],
+               "u_diff": recs[-1]["u_diff"], "lambda_inc": recs[-1]["lambda_inc"], "max_norm": recs[-1]["max_norm"], "Lambda": [float(v) for v in recs[-1]["Lambda"]],
+               "L_lambda_max": max(abs(float(v)) for v in recs[-1]["L_lambda"]), "u_l2": u_l2, "reference_volume": p.ReferenceVolume,
+               "decomposed": bool(p.dom.decomposed), "gather_level": p.dom._dist["gather_level"] if p.dom.decomposed else None, "n_gpus": ug.nranks}
+        if ug.nranks > 1 and p.dom.decomposed:
+            assert p.dom.p2p_status()["error"] == 0, "peer-to-peer interface exchange timed out"
+        return out, p
 
-        def timeit(fn, reps):
-            for _ in range(3):
-                fn()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    extra = {}
+    if args.admm_refs > 0:
+        a4, p4 = admm_leg(ug, 3, args.admm_refs, GRID3D)
+        del p4
+        extra["admm_refs%d" % args.admm_refs] = a4
+        if world > 1 and a4["decomposed"]:
+            # multi-GPU parity inside the driver-run line: the same problem and iteration sequence, UNDIVIDED, on rank 0's own GPU
+            # (the other ranks wait at the barrier)
+            if rank == 0:
+                ug1 = ug4.Backend(device=local, stream=stream.cuda_stream, distributed=False)
+                r4, p1 = admm_leg(ug1, 3, args.admm_refs, GRID3D, collective=False)
+                del p1, ug1
+                rel = lambda a, b, floor: abs(a - b) / max(abs(b), floor)
+                d = {"against": "undivided run of the same numRefs-%d iterations on rank 0 (1 GPU)" % args.admm_refs,
+                     "u_diff_rel": rel(a4["u_diff"], r4["u_diff"], 1e-3), "lambda_inc_rel": rel(a4["lambda_inc"], r4["lambda_inc"], 1e-3),
+                     "max_norm_rel": rel(a4["max_norm"], r4["max_norm"], 1e-3), "u_l2_rel": rel(a4["u_l2"], r4["u_l2"], 1e-300),
+                     "Lambda_rel": max(rel(x, y, 1e-2) for x, y in zip(a4["Lambda"], r4["Lambda"])),
+                     "newton_its": a4["newton_its"], "newton_its_undivided": r4["newton_its"],
+                     "bicgstab_its": a4["bicgstab_its"], "bicgstab_its_undivided": r4["bicgstab_its"], "ms_per_step_undivided": r4["ms_per_step"]}
+                d["ok"] = bool(max(d["u_diff_rel"], d["lambda_inc_rel"], d["max_norm_rel"], d["Lambda_rel"]) <= 1e-8 and d["u_l2_rel"] <= 1e-9
+                               and d["newton_its"] == d["newton_its_undivided"])
+                parity["decomposed"] = d
+                assert d["ok"], "multi-GPU parity failed: %s" % d
             barrier()
-            e0.record(stream)
-            for _ in range(reps):
-                fn()
-            e1.record(stream)
-            e1.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / reps * 1e-3], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
+    if args.dim2_refs > 0:
+        a2, p2 = admm_leg(ug, 2, args.dim2_refs, GRID2D)
+        # SpMV / V-cycle of the 2D top level (2x2 blocks)
+        DD2 = p2.DeformationEquation_DomainDisc
+        DD2.assemble_jacobian(p2.A_u_Hessian, p2.u)
+        lv2 = global_counts(args.dim2_refs, 2)
+        n_loc = p2.DeformationSpace_ApproxSpace.num_dofs()
+        p2.sigma.from_numpy(np.random.default_rng(3 + rank).standard_normal(n_loc)); DD2.adjust_solution(p2.sigma)
+        t_spmv2 = timeit(lambda: p2.A_u_Hessian.apply(p2.Lu, p2.sigma), 20)
+        s2 = p2.SmallProblemRHS_Solver
+        s2.init(p2.A_u_Hessian, p2.sigma)
+        t_v2 = timeit(lambda: s2.vcycle(p2.delta_u, p2.sigma), 10)
+        b2, bv2, bd2 = spmv_bytes(2, *lv2[-1]), vcycle_bytes(2, lv2), vcycle_dram_bytes(2, lv2)
+        a2.update(spmv_ms=t_spmv2 * 1e3, spmv_gbs=b2 / t_spmv2 / 1e9, spmv_frac=b2 / t_spmv2 / 1e9 / (peak * world),
+                  vcycle_ms=t_v2 * 1e3, vcycle_frac_effective=bv2 / t_v2 / 1e9 / (peak * world), vcycle_frac_dram=bd2 / t_v2 / 1e9 / (peak * world))
+        del p2
+        extra["admm_2d_refs%d" % args.dim2_refs] = a2
 
-        t_spmv = timeit(lambda: big.A_u_Hessian.apply(big.Lu, big.sigma), 20)
+    # ---- roofline leg: SpMV / V-cycle / solve on a level larger than L2 ---------------------------------
+    roof = None
+    if args.roofline_refs > 0:
+        from admm_optim_b200.driver import linear_solver
+        # lean problem: deformation space + Hessian + solver only (no P0 tensors)
+        ug.InitUG(3, None)
+        dom = ug.Domain(); ug.LoadDomain(dom, GRID3D)
+        ug.util.refinement.CreateRegularHierarchy(dom, args.roofline_refs, False, None)
+        CMP = ["u1", "u2", "u3"]
+        DS = ug.ApproximationSpace(dom); DS.add_fct(",".join(CMP), "Lagrange", 1); DS.init_levels(); DS.init_top_surface()
+        H = ug.DeformationEquation(",".join(CMP), "outer")
+        Dir = ug.DirichletBoundary()
+        for sub in ("inlet", "wall", "outlet"):
+            for c in CMP:
+                Dir.add(0, c, sub)
+        DD = ug.DomainDiscretization(DS); DD.add(H); DD.add(Dir)
+        A = ug.AssembledLinearOperator(DD)
+        xv, bvec, yv, uv = (ug.GridFunction(DS) for _ in range(4))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        DD.assemble_jacobian(A, uv)                               # cold call (first launch of the kernel)
+        os.environ["ADMM_B200_NO_CACHE"] = "1"                    # the signature cache would answer the repeated request
+        barrier(); e0.record(stream); DD.assemble_jacobian(A, uv); e1.record(stream); e1.synchronize()
+        del os.environ["ADMM_B200_NO_CACHE"]
+        t_asm = maxtime(e0.elapsed_time(e1) * 1e-3)
+        levels = global_counts(args.roofline_refs)
+        nb, nnzb = levels[-1]
+        n_loc = DS.num_dofs()
+        x = np.random.default_rng(1 + rank).standard_normal(n_loc)
+        xv.from_numpy(x)
+        DD.adjust_solution(xv)
+        t_spmv = timeit(lambda: A.apply(yv, xv), 20)
         bytes_spmv = spmv_bytes(3, nb, nnzb)
-        peak, peak_src = measured_peak()
         ach = bytes_spmv / t_spmv / 1e9
         roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak,
                 "traffic": NCU_TRAFFIC_BYTES.get(args.roofline_refs) if world == 1 else None,
@@ -306,31 +475,36 @@ def run_b200(args):
                 "bytes_per_launch": bytes_spmv // world, "us_per_launch": t_spmv * 1e6,
                 "workload": "box_3D_elongated numRefs=%d: %d block rows, %d blocks (matrix %.2f GB > L2)%s" %
                             (args.roofline_refs, nb, nnzb, nnzb * 76 / 1e9, " over %d GPUs; per-GPU figures" % world if world > 1 else "")}
-        s = big.SmallProblemRHS_Solver
-        s.init(big.A_u_Hessian, big.sigma)
-        if levels is None:
-            levels = [s.level_info(l) for l in range(args.roofline_refs + 1)]
-        t_v = timeit(lambda: s.vcycle(big.delta_u, big.sigma), 10)
-        bv = vcycle_bytes(3, levels)
-        # one full solve on the big level (GMG-preconditioned BiCGStab to the script tolerance); the first call allocates the
-        # Krylov workspace and captures the iteration graph (one-off), the second one is timed
-        big.Lu.from_numpy(x, 2)
-        DD.adjust_solution(big.Lu)
+        s = linear_solver(ug, DD, DS, False, 3)
+        s.desc.verbose = 0
+        ug.synchronize(); barrier()
+        te = time.perf_counter(); s.init(A, xv); ug.synchronize(); t_init = maxtime(time.perf_counter() - te)
+        t_v = timeit(lambda: s.vcycle(yv, xv), 10)
+        bv, bd = vcycle_bytes(3, levels), vcycle_dram_bytes(3, levels)
+        # one full solve (GMG-preconditioned BiCGStab to the script tolerance); the first call allocates the Krylov workspace and
+        # captures the iteration graph (one-off), the second one is timed
+        bvec.from_numpy(x, 2)
+        DD.adjust_solution(bvec)
         for _ in range(2):
-            big.sigma.set(0.0)
+            yv.set(0.0)
             barrier()
             t0 = time.perf_counter()
-            ok = s.apply(big.sigma, big.Lu)
+            ok = s.apply(yv, bvec)
             ug.synchronize()
-            t_solve = time.perf_counter() - t0
-        extra = {"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / (peak * world),
-                 "vcycle_bytes": bv, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(), "solve_converged": bool(ok)}
-        if world > 1:
-            st = big.dom.p2p_status()
+            t_solve = maxtime(time.perf_counter() - t0)
+        # assembly roofline: the matrix values are written once (nnzb 8 d^2), the mesh is read once (4 (d+1) per element, 8 d per vertex)
+        ne = len(np.load(GRID3D)["elems"]) * 8 ** args.roofline_refs
+        asm_bytes = nnzb * 72 + ne * 16 + nb * 24
+        extra.update({"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / (peak * world),
+                      "vcycle_frac_effective": bv / t_v / 1e9 / (peak * world), "vcycle_frac_dram": bd / t_v / 1e9 / (peak * world),
+                      "vcycle_bytes": bv, "vcycle_dram_bytes": bd, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(),
+                      "solve_converged": bool(ok), "gmg_init_ms": t_init * 1e3, "assemble_ms": t_asm * 1e3,
+                      "assemble_bytes": asm_bytes, "assemble_gbs": asm_bytes / t_asm / 1e9, "assemble_frac": asm_bytes / t_asm / 1e9 / (peak * world),
+                      "roofline_decomposed": bool(dom.decomposed), "roofline_gather_level": dom._dist["gather_level"] if dom.decomposed else None})
+        if world > 1 and dom.decomposed:
+            st = dom.p2p_status()
             assert st["error"] == 0, "peer-to-peer interface exchange timed out (error %d)" % st["error"]
-            extra["decomposed"] = bool(big.dom.decomposed)
-            extra["gather_level"] = big.dom._dist["gather_level"] if big.dom.decomposed else None
-        del big
+        del s, A, DD, xv, bvec, yv, uv, DS, dom
 
     if rank != 0:
         return
@@ -340,19 +514,18 @@ def run_b200(args):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, ndofs),
                        "numRefs": args.refs, "dofs": ndofs,
-                       "parallelism": ("domain decomposition x%d (RCB of the level-0 grid, NCCL interface sums + all-reduces)" % world) if world > 1 else "1 GPU",
+                       "parallelism": ("%d GPUs; this %d-DoF problem is below the agglomeration threshold and runs undivided (no communication); "
+                                       "admm_refs4 / admm_2d_refs7 / the roofline leg are domain-decomposed" % (world, ndofs)) if world > 1 and not headline_decomposed
+                                      else ("domain decomposition x%d" % world if world > 1 else "1 GPU"),
                        "l2": "L2 flushed (256 MB write) between timed iterations; working set itself is L2-sized",
                        "smoother": "Chebyshev(3)-Jacobi (stated equivalent of the reference's sequential GS, DESIGN.md)",
-                       "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps,
-                       "scaling_note": "value at N>1 = the SAME 44 730-DoF problem domain-decomposed (latency-bound, SURVEY 8e); the strong-scaling "
-                                       "numbers that matter are spmv_gbs / vcycle_ms / solve_ms at roofline numRefs and profiles/r01_scaling.md "
-                                       "(numRefs 6: 7.4x from 1 to 8 GPUs)"},
+                       "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
             "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk}
+            "gpu_launches": launches, "clocks": clk, "parity": parity}
     if roof:
         line["roofline"] = roof
-        line.update(extra)
+    line.update(extra)
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample(args.refs)
     print(json.dumps(line))
@@ -366,6 +539,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--refs", type=int, default=2, help="numRefs of the ADMM workload (3d_admm.lua:46 default 2)")
     ap.add_argument("--roofline-refs", type=int, default=5, help="refinement level of the SpMV / V-cycle / solve roofline leg (0 = skip); 5 = 20.3 M DoFs, 7.6 GB matrix")
+    ap.add_argument("--admm-refs", type=int, default=4, help="refinement of the larger 3D ADMM-iteration leg (BASELINE.json configs[2]: numRefs 4); 0 = skip")
+    ap.add_argument("--dim2-refs", type=int, default=7, help="refinement of the 2D leg (BASELINE.json configs[3]: refined.ugx numRefs 7); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -332,6 +332,20 @@ def c_kernels():
                 lib.oracle_hessian_scatter.restype = None
                 lib.oracle_load_scatter.argtypes = [_C.c_int, _C.c_long, ip, dp, dp, dp, dp, _C.c_double, _C.c_int, dp, _C.c_int, _C.c_double, dp]
                 lib.oracle_load_scatter.restype = None
+            if hasattr(lib, "oracle_gmg_create"):
+                vp, ucp = _C.c_void_p, _C.POINTER(_C.c_ubyte)
+                lib.oracle_gmg_create.argtypes = [_C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_int, _C.c_double, _C.c_double]
+                lib.oracle_gmg_create.restype = vp
+                lib.oracle_gmg_set_level.argtypes = [vp, _C.c_int, _C.c_int, _C.c_int, ip, ip, dp, ip, ip, dp, ucp]
+                lib.oracle_gmg_set_level.restype = None
+                lib.oracle_gmg_setup.argtypes = [vp, ip, ip, dp]
+                lib.oracle_gmg_setup.restype = _C.c_int
+                lib.oracle_gmg_vcycle.argtypes = [vp, dp, dp]
+                lib.oracle_gmg_vcycle.restype = None
+                lib.oracle_bicgstab_gmg.argtypes = [vp, dp, dp, _C.c_double, _C.c_double, _C.c_int, _C.POINTER(_C.c_int), dp]
+                lib.oracle_bicgstab_gmg.restype = _C.c_int
+                lib.oracle_gmg_destroy.argtypes = [vp]
+                lib.oracle_gmg_destroy.restype = None
             _CLIB = lib
     return _CLIB or None
 
@@ -540,6 +554,72 @@ class GMG:
 
     def apply(self, b):
         return self.vcycle(len(self.A) - 1, b)
+
+
+class GMGC:
+    """The hierarchy of `GMG` (same Galerkin operators, smoothers, transfers, direct base solve) built and applied by
+    oracle/solver_c.c on `threads` OpenMP threads, together with the BiCGStab loop: bench.py's multi-threaded CPU baseline.
+    The static part (transfers, Dirichlet masks, work vectors) is set once per mesh hierarchy; `setup(A)` runs what the reference
+    does at every solver:init (RAP chain, smoother data, base-solver factorisation).  Gauss-Seidel runs inside each thread's row
+    block with Jacobi coupling between the blocks (threads = 1: the sequential lexicographic sweep of `GMG`)."""
+    SMOOTHERS = {"gs": 0, "cheb": 1, "jac": 2}
+
+    def __init__(self, levels, dmasks, smoother="gs", nu1=3, nu2=3, cheb_ratio=6.0, omega=0.66, threads=1):
+        self.lib = c_kernels()
+        if self.lib is None or not hasattr(self.lib, "oracle_gmg_create"):
+            raise RuntimeError("oracle/liboracle_c.so is not built (make -C oracle)")
+        d = levels[0].dim
+        self.n = levels[-1].nv * d
+        self.h = self.lib.oracle_gmg_create(len(levels), int(threads), self.SMOOTHERS[smoother], nu1, nu2, cheb_ratio, omega)
+        self._keep = []
+        ip_t, dp_t, uc_t = _C.POINTER(_C.c_int), _C.POINTER(_C.c_double), _C.POINTER(_C.c_ubyte)
+        for l, lev in enumerate(levels):
+            mask = np.ascontiguousarray(dmasks[l], np.uint8)
+            if l == 0:
+                self._keep.append(mask)
+                self.lib.oracle_gmg_set_level(self.h, 0, lev.nv * d, 0, None, None, None, None, None, None, mask.ctypes.data_as(uc_t))
+                continue
+            P = prolongation(lev, d).tocsr(); P.sort_indices()
+            R = P.T.tocsr(); R.sort_indices()
+            arrs = [np.ascontiguousarray(P.indptr, np.int32), np.ascontiguousarray(P.indices, np.int32), np.ascontiguousarray(P.data, np.float64),
+                    np.ascontiguousarray(R.indptr, np.int32), np.ascontiguousarray(R.indices, np.int32), np.ascontiguousarray(R.data, np.float64), mask]
+            self._keep.append(arrs)
+            self.lib.oracle_gmg_set_level(self.h, l, lev.nv * d, levels[l - 1].nv * d, arrs[0].ctypes.data_as(ip_t), arrs[1].ctypes.data_as(ip_t),
+                                          arrs[2].ctypes.data_as(dp_t), arrs[3].ctypes.data_as(ip_t), arrs[4].ctypes.data_as(ip_t),
+                                          arrs[5].ctypes.data_as(dp_t), mask.ctypes.data_as(uc_t))
+        self._A = None
+
+    def setup(self, A_top):
+        A = A_top.tocsr(); A.sort_indices()
+        self._A = (np.ascontiguousarray(A.indptr, np.int32), np.ascontiguousarray(A.indices, np.int32), np.ascontiguousarray(A.data, np.float64))
+        ip_t, dp_t = _C.POINTER(_C.c_int), _C.POINTER(_C.c_double)
+        rc = self.lib.oracle_gmg_setup(self.h, self._A[0].ctypes.data_as(ip_t), self._A[1].ctypes.data_as(ip_t), self._A[2].ctypes.data_as(dp_t))
+        if rc != 0:
+            raise RuntimeError("coarse-level matrix is singular")
+
+    def apply(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.empty(self.n)
+        dp_t = _C.POINTER(_C.c_double)
+        self.lib.oracle_gmg_vcycle(self.h, b.ctypes.data_as(dp_t), x.ctypes.data_as(dp_t))
+        return x
+
+    def solve(self, b, x0, abs_tol=1e-10, max_it=3000, red_tol=0.0):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.array(x0, dtype=np.float64, copy=True)
+        r = np.empty(self.n)
+        ok = _C.c_int(0)
+        dp_t = _C.POINTER(_C.c_double)
+        its = self.lib.oracle_bicgstab_gmg(self.h, b.ctypes.data_as(dp_t), x.ctypes.data_as(dp_t), abs_tol, red_tol, max_it, _C.byref(ok), r.ctypes.data_as(dp_t))
+        return x, bool(ok.value), int(its), r
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.oracle_gmg_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 def bicgstab(A, b, x0, precond, abs_tol=1e-10, max_it=3000, red_tol=0.0, check_half=False):

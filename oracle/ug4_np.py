@@ -290,9 +290,23 @@ class BiCGStabGMG:
         self.A = A
         pre = self.desc["precond"]
         dom = A.dd.space.dom
+        cache = self.ug._gmg_cache
+        if self.ug.c_solver:
+            # compiled solve path (oracle/solver_c.c): the static part lives with the mesh hierarchy + Dirichlet set, every new
+            # matrix triggers what the reference does at solver:init (RAP chain, smoother data, base factorisation)
+            skey = ("c", id(dom), tuple(sorted(A.dd.dir)), self.ug.smoother, self.ug.threads)
+            if skey not in cache:
+                dmasks = [A.dd.dmask(l) if A.dd.dir else np.zeros(l.nv * l.dim, bool) for l in dom.levels]
+                cache[skey] = [F.GMGC(dom.levels, dmasks, smoother=self.ug.smoother, nu1=pre.get("preSmooth", 3), nu2=pre.get("postSmooth", 3),
+                                      cheb_ratio=self.ug.cheb_ratio, threads=self.ug.threads), None]
+            ent = cache[skey]
+            if ent[1] is not A.mat:
+                ent[0].setup(A.mat)
+                ent[1] = A.mat
+            self.gmg = ent[0]
+            return True
         dmasks = [A.dd.dmask(l) if A.dd.dir else np.zeros(l.nv * l.dim, bool) for l in dom.levels]
         key = (id(A.mat), self.ug.smoother)
-        cache = self.ug._gmg_cache
         if key not in cache:
             cache.clear()
             cache[key] = F.GMG(dom.levels, A.mat, dmasks, smoother=self.ug.smoother, nu1=pre.get("preSmooth", 3),
@@ -302,8 +316,11 @@ class BiCGStabGMG:
 
     def _solve(self, x, b):
         cc = self.desc["convCheck"]
-        sol, ok, its, r = F.bicgstab(self.A.mat, b.v, x.v, self.gmg.apply, abs_tol=cc["absolute"], max_it=cc["iterations"],
-                                     red_tol=cc.get("reduction", 0.0))
+        if self.ug.c_solver:
+            sol, ok, its, r = self.gmg.solve(b.v, x.v, abs_tol=cc["absolute"], max_it=cc["iterations"], red_tol=cc.get("reduction", 0.0))
+        else:
+            sol, ok, its, r = F.bicgstab(self.A.mat, b.v, x.v, self.gmg.apply, abs_tol=cc["absolute"], max_it=cc["iterations"],
+                                         red_tol=cc.get("reduction", 0.0))
         x.v[:] = sol
         x.storage = PST_CONSISTENT
         self.steps, self.last_defect = its, float(np.linalg.norm(r))
@@ -338,12 +355,15 @@ class Backend:
     'gs' (lexicographic Gauss-Seidel, what the reference asks for -- iteration counts side by side)."""
     name = "oracle"
 
-    def __init__(self, smoother="cheb", cheb_ratio=6.0, threads=1, fast_assembly=False):
+    def __init__(self, smoother="cheb", cheb_ratio=6.0, threads=1, fast_assembly=False, c_solver=False):
         """fast_assembly: element loops of the P1 assembly in C (oracle_kernels.c) instead of NumPy -- used by bench.py's CPU
-        legs so that the CPU baseline is not dominated by NumPy temporaries; the tests keep the NumPy path as the checker."""
+        legs so that the CPU baseline is not dominated by NumPy temporaries; the tests keep the NumPy path as the checker.
+        c_solver: solver:init + solver:apply (RAP chain, V-cycle, BiCGStab) in C / OpenMP on `threads` threads (oracle/solver_c.c),
+        bench.py's multi-threaded CPU baseline; pinned against the NumPy statement by tests/test_oracle.py."""
         self.dim = None
         self.smoother, self.cheb_ratio, self.threads = smoother, cheb_ratio, threads
         self.fast_assembly = bool(fast_assembly)
+        self.c_solver = bool(c_solver)
         self._gmg_cache = {}
         self._asm_cache = {}
         self.util = _NS()

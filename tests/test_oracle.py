@@ -266,3 +266,40 @@ def test_fast_assembly_backend_reproduces_the_admm_iteration():
     assert len(a["newton"]) == len(b["newton"])
     for k in ("u_diff", "lambda_inc", "max_norm"):
         assert abs(a[k] - b[k]) <= 1e-11 * max(abs(a[k]), 1e-3), k
+
+
+@pytest.mark.parametrize("dim,grid,refs", [(3, GRID3D, 1), (2, GRID2D, 2)])
+@pytest.mark.parametrize("smoother", ["gs", "cheb", "jac"])
+def test_c_solve_path_matches_numpy_statement(dim, grid, refs, smoother):
+    """oracle/solver_c.c (RAP chain, V(3,3) cycle, dense-LU base solve, BiCGStab in C/OpenMP: bench.py's multi-threaded CPU
+    baseline) against the NumPy/SciPy statement of the same algorithm: one thread -> same V-cycle and solution to rounding and
+    the same iteration count; several threads (Gauss-Seidel becomes block-Jacobi across the thread blocks) ->
+    the same solution at the solver tolerance."""
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import fem_np, ug4_np
+    if fem_np.c_kernels() is None or not hasattr(fem_np.c_kernels(), "oracle_gmg_create"):
+        pytest.skip("oracle/liboracle_c.so not built")
+    outs = {}
+    for name, kw in (("numpy", dict(threads=1)), ("c1", dict(threads=1, c_solver=True)), ("c3", dict(threads=3, c_solver=True))):
+        ug = ug4_np.Backend(smoother=smoother, **kw)
+        p = ObstacleOptim(ug, dim, numRefs=refs, grid=grid).setup()
+        p.Hessian_ElemDisc.set_lambda_vol(0.2)
+        p.u.from_numpy(0.01 * np.random.default_rng(0).standard_normal(p.u.v.size))
+        DD = p.DeformationEquation_DomainDisc
+        DD.adjust_solution(p.u)
+        DD.assemble_jacobian(p.A_u_Hessian, p.u)
+        p.Lu.from_numpy(np.random.default_rng(5).standard_normal(p.u.v.size), 2)
+        DD.adjust_solution(p.Lu)
+        s = p.SmallProblemRHS_Solver
+        s.desc["convCheck"]["absolute"] = 1e-12
+        s.init(p.A_u_Hessian, p.sigma)
+        assert s.apply(p.sigma, p.Lu)
+        z = p.sigma.to_numpy()
+        s.vcycle(p.delta_u, p.Lu)
+        outs[name] = (z, s.step(), p.delta_u.to_numpy())
+        if name == "numpy":
+            A, b = p.A_u_Hessian.to_scipy(), p.Lu.to_numpy()
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert outs["c1"][1] == outs["numpy"][1]
+    assert rel(outs["c1"][0], outs["numpy"][0]) < 1e-12 and rel(outs["c1"][2], outs["numpy"][2]) < 1e-12
+    assert abs(outs["c3"][1] - outs["numpy"][1]) <= 2 and np.linalg.norm(A @ outs["c3"][0] - b) < 1e-11
