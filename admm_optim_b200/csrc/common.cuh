@@ -46,6 +46,7 @@ struct Context {
     bool use_loop = true;   // ADMM_B200_LOOP: the whole BiCGStab loop as one graph launch (conditional WHILE node, device-side ConvCheck)
     bool use_pdl = true;    // ADMM_B200_PDL: programmatic dependent launch for the V-cycle / BiCGStab kernel chain
     int assembly_variant = 0; // ADMM_B200_ASSEMBLY: 0 = row-owner gather (no atomics, reproducible), 1 / "atomic" = per-element atomic scatter
+    int spmv2d_lanes = 4;   // ADMM_B200_SPMV2D_LANES: lanes per 2x2-block row in the TMA SpMV (4: 8 rows per warp in flight; 8: quarter-warp rows)
     int coarse_variant = 0; // ADMM_B200_COARSE_VARIANT: 0 = shared-memory-resident blocked Gauss-Jordan, 1 = rows in global memory
     // small device scratch for reductions: partial sums + ticket counters + result slots
     double* d_partials = nullptr;   // kMaxBlocks * kMaxVals

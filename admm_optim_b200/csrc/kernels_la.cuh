@@ -386,7 +386,7 @@ struct SpmvTma {
     static constexpr int SMEM_B = 128 + NSTAGE * (STAGE_B + META_B);
 };
 
-template <int D, int MODE, int DOTS, int U>
+template <int D, int MODE, int DOTS, int U, int HL>
 __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, const int* __restrict__ tile_info, const int* __restrict__ rowptr,
                                                                  const int* __restrict__ colidx, const double* __restrict__ vals,
                                                                  const double* x, const double* b,
@@ -489,11 +489,10 @@ __global__ void __launch_bounds__(SpmvTma<D>::NT, 2) k_bsr_spmv_tma(int ntiles, 
         }
     } else {
         // ---------------- consumers ----------------
-        // HL lanes per block row (half-warp for 3x3 blocks, quarter-warp for 2x2 where rows are ~250 bytes), lane <->
-        // (block slot, column c) of the block: one x gather and D value loads (column c of the DxD block, from shared
-        // memory) feed D independent accumulators -- no idle work per entry, no index division; the 32/HL rows of a warp
-        // share every instruction.
-        constexpr int HL = D == 3 ? 16 : 8;            // lanes per row
+        // HL lanes per block row (half-warp for 3x3 blocks; 2x2 blocks, where a row is only ~250 bytes: 4 lanes, i.e. 8 rows
+        // per warp in flight -- the row count in flight, not the issue rate, bounds that case), lane <-> (block slot, column
+        // c) of the block: one x gather and D value loads (column c of the DxD block, from shared memory) feed D independent
+        // accumulators -- no idle work per entry, no index division; the 32/HL rows of a warp share every instruction.
         constexpr int RPW = 32 / HL;                    // rows per warp
         constexpr int BPH = HL / D;                     // blocks per step of a row group (5 for 3x3, 4 for 2x2)
         const int hl = lane % HL, half = lane / HL;

@@ -424,7 +424,7 @@ static void dev_dots(Context* ctx, int64_t n, int nx, const double* const* xs, c
 }
 
 // SpMV family dispatch. mode 0: y=Ax (dots: 0/1/2 with w), 1: y=b-Ax, 2: smoother step
-template <int D, int U>
+template <int D, int U, int HL>
 static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                             const double* dinv, const double* dvec, double* dout, double c1, double c2, const double* w, double* red, const double* cf, int prefetch) {
     using T = SpmvTma<D>;
@@ -436,7 +436,7 @@ static void spmv_tma_launch(Context* ctx, const LevelDev& L, const double* vals,
     if (ctx->l2_hint && L.nnzb * (int64_t)(D * D * 8 + 4) > ((int64_t)48 << 20)) prefetch |= 2;
 #define AB_SPMV(MODE, DOTS)                                                                                                          \
     do {                                                                                                                              \
-        AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch); \
+        AB_LAUNCH_PDL(ctx, (k_bsr_spmv_tma<D, MODE, DOTS, U, HL>), g, T::NT, T::SMEM_B, L.ntiles, L.tile_info.p, L.rowptr.p, L.colidx.p, vals, x, b, y, dinv, dvec, dout, c1, c2, w, ctx->d_partials, ctx->d_tickets, red, cf, prefetch); \
     } while (0)
     if (mode == 0) {
         if (dots == 0) AB_SPMV(0, 0);
@@ -463,18 +463,19 @@ static void spmv_warp_launch(Context* ctx, const LevelDev& L, const double* vals
 }
 // opt in to the large dynamic shared memory of every TMA SpMV instantiation once, up front (not lazily inside a launch
 // that may be under stream capture)
-template <int D, int U>
+template <int D, int U, int HL>
 static void spmv_prepare_dim() {
     using T = SpmvTma<D>;
-    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
-    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 1, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
-    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 2, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
-    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 1, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
-    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 2, 0, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 0, U, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 1, U, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 0, 2, U, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 1, 0, U, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
+    AB_CUDA(cudaFuncSetAttribute(k_bsr_spmv_tma<D, 2, 0, U, HL>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_B));
 }
 static void spmv_prepare_kernels() {
-    spmv_prepare_dim<2, 2>();
-    spmv_prepare_dim<3, 3>();
+    spmv_prepare_dim<2, 4, 4>();
+    spmv_prepare_dim<2, 2, 8>();
+    spmv_prepare_dim<3, 3, 16>();
 }
 static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, int mode, int dots, const double* x, const double* b, double* y,
                  const double* dinv = nullptr, double* dvec = nullptr, double c1 = 0, double c2 = 0, const double* w = nullptr, double* red = nullptr,
@@ -487,8 +488,10 @@ static void spmv(Context* ctx, int dim, const LevelDev& L, const double* vals, i
     const int variant = (ctx->spmv_variant == 0 && L.ntiles == 0) ? 1 : ctx->spmv_variant;
     switch (variant) {
         case 0:
-            if (dim == 2) spmv_tma_launch<2, 2>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
-            else spmv_tma_launch<3, 3>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            // 2x2 blocks: 4 lanes per row (8 rows per warp in flight); tuning key "spmv2d_lanes" = 8 selects the quarter-warp mapping
+            if (dim == 2 && ctx->spmv2d_lanes == 8) spmv_tma_launch<2, 2, 8>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            else if (dim == 2) spmv_tma_launch<2, 4, 4>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
+            else spmv_tma_launch<3, 3, 16>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
             return;
         default:
             if (dim == 2) spmv_warp_launch<2, 1>(ctx, L, vals, mode, dots, x, b, y, dinv, dvec, dout, c1, c2, w, red, cf, prefetch);
@@ -1065,7 +1068,7 @@ static std::vector<const void*> iteration_key(Context* ctx, const double* Av, Gm
     key.push_back(Av);
     key.push_back(G->Ainv.p);
     key.push_back(G->coefs.p);
-    key.push_back((const void*)(intptr_t)(G->n_free * 64 + ctx->tma_small_ctas * 32 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
+    key.push_back((const void*)(intptr_t)(G->n_free * 256 + ctx->spmv2d_lanes * 8 + ctx->tma_small_ctas * 4 + ctx->spmv_variant * 2 + (ctx->use_pdl ? 1 : 0)));
     for (const GmgLevel& g : G->L) { key.push_back(g.vals); key.push_back(g.mask); key.push_back(g.dinv.p); key.push_back(g.x.p); key.push_back(g.r.p); }
     if (G->coarse) {
         key.push_back(G->coarse->Ainv.p);
@@ -1562,6 +1565,7 @@ int ab_context_create(int device, void* stream, ab_context** out) {
     if (const char* v = getenv("ADMM_B200_LOOP")) c->use_loop = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_L2_HINT")) c->l2_hint = atoi(v) != 0;
     if (const char* v = getenv("ADMM_B200_COARSE_VARIANT")) c->coarse_variant = atoi(v);
+    if (const char* v = getenv("ADMM_B200_SPMV2D_LANES")) c->spmv2d_lanes = atoi(v) == 8 ? 8 : 4;
     if (const char* v = getenv("ADMM_B200_ASSEMBLY")) c->assembly_variant = (strcmp(v, "atomic") == 0 || strcmp(v, "1") == 0) ? 1 : 0;
     spmv_prepare_kernels();
     cudaDeviceProp prop;
@@ -1608,6 +1612,7 @@ int ab_context_set_tuning(ab_context* ctx, const char* key, int value) {
     else if (k == "spmv_waves") ctx->spmv_waves = std::max(1, value);
     else if (k == "graph") ctx->use_graph = value != 0;
     else if (k == "coarse_variant") ctx->coarse_variant = value;
+    else if (k == "spmv2d_lanes") ctx->spmv2d_lanes = value == 8 ? 8 : 4;
     else if (k == "assembly_variant") ctx->assembly_variant = value != 0 ? 1 : 0;
     else if (k == "pdl") ctx->use_pdl = value != 0;
     else if (k == "loop") ctx->use_loop = value != 0;

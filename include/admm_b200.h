@@ -48,7 +48,7 @@ int ab_context_synchronize(ab_context* ctx);
 /* number of kernels the library launched since context creation (bench.py's gpu_launches claim) */
 int ab_context_launch_count(ab_context* ctx, int64_t* out);
 /* backend tuning knobs (no reference counterpart): "spmv_variant" 0 (TMA tiles) | 1 (warp per row), "spmv_waves" >= 1,
-   "graph" 0|1 (CUDA-graph replay of the BiCGStab iteration), "loop" 0|1 (whole loop as one graph with a conditional node), "pdl" 0|1 (programmatic dependent launch), "coarse_variant" 0|1, "assembly_variant" 0 (row-owner gather) | 1 (atomic scatter),
+   "graph" 0|1 (CUDA-graph replay of the BiCGStab iteration), "loop" 0|1 (whole loop as one graph with a conditional node), "pdl" 0|1 (programmatic dependent launch), "coarse_variant" 0|1, "spmv2d_lanes" 4|8 (lanes per 2x2-block row), "assembly_variant" 0 (row-owner gather) | 1 (atomic scatter),
    "l2_hint" 0|1, "tma_small_ctas" 1|2 */
 int ab_context_set_tuning(ab_context* ctx, const char* key, int value);
 /* Multi-GPU: one process per GPU (replaces UG4's pcl/MPI layer, `mpirun -np 4 ugshell ...` 3d_admm.lua:25).
