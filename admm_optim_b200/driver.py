@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 
+from . import gnuplot
 from .schur import Matrix
 
 
@@ -60,8 +61,13 @@ DEFAULTS_2D = dict(numRefs=3, admmSteps=1000, sigma_threshold=0.3, scaling=1.0, 
 class ObstacleOptim:
     """Hot-path half of one `ugshell -ex {2d,3d}_admm.lua` session."""
 
-    def __init__(self, ug, dim, verbose=False, solver_verbose=False, **params):
+    def __init__(self, ug, dim, verbose=False, solver_verbose=False, trace_dir=None, newton_output=False, trace_first_row=1, **params):
+        """trace_dir: directory that receives the reference's trace files (__ADMMStats_step_<k>_.txt, and with newton_output --
+        the scripts' -bNewtonOutput -- __NewtonStats_step_<k>_.txt / __NewtonIterations_step_<k>_.txt), written by the same
+        statements at the same places as in the scripts.  trace_first_row: see gnuplot.write_data."""
         self.ug, self.dim, self.verbose, self.solver_verbose = ug, dim, verbose, solver_verbose
+        self.trace_dir, self.newton_output, self.trace_first_row = trace_dir, bool(newton_output), trace_first_row
+        self.sensitivity_callback = None
         self.P = dict(DEFAULTS_3D if dim == 3 else DEFAULTS_2D)
         unknown = set(params) - set(self.P)
         if unknown:
@@ -219,9 +225,22 @@ class ObstacleOptim:
     # ------------------------------------------------------------------------------------------
     # J' enters here (stands for 3d:816-817: Jprime assemble_defect + SetZeroAwayFromSubset)
     # ------------------------------------------------------------------------------------------
-    def set_sensitivity(self, jprime_host):
+    def set_sensitivity(self, jprime_host, scaling=None):
+        """J' as assembled by the UG4/CPU side with Jprime_ElemDisc:set_step_length(scaling) (3d:816-817, 1286-1287)."""
         self.SensitivityGF.from_numpy(jprime_host, 2)      # additive, like assemble_defect output
         self.ug.SetZeroAwayFromSubset(self.SensitivityGF, self.ucmps, "obstacle_surface")
+        self._jprime_host, self._jprime_scaling = jprime_host, (self.P["scaling"] if scaling is None else scaling)
+
+    def refresh_sensitivity(self, scaling):
+        """3d:1286-1288 / 2d:1234-1236: after a fake convergence the scripts re-assemble J' with the doubled step length
+        (Jprime_ElemDisc:set_step_length(scaling); assemble_defect; SetZeroAwayFromSubset).  The Sensitivity ElemDisc lives on the
+        UG4/CPU side (out of scope): `sensitivity_callback(scaling)` asks it for the new host vector; without a callback the stored
+        J' is rescaled, which is what a J' linear in its step length gives."""
+        if self.sensitivity_callback is not None:
+            self.set_sensitivity(self.sensitivity_callback(scaling), scaling)
+        else:
+            import numpy as np
+            self.set_sensitivity(np.asarray(self._jprime_host) * (scaling / self._jprime_scaling), scaling)
 
     def synthetic_sensitivity(self, amplitude=0.5):
         """Deterministic stand-in for the shape derivative J' (no Navier-Stokes here): a smooth normal
@@ -254,6 +273,9 @@ class ObstacleOptim:
         self.p_solver_failure = False
         self.admm_steps = 0
         self.admm_trace = []
+        # 3d:867-873: the tables behind __ADMMStats_step_<k>_.txt, indexed by admm_steps like the Lua tables
+        self.vADMM = {k: {} for k in ("Step", "Scaling", "Sigma", "Udiff", "LambdaInc", "MaxFrobNorm", "SigmaMinusMaxNorm")}
+        self.vNS = None
 
     # ------------------------------------------------------------------------------------------
     # one pass of the ADMM loop body, 3d_admm.lua:876-1303 (2d_admm.lua:869-1252)
@@ -307,6 +329,18 @@ class ObstacleOptim:
         self.admm_trace.append(rec)
         self.log("ADMM LOOP::STEP=%d  MaxNorm=%.12g  u_diff=%.12g  lambda_inc=%.12g  newton its=%d" %
                  (self.admm_steps, self.maximum_norm, u_diff_norm, lambda_inc_norm, len(newton)))
+        # ---- trace tables + file (3d:1265-1276 / 2d:1213-1223) ----
+        if getattr(self, "vADMM", None) is not None:
+            k = self.admm_steps
+            for name, val in (("Step", k), ("Scaling", P["scaling"]), ("Sigma", sigma_threshold), ("Udiff", u_diff_norm), ("LambdaInc", lambda_inc_norm),
+                              ("MaxFrobNorm", self.maximum_norm), ("SigmaMinusMaxNorm", sigma_threshold - self.maximum_norm)):
+                self.vADMM[name][k] = val
+            if self.trace_dir is not None:
+                import os
+                V = self.vADMM
+                gnuplot.write_data(os.path.join(self.trace_dir, "__ADMMStats_step_%d_.txt" % self.step),
+                                   [V["Step"], V["Scaling"], V["Sigma"], V["Udiff"], V["LambdaInc"], V["MaxFrobNorm"], V["SigmaMinusMaxNorm"]],
+                                   False, first_row=self.trace_first_row)
         # ---- convergence check (3d:1279-1302) ----
         tol = P["admm_tolerance"]
         grad_tol = 0.05 if dim == 3 else P["admm_gradient_tolerance"]
@@ -328,7 +362,10 @@ class ObstacleOptim:
         ns_i = 1
         recs = []
         Norm_Lu_0 = Norm_Llambda_0 = 0.0
+        # 3d:923-934: the tables behind __NewtonStats_step_<k>_.txt / __NewtonIterations_step_<k>_.txt (re-created every ADMM iteration)
+        self.vNS = {k: {} for k in ("Step", "NormSum", "NormDeltaUp", "NormDeltaLambda", "Lu2Norm", "RHS", "Large", "Bvol", "Bx", "By", "Bz")}
         while ns_i <= P["nsMaxIts"]:
+            self.vNS["Step"][ns_i] = ns_i                                        # 3d:942
             self.MinusLu_BdeltaLambda.set(0.0); Lu.set(0.0)                      # 3d:944-948
             delta_u.set(0.0); sigma.set(0.0)
             for i in range(m):
@@ -427,6 +464,12 @@ class ObstacleOptim:
                              S=[[self.S[r][c] for c in range(m)] for r in range(m)],
                              its=dict(rhs=self.SmallProblemRHS_Solver.step(), large=self.LargeProblem_Solver.step(),
                                       B=[s.step() for s in self.B_Solver])))
+            V, its_ = self.vNS, recs[-1]["its"]                                  # 3d:1154-1164
+            V["NormDeltaUp"][ns_i - 1] = delta_u_norm_sum; V["NormDeltaLambda"][ns_i - 1] = delta_lambda_norm
+            V["NormSum"][ns_i - 1] = 0.0; V["Lu2Norm"][ns_i - 1] = lu_norm_sum
+            V["RHS"][ns_i - 1] = its_["rhs"]; V["Large"][ns_i - 1] = its_["large"]; V["Bvol"][ns_i - 1] = its_["B"][0]
+            V["Bx"][ns_i - 1] = its_["B"][1]; V["By"][ns_i - 1] = its_["B"][2]
+            if three_d: V["Bz"][ns_i - 1] = its_["B"][3]
             self.log("#   %d DELTA_U INCREMENT NORM IS: %.6e   DELTA_LAMBDA INCREMENT NORM IS: %.6e   |Lu| %.6e  its %s" %
                      (ns_i, delta_u_norm_sum, delta_lambda_norm, lu_norm_sum, recs[-1]["its"]))
             # (8) stop (3d:1198 ; 2d:1163-1166)
@@ -441,15 +484,48 @@ class ObstacleOptim:
                     break
         return recs
 
-    # the surrounding ADMM loop control, 3d:875,1279-1302
+    # the surrounding ADMM loop control, 3d:875,1279-1311 (2d:868,1227-1259)
     def run_admm(self, max_steps=None):
-        """Run the ADMM loop of one optimisation step until convergence / admmSteps / failure. Returns the trace."""
+        """The ADMM loop of one optimisation step: `while admm_steps < admmSteps` with the scripts' exits --
+          * converged (3d:1279)                      -> break ("convergence break case")
+          * fake convergence (3d:1281-1289)          -> scaling *= 2, admm_steps = 0 (then the increment at the end of the body),
+                                                        J' refreshed for the new scaling (refresh_sensitivity), loop goes on
+          * admm_steps == admmSteps (3d:1296-1301)   -> step marked for repetition (p_solver_failure).  In the scripts this test sits
+                                                        inside `while admm_steps < admmSteps` before the increment, so it can never
+                                                        fire; it is kept at the same place for fidelity
+          * solver failure                           -> break
+        followed by the Newton trace files of the LAST ADMM iteration (3d:1307-1311).  Returns the trace."""
         self.begin_step()
         limit = self.P["admmSteps"] if max_steps is None else max_steps
         while self.admm_steps < limit:
-            rec = self.admm_iteration()
+            rec = self.admm_iteration()                                          # increments admm_steps at its end (3d:1302)
             if rec is None:
                 break
-            if rec["converged"] and not rec["fake"]:
+            self.admm_steps -= 1                                                 # ... so step back to where the scripts run their checks
+            if rec["converged"]:
+                if rec["fake"]:
+                    self.P["scaling"] = self.P["scaling"] * 2.0                  # 3d:1284
+                    self.admm_steps = 0                                          # 3d:1285
+                    self.refresh_sensitivity(self.P["scaling"])                  # 3d:1286-1288
+                    self.log("ADMM LOOP::t'was fake convergence, scaling= %g" % self.P["scaling"])
+                else:
+                    self.admm_steps += 1
+                    break
+            if self.admm_steps == limit:                                         # 3d:1296-1301 (unreachable, see above)
+                self.p_solver_failure = True
+                self.admm_steps = 0
                 break
+            self.admm_steps += 1                                                 # 3d:1302
+        self.write_newton_traces()
         return self.admm_trace
+
+    def write_newton_traces(self):
+        """3d:1307-1311: gnuplot.write_data of the Newton tables of the last ADMM iteration (only with -bNewtonOutput true)."""
+        if not (self.newton_output and self.trace_dir is not None and self.vNS):
+            return
+        import os
+        V = self.vNS
+        gnuplot.write_data(os.path.join(self.trace_dir, "__NewtonStats_step_%d_.txt" % self.step),
+                           [V["Step"], V["NormSum"], V["NormDeltaUp"], V["NormDeltaLambda"], V["Lu2Norm"]])
+        gnuplot.write_data(os.path.join(self.trace_dir, "__NewtonIterations_step_%d_.txt" % self.step),
+                           [V["Step"], V["RHS"], V["Bvol"], V["Bx"], V["By"], V["Large"]])

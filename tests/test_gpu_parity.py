@@ -493,3 +493,26 @@ def test_jacobi_smoother_option_matches_oracle(gpu_backend, monkeypatch, dim, gr
         assert s.apply(p.sigma, p.Lu)
         its.append(s.step()); sols.append(p.sigma.to_numpy())
     assert abs(its[0] - its[1]) <= 1 and _rel(sols[0], sols[1]) < 1e-7
+
+
+def test_gpu_trace_files_match_golden(gpu_backend, tmp_path):
+    """The CUDA path writes the reference's trace files through the same driver statements; against the
+    committed golden files of the oracle: iteration-count columns equal, floating-point columns within 1e-8 relative."""
+    import os
+    from conftest import ROOT
+    from admm_optim_b200 import gnuplot
+    from admm_optim_b200.driver import ObstacleOptim
+    p = ObstacleOptim(gpu_backend, 3, numRefs=1, grid=GRID3D, admmSteps=3, trace_dir=str(tmp_path), newton_output=True).setup()
+    p.set_sensitivity(p.synthetic_sensitivity(0.5))
+    p.run_admm()
+    gold = os.path.join(ROOT, "tests", "golden", "traces_3d_refs1")
+    for n in sorted(os.listdir(gold)):
+        a, b = gnuplot.read_data(str(tmp_path / n)), gnuplot.read_data(os.path.join(gold, n))
+        assert len(a) == len(b), n
+        for x, y in zip(a, b):
+            assert len(x) == len(y)
+            for u, v in zip(x, y):
+                if "Iterations" in n:
+                    assert abs(u - v) <= 1, (n, x, y)               # BiCGStab counts: +-1 (summation order near the tolerance)
+                else:
+                    assert abs(u - v) <= 1e-8 * max(abs(v), 1e-3) or abs(v) < 1e-9, (n, u, v)

@@ -265,3 +265,76 @@ def test_bench_algorithmic_byte_formulas_match_survey():
     l2 = bench.global_counts(3, 2)
     assert l2[3] == (9008, 9008 + 2 * 26672)
     assert abs(bench.spmv_bytes(2, *l2[3]) / 2.57e6 - 1) < 0.01
+
+
+def test_gnuplot_write_data_restates_lua_semantics(tmp_path):
+    """gnuplot.write_data as the scripts use it (3d_admm.lua:1274): columns = Lua tables, rows from index 1 up to the first gap,
+    Lua 5.1 number formatting (%.14g), blank-separated."""
+    from admm_optim_b200 import gnuplot
+    f = str(tmp_path / "t.txt")
+    step = {0: 0, 1: 1, 2: 2}                 # filled at index admm_steps = 0, 1, 2 like vADMM_Step
+    val = {0: 0.5, 1: 1.0 / 3.0, 2: 1e-13}
+    assert gnuplot.write_data(f, [step, val], False) == 2            # index 0 is not in the array part of a Lua table
+    assert open(f).read() == "1 0.33333333333333 \n2 1e-13 \n"
+    assert gnuplot.write_data(f, [step, val], False, first_row=0) == 3
+    assert gnuplot.read_data(f) == [[0.0, 0.5], [1.0, 0.33333333333333], [2.0, 1e-13]]
+    assert gnuplot.write_data(f, [[1, 2, 3], [4.0, 5.5]]) == 2       # the shortest column ends the table
+    assert gnuplot.lua_number(3.0) == "3" and gnuplot.lua_number(0.1 + 0.2) == "0.3" and gnuplot.lua_number(123456789012345678.0) == "1.2345678901235e+17"
+
+
+def test_trace_files_match_committed_golden(tmp_path):
+    """The driver replay writes __ADMMStats_step_<k>_.txt / __NewtonStats_... / __NewtonIterations_... (3d_admm.lua:1274-1276,
+    1307-1311) at the scripts' places; on the oracle backend the files must reproduce tests/golden/traces_3d_refs1
+    (tools/make_golden.py traces): integer columns exactly, floating-point columns to 1e-9 relative."""
+    from admm_optim_b200 import gnuplot
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    p = ObstacleOptim(ug4_np.Backend(smoother="cheb"), 3, numRefs=1, grid=GRID3D, admmSteps=3, trace_dir=str(tmp_path), newton_output=True).setup()
+    p.set_sensitivity(p.synthetic_sensitivity(0.5))
+    p.run_admm()
+    gold = os.path.join(ROOT, "tests", "golden", "traces_3d_refs1")
+    names = sorted(os.listdir(gold))
+    assert names == ["__ADMMStats_step_0_.txt", "__NewtonIterations_step_0_.txt", "__NewtonStats_step_0_.txt"] and sorted(os.listdir(tmp_path)) == names
+    for n in names:
+        a, b = gnuplot.read_data(str(tmp_path / n)), gnuplot.read_data(os.path.join(gold, n))
+        assert len(a) == len(b) and all(len(x) == len(y) for x, y in zip(a, b)), n
+        for x, y in zip(a, b):
+            for u, v in zip(x, y):
+                assert abs(u - v) <= 1e-9 * max(abs(v), 1e-6), (n, u, v)
+    assert open(os.path.join(gold, "__NewtonIterations_step_0_.txt")).read() == open(str(tmp_path / "__NewtonIterations_step_0_.txt")).read()
+    ncols = {"__ADMMStats_step_0_.txt": 7, "__NewtonStats_step_0_.txt": 5, "__NewtonIterations_step_0_.txt": 6}     # SURVEY Appendix D
+    for n in names:
+        assert all(len(r) == ncols[n] for r in gnuplot.read_data(os.path.join(gold, n)))
+
+
+def test_admm_loop_control_branches():
+    """run_admm restates the loop control of 3d_admm.lua:875,1279-1302: a fake convergence doubles `scaling`, resets admm_steps
+    and asks for a new J' (callback standing for the Sensitivity re-assembly of 3d:1286-1288); a true convergence breaks."""
+    from admm_optim_b200.driver import ObstacleOptim
+
+    class Stub(ObstacleOptim):
+        def __init__(self, recs):
+            self.P = dict(admmSteps=10, scaling=1.0)
+            self.recs, self.calls, self.asked = list(recs), [], []
+            self.newton_output, self.trace_dir, self.vNS, self.verbose = False, None, None, False
+            self.sensitivity_callback = lambda sc: self.asked.append(sc) or [0.0]
+        def begin_step(self):
+            self.admm_steps, self.admm_trace, self.p_solver_failure = 0, [], False
+        def set_sensitivity(self, j, scaling=None):
+            self.calls.append(scaling)
+        def admm_iteration(self):
+            r = self.recs.pop(0)
+            if r is not None:
+                self.admm_trace.append((self.admm_steps, r))
+                self.admm_steps += 1
+            return r
+
+    no = dict(converged=False, fake=False)
+    s = Stub([no, dict(converged=True, fake=True), no, dict(converged=True, fake=False), no])
+    tr = s.run_admm()
+    assert [k for k, _ in tr] == [0, 1, 1, 2]          # after the fake convergence: admm_steps = 0, then the increment at the end of the body
+    assert s.P["scaling"] == 2.0 and s.asked == [2.0] and s.calls == [2.0] and len(s.recs) == 1 and not s.p_solver_failure
+    s = Stub([no] * 12)
+    assert len(s.run_admm()) == 10 and not s.p_solver_failure     # `while admm_steps < admmSteps`: ends without marking the step
+    s = Stub([no, None])
+    assert len(s.run_admm()) == 1                                   # solver failure: break

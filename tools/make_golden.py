@@ -39,3 +39,17 @@ for name, (dim, grid, refs) in CASES.items():
     path = os.path.join(ROOT, "tests", "golden", "admm_trace_%s.json" % name)
     json.dump(out, open(path, "w"), indent=1)
     print(path, out["admm"][0]["u_diff"], out["admm"][1]["u_diff"])
+
+
+# ---- trace files in the reference's format, written by the driver replay on the oracle ----------------
+# tests/test_host.py::test_trace_files_match_committed_golden replays this on the CPU and diffs the files byte for byte.
+if not only or "traces" in only:
+    import shutil
+    d = os.path.join(ROOT, "tests", "golden", "traces_3d_refs1")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    p = ObstacleOptim(ug4_np.Backend(smoother="cheb"), 3, numRefs=1, grid=os.path.join(ROOT, "grids", "box_3D_elongated.npz"), admmSteps=3,
+                      trace_dir=d, newton_output=True).setup()
+    p.set_sensitivity(p.synthetic_sensitivity(0.5))
+    p.run_admm()
+    print(d, sorted(os.listdir(d)))
