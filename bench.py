@@ -183,13 +183,43 @@ def oracle_problem(refs, threads=None):
     return p
 
 
+def pick_threads(refs):
+    """The thread count a CPU user would run with: one solver:init + solver:apply of the workload timed on all cores, half, a
+    quarter ... one; the fastest wins (hyper-threads and neighbours on a shared host make 'all' not always the best)."""
+    import numpy as np
+    cores = cpu_cores()
+    cands = sorted({max(1, cores >> k) for k in range(0, 5)} | {1}, reverse=True)
+    p = oracle_problem(refs, cores)
+    DD = p.DeformationEquation_DomainDisc
+    DD.assemble_jacobian(p.A_u_Hessian, p.u)
+    p.Lu.from_numpy(np.random.default_rng(5).standard_normal(p.u.v.size), 2)
+    DD.adjust_solution(p.Lu)
+    s = p.SmallProblemRHS_Solver
+    timings = {}
+    for t in cands:
+        p.ug.threads = t
+        best = 1e30
+        for _ in range(2):
+            p.sigma.set(0.0)
+            t0 = time.perf_counter()
+            s.init(p.A_u_Hessian, p.sigma)
+            s.apply(p.sigma, p.Lu)
+            best = min(best, time.perf_counter() - t0)
+        timings[t] = best
+    return min(timings, key=timings.get), timings
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the OpenMP runtime must spin between the (many, short) parallel regions of the solve: with the default passive policy the
+    # wake-ups cost more than the sweeps.  Set before the OpenMP runtime is loaded (this arm never imports torch).
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
     import numpy as np  # noqa: F401
     cores = cpu_cores()
-    p = oracle_problem(args.refs, cores)
+    threads, calib = (args.threads, {}) if args.threads > 0 else pick_threads(args.refs)
+    p = oracle_problem(args.refs, threads)
     for _ in range(args.warmup):
         p.admm_iteration()
     t0 = time.perf_counter()
@@ -204,35 +234,33 @@ def run_reference(args):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, global_counts(args.refs)[-1][0] * 3),
-                       "numRefs": args.refs, "dofs": global_counts(args.refs)[-1][0] * 3, "note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % cores,
-                       "host_cores_available": cores, "bicgstab_its_per_step": its / args.steps},
-            "cpu_baseline": {"value": v, "unit": "iters/s", "cores": cores, "kind": "port",
-                             "sample": "%d full ADMM iterations of the same workload (C/OpenMP solve path + C assembly on %d threads, NumPy vector algebra)" % (args.steps, cores)},
+                       "numRefs": args.refs, "dofs": global_counts(args.refs)[-1][0] * 3, "note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % threads,
+                       "host_cores_available": cores, "threads_used": threads,
+                       "thread_calibration_s": {str(k): round(x, 4) for k, x in calib.items()}, "bicgstab_its_per_step": its / args.steps},
+            "cpu_baseline": {"value": v, "unit": "iters/s", "cores": threads, "kind": "port", "host_cores_available": cores,
+                             "sample": "%d full ADMM iterations of the same workload (C/OpenMP solve path + C assembly, NumPy vector algebra) on %d of %d host "
+                                       "threads -- the fastest count of a calibration over all / half / quarter ... / one" % (args.steps, threads, cores)},
             "e2e": {"value": v, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def cpu_baseline_sample(refs):
-    cores = cpu_cores()
+    """cpu_baseline of the B200 line: the reference arm in a child process (its OpenMP runtime needs its own wait policy; this
+    process has torch's runtime loaded), two timed iterations on the calibrated thread count and one on a single thread."""
     out = {}
-    for label, threads in (("all", cores), ("one", 1)):
-        p = oracle_problem(refs, threads)
-        p.admm_iteration()                                            # first iteration: static solver data, C library load
-        t0 = time.perf_counter()
-        rec = p.admm_iteration()
-        dt = time.perf_counter() - t0
-        assert rec is not None
-        out[label] = (1.0 / dt, rec)
-    v, rec = out["all"]
-    return {"value": v, "unit": "iters/s", "cores": cores, "kind": "port", "host_cores_available": cores,
-            "value_1_thread": out["one"][0],
-            "sample": "1 ADMM iteration (second of the loop, %d Newton its) of the same workload: CPU port with the C/OpenMP solve path "
-                      "(RAP, V(3,3) Gauss-Seidel GMG, dense-LU base solve, BiCGStab) and C assembly on %d threads; value_1_thread = the same on one thread "
-                      "(sequential lexicographic Gauss-Seidel)" % (len(rec["newton"]), cores),
-            "note": CPU_NOTE,
-            "newton_iterations": len(rec["newton"]),
-            "bicgstab_iterations_first_newton": rec["newton"][0]["its"],
-            "bicgstab_iterations_first_newton_1_thread": out["one"][1]["newton"][0]["its"]}
+    for label, extra in (("best", []), ("one", ["--threads", "1"])):
+        env = dict(os.environ, OMP_WAIT_POLICY="active")
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1", "--refs", str(refs)] + extra,
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[label] = json.loads(r.stdout.strip().splitlines()[-1])
+    b = out["best"]
+    cb = dict(b["cpu_baseline"])
+    cb.update({"value_1_thread": out["one"]["value"], "note": CPU_NOTE, "thread_calibration_s": b["config"]["thread_calibration_s"],
+               "bicgstab_its_per_step": b["config"]["bicgstab_its_per_step"], "bicgstab_its_per_step_1_thread": out["one"]["config"]["bicgstab_its_per_step"]})
+    return cb
 
 
 # ------------------------------------------------------------------------------------------------
@@ -541,6 +569,7 @@ def main():
     ap.add_argument("--roofline-refs", type=int, default=5, help="refinement level of the SpMV / V-cycle / solve roofline leg (0 = skip); 5 = 20.3 M DoFs, 7.6 GB matrix")
     ap.add_argument("--admm-refs", type=int, default=4, help="refinement of the larger 3D ADMM-iteration leg (BASELINE.json configs[2]: numRefs 4); 0 = skip")
     ap.add_argument("--dim2-refs", type=int, default=7, help="refinement of the 2D leg (BASELINE.json configs[3]: refined.ugx numRefs 7); 0 = skip")
+    ap.add_argument("--threads", type=int, default=0, help="reference arm: host threads (0 = calibrate: all / half / ... / one, fastest wins)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

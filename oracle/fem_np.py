@@ -326,6 +326,9 @@ def c_kernels():
             lib.oracle_spmv.argtypes = [_C.c_int, ip, ip, dp, dp, dp, _C.c_int]
             lib.oracle_spmv.restype = None
             lib.oracle_max_threads.restype = _C.c_int
+            if hasattr(lib, "oracle_set_elem_threads"):
+                lib.oracle_set_elem_threads.argtypes = [_C.c_int]
+                lib.oracle_set_elem_threads.restype = None
             if hasattr(lib, "oracle_hessian_scatter"):
                 llp = _C.POINTER(_C.c_longlong)
                 lib.oracle_hessian_scatter.argtypes = [_C.c_int, _C.c_long, ip, dp, dp, _C.c_double, _C.c_double, dp, llp, dp]

@@ -35,8 +35,12 @@ void oracle_gs_forward(int n, const int* ip, const int* idx, const double* a, co
             double s = b[i], d = 1.0;
             for (int k = ip[i]; k < ip[i + 1]; ++k) {
                 const int j = idx[k];
-                if (j == i) d = a[k];
-                else s -= a[k] * ((j >= lo && j < hi) ? x[j] : xold[j]);
+                /* both loads are issued, the select is branch-free (an unpredictable branch per entry costs more than the sweep) */
+                const double xo = xold[j], xn = x[j];
+                const double xv = ((unsigned)(j - lo) < (unsigned)(hi - lo)) ? xn : xo;
+                const double av = a[k];
+                d = (j == i) ? av : d;
+                s -= (j == i) ? 0.0 : av * xv;
             }
             x[i] = s / d;
         }
@@ -51,6 +55,10 @@ void oracle_spmv(int n, const int* ip, const int* idx, const double* a, const do
         y[i] = s;
     }
 }
+
+/* threads of the element loops below (bench.py's CPU legs set it; default 1 = the deterministic serial scatter the tests pin) */
+static int g_elem_threads = 1;
+void oracle_set_elem_threads(int t) { g_elem_threads = t > 0 ? t : 1; }
 
 int oracle_max_threads(void) {
 #ifdef _OPENMP
@@ -121,6 +129,7 @@ void oracle_hessian_scatter(int d, long ne, const int* elems, const double* xyz,
                             const double* lam_b, const long long* slot, double* data) {
     const int nd = (d + 1) * d;
     const int has_lam = lam_vol != 0.0 || lam_b[0] != 0.0 || lam_b[1] != 0.0 || (d == 3 && lam_b[2] != 0.0);
+#pragma omp parallel for schedule(static) num_threads(g_elem_threads)
     for (long e = 0; e < ne; ++e) {
         double X[12], U[12], G[12], F[9], C[9], K[144], vol;
         for (int a = 0; a <= d; ++a) {
@@ -175,7 +184,17 @@ void oracle_hessian_scatter(int d, long ne, const int* elems, const double* xyz,
                 }
         }
         const long long* sl = slot + (long long)e * nd * nd;
-        for (int k = 0; k < nd * nd; ++k) data[sl[k]] += vol * K[k];
+        if (g_elem_threads == 1) {
+            for (int k = 0; k < nd * nd; ++k) data[sl[k]] += vol * K[k];
+        } else {
+            for (int k = 0; k < nd * nd; ++k) {
+                const double v = vol * K[k];
+                if (v != 0.0) {
+#pragma omp atomic
+                    data[sl[k]] += v;
+                }
+            }
+        }
     }
 }
 
@@ -183,6 +202,7 @@ void oracle_hessian_scatter(int d, long ne, const int* elems, const double* xyz,
  *   out[(v_a, i)] += sign vol ( ((S + wc C) G_a)_i + w_i det F / (d+1) ),  wc = w_0 + sum_k w_k (xbar_k + ubar_k) */
 void oracle_load_scatter(int d, long ne, const int* elems, const double* xyz, const double* u, const double* lam, const double* q, double tau,
                          int use_S, const double* w, int has_w, double sign, double* out) {
+#pragma omp parallel for schedule(static) num_threads(g_elem_threads)
     for (long e = 0; e < ne; ++e) {
         double X[12], U[12], G[12], F[9], C[9], M[9], vol;
         for (int a = 0; a <= d; ++a) {
@@ -216,7 +236,12 @@ void oracle_load_scatter(int d, long ne, const int* elems, const double* xyz, co
             for (int i = 0; i < d; ++i) {
                 double s = add[i];
                 for (int j = 0; j < d; ++j) s += M[i * d + j] * G[a * d + j];
-                out[v * d + i] += sign * vol * s;
+                const double val = sign * vol * s;
+                if (g_elem_threads == 1) out[v * d + i] += val;
+                else {
+#pragma omp atomic
+                    out[v * d + i] += val;
+                }
             }
         }
     }

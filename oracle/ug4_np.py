@@ -364,6 +364,8 @@ class Backend:
         self.smoother, self.cheb_ratio, self.threads = smoother, cheb_ratio, threads
         self.fast_assembly = bool(fast_assembly)
         self.c_solver = bool(c_solver)
+        if self.fast_assembly and self.c_solver and F.c_kernels() is not None and hasattr(F.c_kernels(), "oracle_set_elem_threads"):
+            F.c_kernels().oracle_set_elem_threads(int(threads))     # CPU-baseline mode: the element loops run on the same threads
         self._gmg_cache = {}
         self._asm_cache = {}
         self.util = _NS()
