@@ -338,3 +338,56 @@ def test_admm_loop_control_branches():
     assert len(s.run_admm()) == 10 and not s.p_solver_failure     # `while admm_steps < admmSteps`: ends without marking the step
     s = Stub([no, None])
     assert len(s.run_admm()) == 1                                   # solver failure: break
+
+
+# Lua-visible names the reference's hot path needs from the replaced plugins / from the solver glue, with the call sites they were
+# taken from (checked against /root/reference when it is present, see the test below)
+SHIM_ELEMDISC_CLASSES = ["DeformationEquation", "DeformationEquationRHS", "DeformationEquationLargeProblemRHS",     # 3d:393,407,472
+                         "VolumeConstraintSecondDerivative", "SecondDerivativeVolume", "SecondDerivativeBarycenter",     # 3d:559, 2d:564, 3d:577
+                         "XBarycenterConstraintSecondDerivative", "MassModel", "LambdaUpdate"]                         # 3d:616,652,677
+SHIM_FREE_FUNCTIONS = ["Testing", "ProjectWithSpectralNorm", "MaximumFrobeniusNorm", "MaxSpectralNorm", "VolumeDefect", "BarycenterDefect",
+                       "SetZeroAwayFromSubset", "TransformDomainByDisplacement"]                                       # 3d:910,916,1167,1168,817,1333; 2d:901-902
+SHIM_GMG_SETTERS = ["set_base_level", "set_base_solver", "set_gathered_base_solver_if_ambiguous", "set_smoother", "set_cycle_type",
+                    "set_num_presmooth", "set_num_postsmooth", "set_rap", "set_discretization"]                        # obstacle_optim_3d_util.lua:159-172
+
+
+def test_ug4_plugin_shim_registers_the_names_the_scripts_call(tmp_path):
+    """plugins/ADMMOptimB200/admm_b200_plugin.cpp (the UG4 registry shim over the C ABI) compiles against the stand-in of UG4's
+    bridge header, links against libadmm_b200.so, and its InitUGPlugin_ADMMOptimB200 registers every ElemDisc class with every
+    setter the drivers call on it, every plugin free function and the GMG / BiCGStab / CG surface of the solver glue."""
+    import json
+    import re
+    import shutil
+    if not shutil.which("g++"):
+        pytest.skip("no C++ compiler")
+    lib_dir = os.path.join(ROOT, "admm_optim_b200")
+    if not os.path.exists(os.path.join(lib_dir, "libadmm_b200.so")):
+        pytest.skip("libadmm_b200.so not built")
+    exe = str(tmp_path / "shim_test")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "ug4_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "plugins", "ADMMOptimB200", "admm_b200_plugin.cpp"), os.path.join(ROOT, "tests", "ug4_stub", "shim_main.cpp"),
+                        "-o", exe, "-L" + lib_dir, "-l:libadmm_b200.so", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    reg = json.loads(out.stdout)
+    classes, functions = reg["classes"], set(reg["functions"])
+    assert set(SHIM_ELEMDISC_CLASSES) <= set(classes) and all(classes[c]["constructors"] >= 1 for c in SHIM_ELEMDISC_CLASSES)
+    assert set(SHIM_FREE_FUNCTIONS) <= functions
+    assert set(SHIM_GMG_SETTERS) <= set(classes["B200GeometricMultiGrid"]["methods"])
+    assert {"init", "apply", "apply_return_defect", "step", "set_convergence_check"} <= set(classes["B200LinearSolver"]["methods"])
+    assert "set_preconditioner" in classes["B200BiCGStab"]["methods"] and "set_preconditioner" in classes["B200CG"]["methods"]
+    assert {"set", "has_storage_type_additive", "change_storage_type_to_consistent"} <= set(classes["B200GridFunction"]["methods"])
+    assert {"add", "assemble_jacobian", "assemble_defect", "adjust_solution"} <= set(classes["B200DomainDiscretization"]["methods"])
+    assert {"B200VecProd", "B200VecScaleAssign", "B200VecScaleAdd2", "B200VecNorm", "B200L2Norm", "B200LoadDomain", "B200CreateRegularHierarchy"} <= functions
+    setters = set(classes["B200ElemDisc"]["methods"])
+    ref = "/root/reference"
+    if os.path.isdir(ref):          # every method the unchanged drivers call on a hot-path ElemDisc object is registered
+        called = set()
+        pat = re.compile(r"(?:DeformationEquation\w*_ElemDisc|BVolume_ElemDisc|[XYZ]Barycenter_ElemDisc|MassModel_ElemDisc|LambdaUpdate_ElemDisc):(\w+)")
+        for f in ("3d_admm.lua", "2d_admm.lua"):
+            called |= set(pat.findall(open(os.path.join(ref, f)).read()))
+        assert len(called) > 40 and called <= setters, sorted(called - setters)
+        src = open(os.path.join(ref, "3d_admm.lua")).read()
+        for name in SHIM_ELEMDISC_CLASSES + SHIM_FREE_FUNCTIONS:
+            assert re.search(r"\b%s\(" % name, src) or re.search(r"\b%s\(" % name, open(os.path.join(ref, "2d_admm.lua")).read()), name
