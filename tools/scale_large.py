@@ -50,7 +50,13 @@ if mode == "solver":
     out["setup_s"] = maxtime(time.time() - t0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); e0.record(stream); DD.assemble_jacobian(A, u); e1.record(stream); e1.synchronize()
-    out["assemble_ms"] = maxtime(e0.elapsed_time(e1))
+    out["assemble_first_ms"] = maxtime(e0.elapsed_time(e1))           # includes the allocation of the matrix
+    if bench.global_counts(refs, dim)[-1][1] * 8 * dim * dim * 2 / world < 90e9:      # room for a second copy of the matrix
+        os.environ["ADMM_B200_NO_CACHE"] = "1"
+        DD.assemble_jacobian(A, u)                                    # un-shares the operator from the signature cache (new allocation)
+        barrier(); e0.record(stream); DD.assemble_jacobian(A, u); e1.record(stream); e1.synchronize()   # in place: the kernels alone
+        del os.environ["ADMM_B200_NO_CACHE"]
+        out["assemble_ms"] = maxtime(e0.elapsed_time(e1))
     n_loc = DS.num_dofs()
     x.from_numpy(np.random.default_rng(1 + rank).standard_normal(n_loc)); DD.adjust_solution(x)
     def timeit(fn, reps):
@@ -67,7 +73,10 @@ if mode == "solver":
                spmv_frac_per_gpu=bench.spmv_bytes(dim, nb, nnzb) / t_spmv / 1e6 / peak / world)
     s = linear_solver(ug, DD, DS, False, dim)
     s.desc.verbose = 0
+    te = time.time(); s.init(A, x); ug.synchronize(); out["gmg_init_first_ms"] = maxtime((time.time() - te) * 1e3)
+    os.environ["ADMM_B200_NO_CACHE"] = "1"; s.init(A, x); ug.synchronize(); barrier()      # second hierarchy; the first becomes idle and is recycled next
     te = time.time(); s.init(A, x); ug.synchronize(); out["gmg_init_ms"] = maxtime((time.time() - te) * 1e3)
+    del os.environ["ADMM_B200_NO_CACHE"]
     t_v = timeit(lambda: s.vcycle(y, x), 5)
     bv = bench.vcycle_bytes(dim, levels)
     out.update(vcycle_ms=t_v, vcycle_gbs=bv / t_v / 1e6, vcycle_frac=bv / t_v / 1e6 / peak / world)
