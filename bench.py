@@ -442,10 +442,9 @@ def run_b200(args):
         A = ug.AssembledLinearOperator(DD)
         xv, bvec, yv, uv = (ug.GridFunction(DS) for _ in range(4))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        os.environ["ADMM_B200_NO_CACHE"] = "1"                    # no operator sharing: the repeated request re-assembles in place
         DD.assemble_jacobian(A, uv)                               # cold call (first launch of the kernel, allocation of the matrix)
-        os.environ["ADMM_B200_NO_CACHE"] = "1"                    # the signature cache would answer the repeated request
-        DD.assemble_jacobian(A, uv)                               # un-shares the operator from the cache (a new allocation)
-        barrier(); e0.record(stream); DD.assemble_jacobian(A, uv); e1.record(stream); e1.synchronize()   # in place: the kernels alone
+        barrier(); e0.record(stream); DD.assemble_jacobian(A, uv); e1.record(stream); e1.synchronize()   # the kernels alone
         del os.environ["ADMM_B200_NO_CACHE"]
         t_asm = maxtime(e0.elapsed_time(e1) * 1e-3)
         levels = global_counts(args.roofline_refs)

@@ -49,14 +49,12 @@ if mode == "solver":
     x, b, y, u = (ug.GridFunction(DS) for _ in range(4))
     out["setup_s"] = maxtime(time.time() - t0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    os.environ["ADMM_B200_NO_CACHE"] = "1"                            # no operator sharing: the second request re-assembles in place
     barrier(); e0.record(stream); DD.assemble_jacobian(A, u); e1.record(stream); e1.synchronize()
     out["assemble_first_ms"] = maxtime(e0.elapsed_time(e1))           # includes the allocation of the matrix
-    if bench.global_counts(refs, dim)[-1][1] * 8 * dim * dim * 2 / world < 90e9:      # room for a second copy of the matrix
-        os.environ["ADMM_B200_NO_CACHE"] = "1"
-        DD.assemble_jacobian(A, u)                                    # un-shares the operator from the signature cache (new allocation)
-        barrier(); e0.record(stream); DD.assemble_jacobian(A, u); e1.record(stream); e1.synchronize()   # in place: the kernels alone
-        del os.environ["ADMM_B200_NO_CACHE"]
-        out["assemble_ms"] = maxtime(e0.elapsed_time(e1))
+    barrier(); e0.record(stream); DD.assemble_jacobian(A, u); e1.record(stream); e1.synchronize()   # the kernels alone
+    out["assemble_ms"] = maxtime(e0.elapsed_time(e1))
+    del os.environ["ADMM_B200_NO_CACHE"]
     n_loc = DS.num_dofs()
     x.from_numpy(np.random.default_rng(1 + rank).standard_normal(n_loc)); DD.adjust_solution(x)
     def timeit(fn, reps):
