@@ -273,9 +273,10 @@ static void smooth_exchange_p2p(Domain* dom, int level, int D, const double* cf,
     if (I.total == 0) return;
     launch_xchg(dom, I, D, true, dout, cf, din, xin, xout);
 }
-// global sum / max of device scalars (no-op on one GPU)
-static void allreduce_dev(Context* ctx, double* d, int n, bool max_op = false) {
-    if (ctx->comm && ctx->comm->nranks > 1) ctx->comm->allreduce(d, n, max_op, ctx->stream);
+// global sum / max of device scalars over the ranks that hold the parts of a DECOMPOSED domain (no-op on one GPU and for an
+// undivided domain on a multi-rank context: there every rank already holds the whole value)
+static void allreduce_dev(Domain* dom, double* d, int n, bool max_op = false) {
+    if (dom->distributed()) dom->ctx->comm->allreduce(d, n, max_op, dom->ctx->stream);
 }
 
 struct Space {
@@ -668,7 +669,7 @@ static void gmg_setup_kernels(Gmg& G) {
         }
     }
     if (dist) {
-        if (top > base) allreduce_dev(ctx, ctx->d_results + base + 1, top - base, true);
+        if (top > base) allreduce_dev(dom, ctx->d_results + base + 1, top - base, true);
         AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
         TraceTimer tt(ctx->stream, "gmg: gather + coarse setup");
         gmg_gather_operator<D>(G);
@@ -995,7 +996,7 @@ static void dot_owned(Domain* dom, int64_t n, const double* x0, const double* x1
     const unsigned char* owned = dom->iface[dom->top()].owned.p;
     if (nx == 1) AB_LAUNCH(ctx, (k_dot_owned<1>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x0, y, ctx->d_partials, ctx->d_tickets, out);
     else AB_LAUNCH(ctx, (k_dot_owned<2>), red_grid(ctx, n), 256, 0, n, dom->dim(), owned, x0, x1, y, ctx->d_partials, ctx->d_tickets, out);
-    allreduce_dev(ctx, out, nx);
+    allreduce_dev(dom, out, nx);
 }
 static void to_unique(Domain* dom, int64_t n, const double* src, double* dst) {
     dev_copy(dom->ctx, n, src, dst);
@@ -1050,7 +1051,7 @@ static void bicg_iteration(Domain* dom, const double* Av, Gmg* G, KrylovWs& W, i
     if (dist) {      // owner-masked local sums, one all-reduce, then the scalar bookkeeping
         AB_LAUNCH_PDL(ctx, k_bicg_xr<0>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
                       ctx->d_tickets, W.out2.p, 0ull, (double*)nullptr, (double*)nullptr, 0, owned, dim);
-        allreduce_dev(ctx, W.out2.p, 2);
+        allreduce_dev(dom, W.out2.p, 2);
         AB_LAUNCH(ctx, k_bicg_roll, 1, 1, 0, sc, W.out2.p);
     } else if (in_loop) {       // body of the conditional WHILE node: the ConvCheck runs on the device, nothing goes to the host
         AB_LAUNCH_PDL(ctx, k_bicg_xr<2>, red_grid(ctx, n), 256, 0, n, sc, W.ph.p, W.sh.p, W.s.p, W.t.p, W.rh.p, W.x.p, W.r.p, ctx->d_partials,
@@ -1232,7 +1233,7 @@ static bool bicgstab_apply(Solver* S, Vector* x, Vector* b, bool return_defect) 
     AB_LAUNCH(ctx, k_bicg_init, red_grid(ctx, n), 256, 0, n, x->d.p, W.x.p, W.r.p, W.rh.p, W.p.p, W.v.p, sc, ctx->d_partials, ctx->d_tickets, W.out2.p,
               W.ctl.p, tol2, S->desc.red_tol > 0 ? S->desc.red_tol * S->desc.red_tol : 0.0, S->desc.max_iterations, owned, dim);
     if (dist) {
-        allreduce_dev(ctx, W.out2.p, 1);
+        allreduce_dev(dom, W.out2.p, 1);
         AB_LAUNCH(ctx, k_bicg_init_fix, 1, 1, 0, sc, W.ctl.p, W.out2.p);
     }
     read_back(ctx, sc, SC_COUNT, h);
@@ -1305,7 +1306,7 @@ static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect)
     const double tol2 = S->desc.abs_tol * S->desc.abs_tol;
     double h[SC_COUNT];
     AB_LAUNCH(ctx, k_cg_init, red_grid(ctx, n), 256, 0, n, S->damp, diag, b->d.p, x->d.p, r, z, p, ctx->d_partials, ctx->d_tickets, S->out2.p);
-    allreduce_dev(ctx, S->out2.p, 2);      // P0 dofs are element-local: plain sums over ranks
+    allreduce_dev(S->sp->dom, S->out2.p, 2);      // P0 dofs are element-local: plain sums over ranks
     AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
     read_back(ctx, sc, SC_COUNT, h);
     double rr = h[SC_RR];
@@ -1316,9 +1317,9 @@ static bool cg_jacobi_apply(Solver* S, Vector* x, Vector* b, bool return_defect)
     while (!ok && it < S->desc.max_iterations) {
         ++it;
         AB_LAUNCH(ctx, k_diag_apply_dot, red_grid(ctx, n), 256, 0, n, diag, p, q, ctx->d_partials, ctx->d_tickets, sc + SC_PQ);
-        allreduce_dev(ctx, sc + SC_PQ, 1);
+        allreduce_dev(S->sp->dom, sc + SC_PQ, 1);
         AB_LAUNCH(ctx, k_cg_step, red_grid(ctx, n), 256, 0, n, S->damp, sc, diag, p, q, x->d.p, r, z, ctx->d_partials, ctx->d_tickets, S->out2.p);
-        allreduce_dev(ctx, S->out2.p, 2);
+        allreduce_dev(S->sp->dom, S->out2.p, 2);
         AB_LAUNCH(ctx, k_cg_roll, 1, 1, 0, sc, S->out2.p);
         AB_LAUNCH(ctx, k_cg_p, ew_grid(ctx, n), 256, 0, n, sc, z, p);
         read_back(ctx, sc, SC_COUNT, h);
@@ -2096,7 +2097,7 @@ int ab_vec_prod_multi(int n, ab_vector* const* xs, ab_vector* y, double* out) {
         }
         AB_CUDA(cudaStreamSynchronize(ctx->stream));   // tmp is released below
     }
-    allreduce_dev(ctx, ctx->d_results, n);
+    allreduce_dev(dom, ctx->d_results, n);
     read_back(ctx, ctx->d_results, n, out);
     AB_CATCH
 }
@@ -2155,7 +2156,7 @@ int ab_l2norm_all(ab_vector* v, double* out) {
         if (dim == 2) AB_LAUNCH(ctx, (k_l2norm_p0<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
         else AB_LAUNCH(ctx, (k_l2norm_p0<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, v->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     }
-    allreduce_dev(ctx, ctx->d_results, nc);
+    allreduce_dev(dom, ctx->d_results, nc);
     read_back(ctx, ctx->d_results, nc, out);
     for (int i = 0; i < nc; ++i) out[i] = std::sqrt(out[i]);
     AB_CATCH
@@ -2442,7 +2443,7 @@ static int max_norm_impl(ab_vector* u, double* out, bool spectral) {
         AB_REQUIRE(!spectral, AB_ERR_UNSUPPORTED, "MaxSpectralNorm exists for 2D only (2d_admm.lua:901)");
         AB_LAUNCH(ctx, (k_max_grad_norm<3, 0>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     }
-    allreduce_dev(ctx, ctx->d_results, 1, true);
+    allreduce_dev(dom, ctx->d_results, 1, true);
     read_back(ctx, ctx->d_results, 1, out);
     AB_CATCH
 }
@@ -2458,7 +2459,7 @@ static int vol_bary_impl(ab_vector* u, double* out4) {
     const int g = red_grid(ctx, L.ne);
     if (dom->dim() == 2) AB_LAUNCH(ctx, (k_volume_barycenter<2>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
     else AB_LAUNCH(ctx, (k_volume_barycenter<3>), g, 256, 0, (int64_t)L.ne, L.elems.p, L.xyz.p, u->d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results);
-    allreduce_dev(ctx, ctx->d_results, dom->dim() + 1);
+    allreduce_dev(dom, ctx->d_results, dom->dim() + 1);
     read_back(ctx, ctx->d_results, dom->dim() + 1, out4);
     AB_CATCH
 }

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 
@@ -43,11 +44,20 @@ class _Handle:
     def __init__(self):
         self.h = C.c_void_p()
 
+    def close(self):
+        """Release the native object now (idempotent)."""
+        if self._destroy and self.h:
+            getattr(_lib.load(), self._destroy)(self.h)
+            self.h = C.c_void_p()
+
     def __del__(self):
+        # At interpreter shutdown the objects of a session are finalised in arbitrary order, on every rank at a different time:
+        # tearing down device windows that peers have mapped (CUDA IPC) or a communicator from there can block a rank for good.
+        # The process is about to end and the driver reclaims everything, so native teardown only happens while the interpreter lives.
+        if sys.is_finalizing():
+            return
         try:
-            if self._destroy and self.h:
-                getattr(_lib.load(), self._destroy)(self.h)
-                self.h = C.c_void_p()
+            self.close()
         except Exception:
             pass
 
@@ -569,11 +579,17 @@ class Backend:
         ug.util.refinement.CreateRegularHierarchy = ug._create_regular_hierarchy
         return ug
 
+    def close(self):
+        """Destroy the context (and its communicator) now; every object created from it must have been released before."""
+        if self.ctx:
+            self.lib.ab_context_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
     def __del__(self):
+        if sys.is_finalizing():          # see _Handle.__del__
+            return
         try:
-            if self.ctx:
-                self.lib.ab_context_destroy(self.ctx)
-                self.ctx = C.c_void_p()
+            self.close()
         except Exception:
             pass
 

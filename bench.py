@@ -581,6 +581,13 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            # every rank has finished its device work (the last leg ends with a barrier); leave without the interpreter-shutdown
+            # teardown, whose order differs from rank to rank (peer-mapped device windows, communicators)
+            import torch.distributed as dist
+            dist.barrier()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
 
 
 if __name__ == "__main__":

@@ -100,4 +100,6 @@ else:
 if rank == 0:
     print(json.dumps(out))
 if world > 1:
-    dist.barrier(); dist.destroy_process_group()
+    dist.barrier()
+sys.stdout.flush(); sys.stderr.flush()
+os._exit(0)       # multi-rank tools end here: no interpreter-shutdown teardown order to depend on (every rank has passed the barrier)
