@@ -454,6 +454,12 @@ def run_b200(args):
         xv.from_numpy(x)
         DD.adjust_solution(xv)
         t_spmv = timeit(lambda: A.apply(yv, xv), 20)
+        t_spmv_x = None
+        if world > 1 and dom.decomposed:       # the product a solver sees: local SpMV + interface sum over NVLink (additive -> consistent)
+            def spmv_consistent():
+                A.apply(yv, xv)
+                yv.change_storage_type_to_consistent()
+            t_spmv_x = timeit(spmv_consistent, 20)
         bytes_spmv = spmv_bytes(3, nb, nnzb)
         ach = bytes_spmv / t_spmv / 1e9
         roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak,
@@ -487,6 +493,9 @@ def run_b200(args):
         # assembly roofline: the matrix values are written once (nnzb 8 d^2), the mesh is read once (4 (d+1) per element, 8 d per vertex)
         ne = len(np.load(GRID3D)["elems"]) * 8 ** args.roofline_refs
         asm_bytes = nnzb * 72 + ne * 16 + nb * 24
+        if t_spmv_x is not None:
+            extra.update({"spmv_with_exchange_ms": t_spmv_x * 1e3, "spmv_with_exchange_gbs": bytes_spmv / t_spmv_x / 1e9,
+                          "spmv_with_exchange_frac": bytes_spmv / t_spmv_x / 1e9 / (peak * world)})
         extra.update({"spmv_gbs": ach, "vcycle_ms": t_v * 1e3, "vcycle_gbs": bv / t_v / 1e9, "vcycle_frac": bv / t_v / 1e9 / (peak * world),
                       "vcycle_frac_effective": bv / t_v / 1e9 / (peak * world), "vcycle_frac_dram": bd / t_v / 1e9 / (peak * world),
                       "vcycle_bytes": bv, "vcycle_dram_bytes": bd, "roofline_levels": levels, "solve_ms": t_solve * 1e3, "solve_its": s.step(),
