@@ -87,7 +87,7 @@ struct Interface {
 //   4. sum   : the thread adds what the neighbours wrote for ITS vertex, contributions taken in ascending rank order with its own
 //              value at its own rank's place -- every rank sharing a vertex performs the same additions in the same order, so the
 //              consistent copies are bitwise identical on all ranks, and the result is written by the thread that read the input
-//              (no intra-grid hazard, hence no co-residency assumption).
+//              (no intra-grid hazard, no grid-wide barrier).
 // The epoch lives in device memory (state[0]) and is advanced by the CTA that finishes last, so the launch carries no
 // host-side counter and can be captured into a CUDA graph.  Windows are double-buffered by epoch parity (a neighbour is at
 // most one exchange ahead: it cannot finish exchange e+1 before this rank has published e+1, i.e. finished reading e).
@@ -105,26 +105,22 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
                                                     const unsigned long long* __restrict__ peer_stride, const unsigned long long* __restrict__ peer_flag,
                                                     int total, const double* my_recv, unsigned long long* my_flags, unsigned long long* state,
                                                     int* err, double* v, const double* cf, const double* din, const double* xin, double* xout) {
+    // The grid is capped by the host (kXchgCtasPerSm CTAs per SM, far below the residency limit of this 32-register kernel): every
+    // CTA of the grid is resident while it waits for the neighbours, so the CTAs that still have to store can always run -- a grid
+    // larger than the device could hold would dead-lock against the neighbour's equally oversized grid.  The entries are therefore
+    // walked with a grid-stride loop, in the put phase and again in the sum phase.
     __shared__ int s_fail;
     const unsigned long long epoch = *(volatile unsigned long long*)state + 1ull;   // stable until the last CTA of THIS launch is done
     const int parity = (int)(epoch & 1ull);
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool on = t < niv * D;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x, n_ent = niv * D;
+    const double c1 = (SMOOTH && cf) ? cf[0] : 0.0;
     if (threadIdx.x == 0) s_fail = 0;
-    int k = 0, c = 0, e0 = 0, e1 = 0;
-    int64_t i = 0;
-    double own = 0.0, dold = 0.0;
-    if (on) {
-        k = t / D; c = t - k * D;
-        i = (int64_t)iv[k] * D + c;
-        e0 = iv_ptr[k]; e1 = iv_ptr[k + 1];
-        own = v[i];
-        if (SMOOTH) {
-            const double c1 = cf ? cf[0] : 0.0;
-            dold = (c1 != 0.0 && din) ? c1 * din[i] : 0.0;
-            own -= dold;                                              // additive increment c2 D^-1 r_local
-        }
-        for (int e = e0; e < e1; ++e) {
+    for (int t = t0; t < n_ent; t += nthreads) {                          // 1. put
+        const int k = t / D, c = t - k * D;
+        const int64_t i = (int64_t)iv[k] * D + c;
+        double own = v[i];
+        if (SMOOTH && c1 != 0.0 && din) own -= c1 * din[i];               // additive increment c2 D^-1 r_local
+        for (int e = iv_ptr[k]; e < iv_ptr[k + 1]; ++e) {
             const int nb = iv_nb[e];
             double* dst = reinterpret_cast<double*>(peer_dst[nb] + (unsigned long long)parity * peer_stride[nb]) + (size_t)(iv_slot[e] - offset[nb]) * D + c;
             *dst = own;
@@ -132,9 +128,9 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {                                               // 2. signal
         const unsigned long long old = atomicAdd(state + 1, 1ull);
-        if (old + 1 == gridDim.x) {                                   // every CTA's stores are out: publish the epoch
+        if (old + 1 == gridDim.x) {                                       // every CTA's stores are out: publish the epoch
             __threadfence_system();
             for (int n = 0; n < nneigh; ++n) {
                 unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_flag[n]);
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
             }
         }
     }
-    for (int n = threadIdx.x; n < nneigh; n += blockDim.x) {          // one polling thread per neighbour
+    for (int n = threadIdx.x; n < nneigh; n += blockDim.x) {              // 3. wait: one polling thread per neighbour
         long long spins = 0;
         unsigned long long f;
         do {
@@ -154,28 +150,35 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
     __syncthreads();
     const bool fail = s_fail != 0;
     if (fail && threadIdx.x == 0) *err = 1;
-    if (on && !fail) {
+    if (!fail) {
         const double* buf = my_recv + (size_t)parity * total * D;
-        double tot = 0.0;
-        int e = e0;
-        for (int pos = 0; pos <= nneigh; ++pos) {                      // ascending rank order, own value at position my_pos
-            if (pos == my_pos) { tot += own; continue; }
-            const int nb = pos < my_pos ? pos : pos - 1;
-            if (e < e1 && iv_nb[e] == nb) { tot += __ldcg(buf + (size_t)iv_slot[e] * D + c); ++e; }
-        }
-        if (SMOOTH) {
-            const double dn = dold + tot;
-            v[i] = dn;
-            xout[i] = (xin ? xin[i] : 0.0) + dn;
-        } else {
-            v[i] = tot;
+        for (int t = t0; t < n_ent; t += nthreads) {                      // 4. sum: v[i] is read and written by this thread only
+            const int k = t / D, c = t - k * D;
+            const int64_t i = (int64_t)iv[k] * D + c;
+            double own = v[i], dold = 0.0;
+            if (SMOOTH && c1 != 0.0 && din) { dold = c1 * din[i]; own -= dold; }
+            const int e1 = iv_ptr[k + 1];
+            int e = iv_ptr[k];
+            double tot = 0.0;
+            for (int pos = 0; pos <= nneigh; ++pos) {                      // ascending rank order, own value at position my_pos
+                if (pos == my_pos) { tot += own; continue; }
+                const int nb = pos < my_pos ? pos : pos - 1;
+                if (e < e1 && iv_nb[e] == nb) { tot += __ldcg(buf + (size_t)iv_slot[e] * D + c); ++e; }
+            }
+            if (SMOOTH) {
+                const double dn = dold + tot;
+                v[i] = dn;
+                xout[i] = (xin ? xin[i] : 0.0) + dn;
+            } else {
+                v[i] = tot;
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(state + 2, 1ull);
-        if (old + 1 == gridDim.x) {                                   // last CTA out: every CTA has read the epoch and arrived
+        if (old + 1 == gridDim.x) {                                       // last CTA out: every CTA has read the epoch and arrived
             state[1] = 0ull;
             state[2] = 0ull;
             __threadfence();
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
         }
     }
 }
+constexpr int kXchgCtasPerSm = 2;
 
 __global__ void k_iface_pack(int total, int D, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total * D; t += gridDim.x * blockDim.x) {

@@ -238,7 +238,8 @@ void Domain::finalize() {
 // interface sum: additive -> consistent for a P1 vector with D components on `level`
 static void launch_xchg(Domain* dom, Interface& I, int D, bool smooth, double* v, const double* cf, const double* din, const double* xin, double* xout) {
     Context* ctx = dom->ctx;
-    const int g = std::max(1, (I.niv * D + 255) / 256);
+    // capped grid: all CTAs are resident while they wait for the neighbours (see k_iface_xchg); larger interfaces are strided
+    const int g = std::max(1, std::min((I.niv * D + 255) / 256, kXchgCtasPerSm * ctx->num_sms));
     if (smooth)
         AB_LAUNCH(ctx, (k_iface_xchg<true>), g, 256, 0, I.niv, D, (int)I.neigh.size(), I.my_pos, I.iv.p, I.iv_ptr.p, I.iv_slot.p, I.iv_nb.p, I.d_offset.p, I.d_neigh.p,
                   I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.total, I.win_recv, I.win_flags, I.state.p, dom->p2p_err.p, v, cf, din, xin, xout);
@@ -815,6 +816,12 @@ void Gmg::setup(const double* top_vals, const std::vector<std::pair<int, int>>& 
         AB_CUDA(cudaMemcpyAsync(coefs.p, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     AB_REQUIRE(hfail == 0, AB_ERR_STATE, "coarse-level matrix is singular");
+    if (dist && dom->p2p_connected) {      // the setup's interface sums (diagonal, row sums) must have arrived as well
+        int herr = 0;
+        AB_CUDA(cudaMemcpyAsync(&herr, dom->p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        AB_CUDA(cudaStreamSynchronize(ctx->stream));
+        AB_REQUIRE(herr == 0, AB_ERR_CUDA, "peer-to-peer interface exchange timed out during solver:init (a neighbour rank did not arrive)");
+    }
 }
 
 void Gmg::smooth(int l, const double* b, double* x, int nu, bool zero_guess, const std::vector<std::pair<double, double>>& coef, const double* cf,
