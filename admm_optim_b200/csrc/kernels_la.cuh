@@ -229,35 +229,40 @@ __global__ void k_diag_rowabs(int nb, const int* __restrict__ rowptr, const int*
         rowabs[t] = sum;
     }
 }
-__global__ void __launch_bounds__(256) k_dinv_lmax(int64_t n, double* __restrict__ diag_to_dinv, const double* __restrict__ rowabs,
-                                                   double* partials, unsigned int* ticket, double* red) {
-    double mx[1] = {0.0};
+// point-Jacobi data from consistent diagonal / row sums with two row-sum variants: red[0] = max rows_a / a_ii, red[1] = max rows_b / a_ii
+__global__ void __launch_bounds__(256) k_dinv_lmax2(int64_t n, double* __restrict__ diag_to_dinv, const double* __restrict__ rows_a,
+                                                    const double* __restrict__ rows_b, double* partials, unsigned int* ticket, double* red) {
+    double mx[2] = {0.0, 0.0};
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const double aii = diag_to_dinv[t];
         diag_to_dinv[t] = 1.0 / aii;
-        mx[0] = fmax(mx[0], rowabs[t] / aii);
+        mx[0] = fmax(mx[0], rows_a[t] / aii);
+        mx[1] = fmax(mx[1], rows_b[t] / aii);
     }
-    grid_reduce<1, 1>(mx, partials, ticket, red);
+    grid_reduce<2, 1>(mx, partials, ticket, red);
 }
-// replicated coarse solve: local additive rhs -> global free-dof vector, dense GEMV, global -> local consistent solution
-__global__ void k_coarse_gather(int ndof, const int* __restrict__ dof2gfree, const double* __restrict__ b, double* __restrict__ bg) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ndof; t += gridDim.x * blockDim.x)
-        if (dof2gfree[t] >= 0) atomicAdd(bg + dof2gfree[t], b[t]);
-}
-__global__ void __launch_bounds__(256) k_dense_gemv(int n, const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < n; i += nwarps) {
-        double acc = 0.0;
-        for (int c = lane; c < n; c += 32) acc += A[i * n + c] * b[c];
-        acc = warp_sum(acc);
-        if (lane == 0) x[i] = acc;
+// exact row sums of an additive operator (multi-GPU): compact copy of the blocks shared with neighbour ranks ...
+__global__ void k_pack_blocks(int64_t n, int DD, const int* __restrict__ bpos, const double* __restrict__ vals, double* __restrict__ cv) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = t / DD;
+        cv[t] = vals[(int64_t)bpos[k] * DD + (t - k * DD)];
     }
 }
-__global__ void k_coarse_scatter(int ndof, const int* __restrict__ dof2gfree, const double* __restrict__ xg, double* __restrict__ x) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ndof; t += gridDim.x * blockDim.x) x[t] = dof2gfree[t] >= 0 ? xg[dof2gfree[t]] : 0.0;
+// ... and, once the neighbours' parts were added to cv, the correction of the local row sums: every rank holding a shared block
+// contributes |sum| / mult instead of |its own part|, so that the interface sum of the rows counts |sum| exactly once
+template <int D>
+__global__ void k_rowabs_fix(int nsb, const int* __restrict__ bpos, const int* __restrict__ brow, const int* __restrict__ mult,
+                             const double* __restrict__ vals, const double* __restrict__ cv, double* rowabs) {
+    constexpr int DD = D * D;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nsb * D; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t / D), r = (int)(t - (int64_t)k * D);
+        const double inv = 1.0 / (double)mult[k];
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) s += fabs(cv[(int64_t)k * DD + r * D + c]) * inv - fabs(vals[(int64_t)bpos[k] * DD + r * D + c]);
+        atomicAdd(rowabs + (int64_t)brow[k] * D + r, s);
+    }
 }
-
 // ---------------------------------------------------------------------------------------------
 // BSR SpMV family (k_bsr_spmv_tma: default; k_bsr_spmv_warp: fallback when a row exceeds a tile).
 //   MODE 0: y = A x

@@ -73,6 +73,16 @@ struct Domain {
     struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
     std::vector<HostIface> host_iface;
     std::vector<Interface> iface;
+    // Matrix blocks shared with neighbour ranks (both vertices on the interface, block present on both sides), per decomposed
+    // level: the exact Gershgorin bound of the additive operators needs their sum BEFORE the absolute value (gmg_setup_kernels).
+    // Setup-only traffic: packed ncclSend/ncclRecv.
+    struct BlockIface {
+        std::vector<int> neigh, offset, h_idx, h_bpos, h_brow, h_mult;     // host staging until finalize
+        int total = 0, nsb = 0;
+        DevBuf<int> idx, bpos, brow, mult;     // slot -> compact block id; compact id -> local block position / row vertex / ranks holding it
+        DevBuf<double> cv, send, recv;         // compact values (nsb x d*d), packed buffers (total x d*d)
+    };
+    std::vector<BlockIface> biface;
     // Hierarchical agglomeration (the reference keeps level 0 on one process and widens the process set level by level,
     // 3d_admm.lua:151-183): levels <= gather_level live on rank 0 as ONE global, non-distributed hierarchy (`cdom`, the global
     // grid refined gather_level times); the level-`gather_level` Galerkin operators of all ranks are summed into it at every
@@ -229,6 +239,17 @@ void Domain::finalize() {
             I.save.alloc((size_t)std::max(I.niv, 1) * 2 * maxc);
             I.state.alloc(4);
             I.state.zero(ctx->stream);
+        }
+        const int DD = mesh.dim * mesh.dim;
+        for (BlockIface& B : biface) {
+            if (B.nsb == 0) continue;
+            B.idx.upload(B.h_idx, ctx->stream);
+            B.bpos.upload(B.h_bpos, ctx->stream);
+            B.brow.upload(B.h_brow, ctx->stream);
+            B.mult.upload(B.h_mult, ctx->stream);
+            B.cv.alloc((size_t)B.nsb * DD);
+            B.send.alloc((size_t)std::max(B.total, 1) * DD);
+            B.recv.alloc((size_t)std::max(B.total, 1) * DD);
         }
     }
     AB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -662,15 +683,41 @@ static void gmg_setup_kernels(Gmg& G) {
         if (!dist) {
             AB_LAUNCH(ctx, (k_diag_gershgorin<D>), red_grid(ctx, n), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p,
                       ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
-        } else {   // additive rows: diagonal and |row| sums are made consistent across the interfaces first
+        } else {
+            // additive rows: diagonal and |row| sums are made consistent across the interfaces.  Summing the per-rank |a_ij| over-
+            // estimates sum_j |a_ij| wherever a block is shared (|x| + |y| >= |x + y|): the bound -- and with it the Chebyshev
+            // interval and the iteration counts -- would depend on the partition.  With the shared-block lists (Domain::biface) the
+            // shared blocks are summed first and every rank adds |sum| / (ranks holding the block) instead of its own |part|: the
+            // interface sum of the rows is then EXACTLY the row sum of the global operator.  The loose sum is kept beside it (g.d is
+            // free during setup) and only serves as a plausibility bracket for the exact one (Gmg::setup).
             AB_LAUNCH(ctx, (k_diag_rowabs<D>), ew_grid(ctx, n), 256, 0, Ld.nv, Ld.rowptr.p, Ld.diagpos.p, g.vals, g.dinv.p, g.r.p);
+            dev_copy(ctx, n, g.r.p, g.d.p);
+            if (l < (int)dom->biface.size() && dom->biface[l].nsb > 0) {
+                Domain::BlockIface& B = dom->biface[l];
+                NcclApi& nc = NcclApi::get();
+                AB_LAUNCH(ctx, k_pack_blocks, ew_grid(ctx, (int64_t)B.nsb * DD), 256, 0, (int64_t)B.nsb * DD, DD, B.bpos.p, g.vals, B.cv.p);
+                if (B.total > 0) {
+                    AB_LAUNCH(ctx, k_iface_pack, grid_for((int64_t)B.total * DD, 256, ctx->num_sms * 4), 256, 0, B.total, DD, B.idx.p, B.cv.p, B.send.p);
+                    AB_NCCL(nc.GroupStart());
+                    for (size_t q = 0; q < B.neigh.size(); ++q) {
+                        const size_t cnt = (size_t)(B.offset[q + 1] - B.offset[q]) * DD;
+                        if (cnt == 0) continue;                      // symmetric: the common block list is empty on both sides
+                        AB_NCCL(nc.Send(B.send.p + (size_t)B.offset[q] * DD, cnt, ncclFloat64, B.neigh[q], ctx->comm->comm, ctx->stream));
+                        AB_NCCL(nc.Recv(B.recv.p + (size_t)B.offset[q] * DD, cnt, ncclFloat64, B.neigh[q], ctx->comm->comm, ctx->stream));
+                    }
+                    AB_NCCL(nc.GroupEnd());
+                    AB_LAUNCH(ctx, k_iface_unpack_add, grid_for((int64_t)B.total * DD, 256, ctx->num_sms * 4), 256, 0, B.total, DD, B.idx.p, B.recv.p, B.cv.p);
+                }
+                AB_LAUNCH(ctx, (k_rowabs_fix<D>), ew_grid(ctx, (int64_t)B.nsb * D), 256, 0, B.nsb, B.bpos.p, B.brow.p, B.mult.p, g.vals, B.cv.p, g.r.p);
+            }
             exchange_sum(dom, l, g.dinv.p, D);
             exchange_sum(dom, l, g.r.p, D);
-            AB_LAUNCH(ctx, k_dinv_lmax, red_grid(ctx, n), 256, 0, n, g.dinv.p, g.r.p, ctx->d_partials, ctx->d_tickets, ctx->d_results + l);
+            exchange_sum(dom, l, g.d.p, D);
+            AB_LAUNCH(ctx, k_dinv_lmax2, red_grid(ctx, n), 256, 0, n, g.dinv.p, g.r.p, g.d.p, ctx->d_partials, ctx->d_tickets, ctx->d_results + 2 * l);
         }
     }
     if (dist) {
-        if (top > base) allreduce_dev(dom, ctx->d_results + base + 1, top - base, true);
+        if (top > base) allreduce_dev(dom, ctx->d_results + 2 * (base + 1), 2 * (top - base), true);   // (exact, loose) per level
         AB_CUDA(cudaMemsetAsync(G.fail.p, 0, sizeof(int), ctx->stream));
         TraceTimer tt(ctx->stream, "gmg: gather + coarse setup");
         gmg_gather_operator<D>(G);
@@ -788,7 +835,9 @@ void Gmg::setup(const double* top_vals, const std::vector<std::pair<int, int>>& 
     // ONE synchronisation per setup: Gershgorin bounds and the singularity flag come back together (pinned memory)
     int* h_fail = reinterpret_cast<int*>(ctx->h_results + Context::kResultSlots - 1);
     auto fetch = [&]() {
-        if (top >= 1) AB_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results + 1, top * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (dist) {          // (exact, loose) per decomposed level, levels base+1 .. top
+            if (top > base) AB_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results + 2 * (base + 1), 2 * (top - base) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        } else if (top >= 1) AB_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results + 1, top * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         AB_CUDA(cudaMemcpyAsync(h_fail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         AB_CUDA(cudaStreamSynchronize(ctx->stream));
         return *h_fail;
@@ -802,7 +851,14 @@ void Gmg::setup(const double* top_vals, const std::vector<std::pair<int, int>>& 
     if (top > base) {
         std::vector<double> hc((size_t)(top + 1) * 2 * coef_stride, 0.0);
         for (int l = base + 1; l <= top; ++l) {
-            L[l].lmax = ctx->h_results[l - 1];
+            if (dist) {
+                // the exact bound (shared blocks summed before the absolute value) lies in (0.5 loose, loose]; anything else means the
+                // shared-block lists do not match the operator -- fall back to the loose (always valid, partition-dependent) bound
+                const double exact = ctx->h_results[2 * (l - base - 1)], loose = ctx->h_results[2 * (l - base - 1) + 1];
+                L[l].lmax = (exact > 0.5 * loose && exact <= loose * (1.0 + 1e-9)) ? exact : loose;
+            } else {
+                L[l].lmax = ctx->h_results[l - 1];
+            }
             smoother_coefs(desc, L[l].lmax, desc.pre_smooth, L[l].coef_pre);
             smoother_coefs(desc, L[l].lmax, desc.post_smooth, L[l].coef_post);
             double* hp = hc.data() + (size_t)l * 2 * coef_stride;
@@ -1773,6 +1829,27 @@ int ab_domain_set_gather(ab_domain* dom, int gather_level, ab_domain* coarse, co
     dom->g_gpos.upload(std::vector<int>(gpos_cat, gpos_cat + nbt), ctx->stream);
     dom->g_vstage.alloc((size_t)nvt * D);
     dom->g_mstage.alloc((size_t)nbt * D * D);
+    AB_CATCH
+}
+int ab_domain_set_block_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets,
+                                  const int32_t* slot_block, int nshared, const int32_t* bpos, const int32_t* brow, const int32_t* mult) {
+    AB_TRY
+    AB_REQUIRE(dom && !dom->finalized, AB_ERR_STATE, "block interfaces must be set before the first ApproximationSpace");
+    AB_REQUIRE(level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    AB_REQUIRE(nneigh >= 0 && nshared >= 0 && offsets, AB_ERR_ARG, "bad block interface");
+    if (dom->biface.size() < dom->mesh.levels.size()) dom->biface.resize(dom->mesh.levels.size());
+    Domain::BlockIface& B = dom->biface[level];
+    B.neigh.assign(neigh_ranks, neigh_ranks + nneigh);
+    B.offset.assign(offsets, offsets + nneigh + 1);
+    B.total = nneigh ? offsets[nneigh] : 0;
+    B.nsb = nshared;
+    B.h_idx.assign(slot_block, slot_block + B.total);
+    B.h_bpos.assign(bpos, bpos + nshared);
+    B.h_brow.assign(brow, brow + nshared);
+    B.h_mult.assign(mult, mult + nshared);
+    const int nv = dom->mesh.levels[level].nv;
+    for (int k : B.h_idx) AB_REQUIRE(k >= 0 && k < nshared, AB_ERR_ARG, "block interface: slot refers to no shared block");
+    for (int k = 0; k < nshared; ++k) AB_REQUIRE(B.h_bpos[k] >= 0 && B.h_brow[k] >= 0 && B.h_brow[k] < nv && B.h_mult[k] >= 2, AB_ERR_ARG, "block interface: bad shared block");
     AB_CATCH
 }
 int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* rowptr, int32_t* colidx) {

@@ -202,3 +202,49 @@ def block_positions(local_elems, nv_local: int, l2g, global_keys, nv_global: int
     if len(gk) and (pos.max(initial=0) >= len(global_keys) or not np.array_equal(global_keys[pos], gk)):
         raise ValueError("a local matrix block has no global counterpart")
     return pos.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# shared matrix blocks of a decomposed level (exact Gershgorin bound of the additive operators)
+# ------------------------------------------------------------------------------------------------
+def match_blocks(rowptr, colidx, neigh, offsets, idx, rank: int, gather):
+    """Matrix blocks (i, j) whose two vertices are shared with a neighbour rank AND that exist in both local patterns: their
+    values are additive over the ranks, so sum_j |a_ij| of the global operator needs their sum before the absolute value.
+    `neigh/offsets/idx`: the vertex interface of the level (match_level).  Every pair of neighbours derives the same ordered
+    list from integers only: a block is keyed by the positions of its two vertices in the pair's common vertex order.
+    Returns (offsets_b, slot_block, bpos, brow, mult): per neighbour (same order as `neigh`) the slots offsets_b[n]..offsets_b[n+1]
+    into slot_block = compact ids of the shared blocks; bpos = local block position of every compact id, brow = its row vertex,
+    mult = number of ranks holding it."""
+    rowptr = np.asarray(rowptr, np.int64)
+    colidx = np.asarray(colidx, np.int64)
+    nv = len(rowptr) - 1
+    cand = {}
+    for n, q in enumerate(neigh):
+        verts = np.asarray(idx[offsets[n]:offsets[n + 1]], np.int64)
+        m = len(verts)
+        pos = -np.ones(nv, np.int64)
+        pos[verts] = np.arange(m)
+        cnt = rowptr[verts + 1] - rowptr[verts]
+        start = np.repeat(rowptr[verts], cnt)
+        within = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        b = start + within                                           # local block positions of the rows of the shared vertices
+        pi = np.repeat(np.arange(m), cnt)
+        pj = pos[colidx[b]]
+        keep = pj >= 0
+        key = pi[keep] * m + pj[keep]
+        order = np.argsort(key)
+        cand[int(q)] = (key[order], b[keep][order])
+    everyone = gather({q: k for q, (k, _) in cand.items()})
+    offsets_b, slots = [0], []
+    for q in [int(x) for x in neigh]:
+        mine_k, mine_b = cand[q]
+        theirs = everyone[q].get(rank)
+        if theirs is None:
+            theirs = np.zeros(0, np.int64)
+        _, ia, _ = np.intersect1d(mine_k, theirs, return_indices=True)    # ascending common keys: the same order on both sides
+        slots.append(mine_b[ia])
+        offsets_b.append(offsets_b[-1] + len(ia))
+    allb = np.concatenate(slots) if slots else np.zeros(0, np.int64)
+    bpos, inv, counts = np.unique(allb, return_inverse=True, return_counts=True)
+    brow = np.searchsorted(rowptr, bpos, side="right") - 1
+    return (np.array(offsets_b, np.int32), inv.astype(np.int32), bpos.astype(np.int32), brow.astype(np.int32), (counts + 1).astype(np.int32))

@@ -54,9 +54,9 @@ class _Handle:
         # At interpreter shutdown the objects of a session are finalised in arbitrary order, on every rank at a different time:
         # tearing down device windows that peers have mapped (CUDA IPC) or a communicator from there can block a rank for good.
         # The process is about to end and the driver reclaims everything, so native teardown only happens while the interpreter lives.
-        if sys.is_finalizing():
-            return
         try:
+            if sys is None or sys.is_finalizing():
+                return
             self.close()
         except Exception:
             pass
@@ -586,9 +586,9 @@ class Backend:
             self.ctx = C.c_void_p()
 
     def __del__(self):
-        if sys.is_finalizing():          # see _Handle.__del__
-            return
         try:
+            if sys is None or sys.is_finalizing():          # see _Handle.__del__
+                return
             self.close()
         except Exception:
             pass
@@ -705,6 +705,21 @@ class Backend:
             call("ab_domain_set_interface", dom.h, level, len(neigh), _ip(neigh) if len(neigh) else None, _ip(offsets),
                  _ip(idx) if len(idx) else None, owned.ctypes.data_as(C.POINTER(C.c_ubyte)))
             dom._iface.append(dict(neigh=neigh, offsets=offsets, idx=idx, owned=owned))
+        # ---- shared matrix blocks of the decomposed levels: exact (partition-independent) Gershgorin bound at solver:init ----
+        dom._biface = {}
+        if os.environ.get("ADMM_B200_EXACT_GERSHGORIN", "1") != "0":
+            for level in range(lg + 1, dom.num_levels()):
+                info = dom.level_info(level)
+                rp, ci = np.empty(info["nv"] + 1, np.int32), np.empty(info["nv"] + 2 * info["nedges"], np.int32)
+                nn = C.c_int64()
+                call("ab_domain_level_pattern", dom.h, level, C.byref(nn), _ip(rp), _ip(ci))
+                I = dom._iface[level]
+                offb, slotb, bpos, brow, mult = P.match_blocks(rp, ci, I["neigh"], I["offsets"], I["idx"], self.rank, self._gather)
+                del rp, ci
+                call("ab_domain_set_block_interface", dom.h, level, len(I["neigh"]), _ip(I["neigh"]) if len(I["neigh"]) else None, _ip(offb),
+                     _ip(slotb) if len(slotb) else None, len(bpos), _ip(bpos) if len(bpos) else None, _ip(brow) if len(brow) else None,
+                     _ip(mult) if len(mult) else None)
+                dom._biface[level] = dict(offsets=offb, slot_block=slotb, bpos=bpos, brow=brow, mult=mult)
         # ---- gathered levels: the global grid refined lg times (every rank builds it on the host for the maps; rank 0 keeps it) ----
         cdom = Domain(self)
         self._create_from_dict(cdom, g, host_only=(self.rank != 0 or not self.ctx))

@@ -85,6 +85,14 @@ int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t
  * (BSR order of ab_domain_level_pattern).  Other ranks pass NULL for all of them.                                 */
 int ab_domain_set_gather(ab_domain* dom, int gather_level, ab_domain* coarse, const int32_t* nv_per_rank, const int32_t* l2g_cat,
                          const int64_t* nblk_per_rank, const int32_t* gpos_cat);
+/* Matrix blocks shared with neighbour ranks on a decomposed level (both vertices on the interface, block present on both sides), in
+ * an order both sides agree on: slots offsets[n]..offsets[n+1] of neighbour n refer to compact ids 0..nshared-1 (slot_block);
+ * bpos / brow / mult give, per compact id, the local block position (BSR order), its row vertex and the number of ranks holding
+ * the block.  With these lists solver:init computes the Gershgorin bound of the GLOBAL operator exactly (shared blocks are summed
+ * before the absolute value), so the Chebyshev smoother does not depend on the partition; without them the bound is the (valid,
+ * partition-dependent) sum of the per-rank row sums.  Optional; before the first ApproximationSpace.                      */
+int ab_domain_set_block_interface(ab_domain* dom, int level, int nneigh, const int32_t* neigh_ranks, const int32_t* offsets,
+                                  const int32_t* slot_block, int nshared, const int32_t* bpos, const int32_t* brow, const int32_t* mult);
 /* P1 block pattern of a level (host side, no GPU needed): block rows = vertices, columns ascending, diagonal included;
  * nnzb = V + 2E.  rowptr (nv+1) / colidx (nnzb) may be NULL to query the size only.                              */
 int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* rowptr, int32_t* colidx);

@@ -2,6 +2,7 @@
 Exercises the host side of the multi-GPU path: RCB partition, sub-grid extraction, native refinement of the local
 sub-grid, candidate masks, coordinate matching over torch.distributed, the C-ABI interface registration and the
 vertical-interface maps of the agglomerated coarse levels (local -> global vertices / matrix blocks on the gather level)."""
+import ctypes as C
 import json
 import os
 import sys
@@ -54,7 +55,6 @@ def incidence(elems, nv):
 lk, lc = incidence(ll["elems"], nvl)
 assert np.array_equal(lk, P.pattern_keys(ll["elems"], nvl)) and len(lk) == len(G["gpos"])
 # the C++ pattern (what the device matrices use) has exactly this order
-import ctypes as C
 nn = C.c_int64()
 ug4.call("ab_domain_level_pattern", dom.h, lg, C.byref(nn), None, None)
 rp, ci = np.empty(nvl + 1, np.int32), np.empty(nn.value, np.int32)
@@ -75,7 +75,69 @@ if rank == 0:
     for _, _, l2g, _ in parts:
         covered[l2g] = True
     ok = ok and bool(covered.all())
-allres = gather(dict(decomposed=True, gather_level=lg, levels=res, blocks_ok=ok))
+# shared matrix blocks of the top level (exact Gershgorin bound, partition.match_blocks): a NumPy twin of the device steps of
+# lib.cu gmg_setup_kernels -- pack the shared blocks, add the neighbours' parts, replace |own part| by |sum| / mult in the local
+# row sums, interface-sum the rows -- must reproduce the row sums of the GLOBAL operator (scalar P1 stiffness as test matrix)
+import scipy.sparse as sp
+
+
+def stiffness(X, el):
+    n, dd = el.shape[1], X.shape[1]
+    J = np.transpose(X[el[:, 1:]] - X[el[:, :1]], (0, 2, 1))
+    vol = np.abs(np.linalg.det(J)) / (2 if dd == 2 else 6)
+    Gi = np.linalg.inv(J)
+    G = np.concatenate([-Gi.sum(axis=1, keepdims=True), Gi], axis=1)
+    K = vol[:, None, None] * np.einsum("eac,ebc->eab", G, G)
+    A = sp.csr_matrix((K.ravel(), (np.repeat(el, n, axis=1).ravel(), np.tile(el, (1, n)).ravel())), shape=(len(X), len(X)))
+    A.sum_duplicates(); A.sort_indices()
+    return A
+
+
+top = refs
+lt, It, Bt = dom.get_level(top), dom._iface[top], dom._biface[top]
+A = stiffness(lt["xyz"], lt["elems"])
+nvt = len(lt["xyz"])
+nn = C.c_int64()
+rp, ci = np.empty(nvt + 1, np.int32), np.empty(A.nnz, np.int32)
+ug4.call("ab_domain_level_pattern", dom.h, top, C.byref(nn), rp.ctypes.data_as(C.POINTER(C.c_int32)), ci.ctypes.data_as(C.POINTER(C.c_int32)))
+assert nn.value == A.nnz and np.array_equal(A.indptr, rp) and np.array_equal(A.indices, ci)
+vals = A.data
+
+
+def vertex_sum(v):
+    send = {int(q): v[It["idx"][It["offsets"][n]:It["offsets"][n + 1]]] for n, q in enumerate(It["neigh"])}
+    ev = gather(send)
+    out = v.copy()
+    for n, q in enumerate(It["neigh"]):
+        np.add.at(out, It["idx"][It["offsets"][n]:It["offsets"][n + 1]], ev[int(q)][rank])
+    return out
+
+
+rowabs = np.add.reduceat(np.abs(vals), rp[:-1])
+loose = vertex_sum(rowabs)
+cv = vals[Bt["bpos"]].copy()
+ev = gather({int(q): cv[Bt["slot_block"][Bt["offsets"][n]:Bt["offsets"][n + 1]]] for n, q in enumerate(It["neigh"])})
+tot = cv.copy()
+for n, q in enumerate(It["neigh"]):
+    np.add.at(tot, Bt["slot_block"][Bt["offsets"][n]:Bt["offsets"][n + 1]], ev[int(q)][rank])
+np.add.at(rowabs, Bt["brow"], np.abs(tot) / Bt["mult"] - np.abs(vals[Bt["bpos"]]))
+exact = vertex_sum(rowabs)
+rows = gather((lt["xyz"], exact, loose))
+gersh = dict(ok=True)
+if rank == 0:
+    gdom = ug4.Domain(ug)
+    ug._create_from_dict(gdom, dom._global, host_only=True)
+    ug4.call("ab_domain_refine", gdom.h, top)
+    gl2 = gdom.get_level(top)
+    Ag = stiffness(gl2["xyz"], gl2["elems"])
+    lut = {tuple(x): v for x, v in zip(gl2["xyz"].tolist(), np.abs(Ag).sum(axis=1).A1)}
+    worst, differing = 0.0, 0
+    for Xr, ex, lo in rows:
+        ref = np.array([lut[tuple(x)] for x in Xr.tolist()])
+        worst = max(worst, float(np.abs(ex - ref).max() / ref.max()))
+        differing += int((np.abs(lo - ref) > 1e-9 * ref.max()).sum())
+    gersh = dict(ok=bool(worst < 1e-12), worst=worst, rows_where_loose_differs=differing, shared_blocks=int(len(Bt["bpos"])))
+allres = gather(dict(decomposed=True, gather_level=lg, levels=res, blocks_ok=ok, gershgorin=gersh))
 if rank == 0:
     print(json.dumps(allres))
 dist.barrier()

@@ -173,6 +173,8 @@ def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts, gather_d
     res = _run_dist_host_workers(grid, refs, gather_dofs, 29613)
     assert all(r["decomposed"] and r["gather_level"] == lg for r in res)
     assert res[0]["blocks_ok"]
+    # exact Gershgorin rows through the shared-block lists (NumPy twin of the device steps) = rows of the global operator
+    assert res[0]["gershgorin"]["ok"] and res[0]["gershgorin"]["shared_blocks"] > 0, res[0]["gershgorin"]
     lv = [r["levels"] for r in res]
     for level in range(refs + 1):
         assert sum(r[level]["owned"] for r in lv) == counts[level]
