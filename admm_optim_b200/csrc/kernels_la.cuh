@@ -206,12 +206,6 @@ __global__ void k_bicg_roll(double* sc, const double* out2) {
     sc[SC_RR] = out2[0];
     sc[SC_RHO] = out2[1];
 }
-// x += alpha * ph (half-step exit of BiCGStab)
-__global__ void k_bicg_half_x(int64_t n, const double* __restrict__ sc, const double* __restrict__ ph, double* __restrict__ x) {
-    const double alpha = sc[SC_RHO] / sc[SC_RV];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += alpha * ph[i];
-}
-
 // point-Jacobi data, distributed: additive diagonal and additive absolute row sums (made consistent by an interface sum)
 template <int D>
 __global__ void k_diag_rowabs(int nb, const int* __restrict__ rowptr, const int* __restrict__ diagpos, const double* __restrict__ vals,
