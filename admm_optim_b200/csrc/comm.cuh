@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
         const int k = t / D, c = t - k * D;
         const int64_t i = (int64_t)iv[k] * D + c;
         double own = v[i];
-        if (SMOOTH && c1 != 0.0 && din) own -= c1 * din[i];               // additive increment c2 D^-1 r_local
+        // additive increment c2 D^-1 r_local.  Separate multiply and subtract (no FMA contraction): the sum phase below recomputes
+        // this value and must get the same bits as the copy sent to the neighbours
+        if (SMOOTH && c1 != 0.0 && din) own = __dsub_rn(own, __dmul_rn(c1, din[i]));
         for (int e = iv_ptr[k]; e < iv_ptr[k + 1]; ++e) {
             const int nb = iv_nb[e];
             double* dst = reinterpret_cast<double*>(peer_dst[nb] + (unsigned long long)parity * peer_stride[nb]) + (size_t)(iv_slot[e] - offset[nb]) * D + c;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(256) k_iface_xchg(int niv, int D, int nneigh, 
             const int k = t / D, c = t - k * D;
             const int64_t i = (int64_t)iv[k] * D + c;
             double own = v[i], dold = 0.0;
-            if (SMOOTH && c1 != 0.0 && din) { dold = c1 * din[i]; own -= dold; }
+            if (SMOOTH && c1 != 0.0 && din) { dold = __dmul_rn(c1, din[i]); own = __dsub_rn(own, dold); }
             const int e1 = iv_ptr[k + 1];
             int e = iv_ptr[k];
             double tot = 0.0;
