@@ -151,11 +151,11 @@ def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
     assert outs[1] == ""
 
 
-def _run_dist_host_workers(grid, refs, gather_dofs, port):
+def _run_dist_host_workers(grid, refs, gather_dofs, port, world=2):
     import json
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", ADMM_B200_GATHER_DOFS=str(gather_dofs))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), ADMM_B200_GATHER_DOFS=str(gather_dofs))
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_host_worker.py"), grid, str(refs)],
-                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
     outs = []
     for p in procs:
         out, err = p.communicate(timeout=300)
@@ -181,6 +181,20 @@ def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts, gather_d
         a, b = lv[0][level]["shared"].get("1"), lv[1][level]["shared"].get("0")
         assert a is not None and a == b and len(a) > 0
         assert lv[0][level]["nv"] + lv[1][level]["nv"] - len(a) == counts[level]
+
+
+def test_partition_with_vertices_shared_by_four_ranks_gloo_world_size_4():
+    """Four ranks on the 3D box: every rank neighbours every other one (edges shared by all four).  Ownership is unique, the
+    vertical-interface maps are exact, and the shared-block lists reproduce the global row sums although blocks are held by up to
+    four ranks."""
+    res = _run_dist_host_workers(GRID3D, 2, 7000, 29615, world=4)
+    assert all(r["decomposed"] and r["gather_level"] == 1 for r in res) and res[0]["blocks_ok"]
+    g = res[0]["gershgorin"]
+    assert g["ok"] and g["rows_where_loose_differs"] > 0 and g["shared_blocks"] > 0, g
+    lv = [r["levels"] for r in res]
+    for level, count in enumerate([338, 2124, 14910]):
+        assert sum(r[level]["owned"] for r in lv) == count
+    assert all(len(r[2]["shared"]) == 3 for r in lv)              # three neighbours each on the top level
 
 
 def test_small_problem_is_not_decomposed_gloo_world_size_2():
