@@ -509,6 +509,42 @@ def run_b200(args):
 
     if args.admm_refs > 0:
         a4, p4 = admm_leg(ug, 3, args.admm_refs, GRID3D)
+        # roofline figures of the BLAS-1 and P0 (ADMM prox / dual / norm) kernels on this problem's LOCAL vectors: algorithmic bytes
+        # (8 B x vectors read + written; element kernels: + 4 (d+1) connectivity per element and the coordinate / u gathers counted
+        # once per vertex) over the wall time of the public call, which for the reductions includes the read-back
+        try:
+            n1, n0 = p4.DeformationSpace_ApproxSpace.num_dofs(), p4.Lambda_ApproxSpace.num_dofs()
+            ne, nvl = n0 // 9, n1 // 3
+            mesh_b = ne * 16 + nvl * 24
+
+            def wall(fn, reps=20):            # local clock: the reductions synchronise the ranks themselves
+                for _ in range(3):
+                    fn()
+                ug.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    fn()
+                ug.synchronize()
+                return (time.perf_counter() - t0) / reps
+
+            el = {}
+            for name, fn, nbytes in (
+                    ("axpby_p0", lambda: ug.VecScaleAdd2(p4.temp1_piecewise, 1.0, p4.lambda_piecewise, -0.5, p4.q_projected), 3 * 8 * n0),
+                    ("dot_p0", lambda: ug.VecProdMulti([p4.lambda_piecewise], p4.q_projected), 2 * 8 * n0),
+                    ("axpby_p1", lambda: ug.VecScaleAdd2(p4.u_diff, 1.0, p4.u, -1.0, p4.u_old), 3 * 8 * n1),
+                    ("project_frobenius", lambda: ug.Testing(p4.q_projected, p4.q_piecewise, p4.lcmps, 0.3), 2 * 8 * n0),
+                    ("l2norm_p0", lambda: ug.L2NormAll(p4.temp1_piecewise), 8 * n0 + mesh_b),
+                    ("l2norm_p1", lambda: ug.L2NormAll(p4.u), 8 * n1 + mesh_b),
+                    ("lambda_update_defect", lambda: p4.LambdaUpdate_DomainDisc.assemble_defect(p4.temp1_piecewise, p4.u_negative), 2 * 8 * n0 + 8 * n1 + mesh_b),
+                    ("mass_model_defect", lambda: p4.MassModel_DomainDisc.assemble_defect(p4.rhs_piecewise, p4.u_negative), 2 * 8 * n0 + 8 * n1 + mesh_b),
+                    ("volume_barycenter", lambda: ug.BarycenterDefect(p4.u, p4.ucmps, "outer", 4), 8 * n1 + mesh_b),
+                    ("load_vector_defect", lambda: p4.DeformationEquation_DomainDisc.assemble_defect(p4.Lu, p4.u), 2 * 8 * n0 + 2 * 8 * n1 + mesh_b)):
+                t = wall(fn)
+                el[name] = {"us": t * 1e6, "gbs": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak}
+            el["note"] = "per-GPU figures on the local part of the numRefs-%d problem (%d P0 / %d P1 dofs per rank); wall time of the public call" % (args.admm_refs, n0, n1)
+            extra["elementwise_roofline"] = el
+        except Exception as exc:                                   # never lose the line over a secondary figure
+            extra["elementwise_roofline"] = {"error": repr(exc)[:300]}
         del p4
         extra["admm_refs%d" % args.admm_refs] = a4
         if world > 1 and a4["decomposed"]:
