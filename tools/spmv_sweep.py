@@ -7,7 +7,7 @@ from admm_optim_b200.driver import ObstacleOptim
 import bench
 
 refs = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1]
 waves = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 4, 8]
 stream = torch.cuda.Stream()
 ug = ug4.Backend(device=0, stream=stream.cuda_stream)
