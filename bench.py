@@ -155,6 +155,18 @@ def vcycle_dram_bytes(dim, levels, pre=3, post=3):
 # ------------------------------------------------------------------------------------------------
 # CPU oracle legs (cpu_baseline / --impl reference)
 # ------------------------------------------------------------------------------------------------
+def common_config(refs):
+    """`config` is the same object in both arms (the driver compares them): workload, size and the conventions of either arm."""
+    dofs = global_counts(refs)[-1][0] * 3
+    return {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (refs, dofs),
+            "numRefs": refs, "dofs": dofs,
+            "l2": "GPU arm: L2 flushed (256 MB write) between timed iterations; the working set itself is L2-sized",
+            "smoother": "GPU arm: Chebyshev(3)-Jacobi (stated equivalent of the reference's sequential Gauss-Seidel, DESIGN.md); "
+                        "CPU arm: Gauss-Seidel inside each thread's row block, Jacobi between blocks (UG4 under mpirun)",
+            "multi_gpu": "a problem of this size is below the agglomeration threshold and runs undivided on every rank (no communication); the "
+                         "decomposed path is measured by the legs admm_refs4 / admm_2d_refs7 / roofline of the GPU arm"}
+
+
 def cpu_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -233,10 +245,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, global_counts(args.refs)[-1][0] * 3),
-                       "numRefs": args.refs, "dofs": global_counts(args.refs)[-1][0] * 3, "note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % threads,
-                       "host_cores_available": cores, "threads_used": threads,
-                       "thread_calibration_s": {str(k): round(x, 4) for k, x in calib.items()}, "bicgstab_its_per_step": its / args.steps},
+            "config": common_config(args.refs),
+            "arm": {"note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % threads,
+                    "host_cores_available": cores, "threads_used": threads,
+                    "thread_calibration_s": {str(k): round(x, 4) for k, x in calib.items()}, "bicgstab_its_per_step": its / args.steps},
             "cpu_baseline": {"value": v, "unit": "iters/s", "cores": threads, "kind": "port", "host_cores_available": cores,
                              "sample": "%d full ADMM iterations of the same workload (C/OpenMP solve path + C assembly, NumPy vector algebra) on %d of %d host "
                                        "threads -- the fastest count of a calibration over all / half / quarter ... / one" % (args.steps, threads, cores)},
@@ -258,8 +270,8 @@ def cpu_baseline_sample(refs):
         out[label] = json.loads(r.stdout.strip().splitlines()[-1])
     b = out["best"]
     cb = dict(b["cpu_baseline"])
-    cb.update({"value_1_thread": out["one"]["value"], "note": CPU_NOTE, "thread_calibration_s": b["config"]["thread_calibration_s"],
-               "bicgstab_its_per_step": b["config"]["bicgstab_its_per_step"], "bicgstab_its_per_step_1_thread": out["one"]["config"]["bicgstab_its_per_step"]})
+    cb.update({"value_1_thread": out["one"]["value"], "note": CPU_NOTE, "thread_calibration_s": b["arm"]["thread_calibration_s"],
+               "bicgstab_its_per_step": b["arm"]["bicgstab_its_per_step"], "bicgstab_its_per_step_1_thread": out["one"]["arm"]["bicgstab_its_per_step"]})
     return cb
 
 
@@ -590,17 +602,13 @@ def run_b200(args):
     e2e_v = args.steps / (ms_e2e * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3d_admm.lua ADMM loop (3d_admm.lua:875-1304) on box_3D_elongated.ugx, numRefs=%d, %d deformation DoFs, synthetic J'" % (args.refs, ndofs),
-                       "numRefs": args.refs, "dofs": ndofs,
-                       "parallelism": ("%d GPUs; this %d-DoF problem is below the agglomeration threshold and runs undivided (no communication); "
-                                       "admm_refs4 / admm_2d_refs7 / the roofline leg are domain-decomposed" % (world, ndofs)) if world > 1 and not headline_decomposed
-                                      else ("domain decomposition x%d" % world if world > 1 else "1 GPU"),
-                       "l2": "L2 flushed (256 MB write) between timed iterations; working set itself is L2-sized",
-                       "smoother": "Chebyshev(3)-Jacobi (stated equivalent of the reference's sequential GS, DESIGN.md)",
-                       "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
+            "config": common_config(args.refs),
+            "arm": {"parallelism": ("%d GPUs, headline undivided" % world if not headline_decomposed else "domain decomposition x%d" % world) if world > 1 else "1 GPU",
+                    "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
             "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk, "parity": parity}
+            "gpu_launches": launches, "clocks": clk, "parity": parity,
+            "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps}
     if roof:
         line["roofline"] = roof
     line.update(extra)
