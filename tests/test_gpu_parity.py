@@ -516,3 +516,67 @@ def test_gpu_trace_files_match_golden(gpu_backend, tmp_path):
                     assert abs(u - v) <= 1, (n, x, y)               # BiCGStab counts: +-1 (summation order near the tolerance)
                 else:
                     assert abs(u - v) <= 1e-8 * max(abs(v), 1e-3) or abs(v) < 1e-9, (n, u, v)
+
+
+@pytest.mark.parametrize("dim,grid,refs", CASES)
+def test_row_owner_assembly_matches_atomic_scatter_and_is_reproducible(gpu_backend, monkeypatch, dim, grid, refs):
+    """The default Hessian assembly (row-owner gather: no atomics, no memset) against the per-element atomic scatter it replaced:
+    entrywise equal to rounding; two row-owner assemblies of the same state are bitwise identical."""
+    from admm_optim_b200.driver import ObstacleOptim
+    monkeypatch.setenv("ADMM_B200_NO_CACHE", "1")            # every request assembles
+    g = ObstacleOptim(gpu_backend, dim, numRefs=refs, grid=grid).setup()
+    n = g.DeformationSpace_ApproxSpace.num_dofs()
+    g.u.from_numpy(0.02 * np.random.default_rng(4).standard_normal(n))
+    DD = g.DeformationEquation_DomainDisc
+    DD.adjust_solution(g.u)
+    g.Hessian_ElemDisc.set_lambda_vol(0.3)
+    g.Hessian_ElemDisc.set_lambda_barycenter(-0.2, 0.1, 0.05 if dim == 3 else 0.0)
+    mats = {}
+    try:
+        for name, variant in (("rows", 0), ("rows_again", 0), ("atomic", 1)):
+            gpu_backend.set_tuning("assembly_variant", variant)
+            DD.assemble_jacobian(g.A_u_Hessian, g.u)
+            mats[name] = g.A_u_Hessian.to_scipy().tocsr()
+    finally:
+        gpu_backend.set_tuning("assembly_variant", 0)
+    assert np.array_equal(mats["rows"].data, mats["rows_again"].data)                       # fixed summation order
+    assert abs(mats["rows"] - mats["atomic"]).max() <= 1e-12 * abs(mats["atomic"]).max()
+
+
+def test_aliased_import_is_never_served_from_the_hessian_cache(gpu_backend):
+    """ab_vector_device_ptr hands out the device pointer of u: its contents may then change without a version bump.  With
+    multipliers the Hessian depends on u, so a second assemble_jacobian must re-assemble instead of reusing the cached operator."""
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    g, o = _pair(gpu_backend, 3, GRID3D, 1)
+    u0, _, _ = _seed_state(g, o, seed=9, amp=0.01)
+    u0 = g.u.to_numpy()
+    for p in (g, o):
+        p.Hessian_ElemDisc.set_lambda_vol(0.3)
+        p.Hessian_ElemDisc.set_lambda_barycenter(0.1, -0.1, 0.05)
+    DD = g.DeformationEquation_DomainDisc
+    DD.assemble_jacobian(g.A_u_Hessian, g.u)
+    A1 = g.A_u_Hessian.to_scipy().tocsr()
+    ptr, n = g.u.device_ptr()                                # aliased from here on
+    mutated = False
+    try:                                                     # write through the raw pointer, behind the library's back
+        import torch
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        gpu_backend.synchronize()
+        t = torch.as_tensor(_View(), device="cuda")
+        t.mul_(2.0)
+        torch.cuda.synchronize()
+        mutated = bool(np.allclose(g.u.to_numpy(), 2.0 * u0, rtol=0, atol=1e-15))    # the view really aliased the vector
+    except Exception:
+        pass
+    l0 = gpu_backend.launch_count()
+    DD.assemble_jacobian(g.A_u_Hessian, g.u)
+    assert gpu_backend.launch_count() > l0                   # not answered from the cache
+    if mutated:
+        o.u.from_numpy(2.0 * u0)
+        o.DeformationEquation_DomainDisc.assemble_jacobian(o.A_u_Hessian, o.u)
+        A2, B2 = g.A_u_Hessian.to_scipy().tocsr(), o.A_u_Hessian.to_scipy().tocsr()
+        assert abs(A2 - B2).max() <= 1e-12 * abs(B2).max()
+        assert abs(A2 - A1).max() > 1e-6 * abs(A1).max()     # and it really is a different operator
