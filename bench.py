@@ -582,7 +582,9 @@ def run_b200(args):
                 d["ok"] = bool(max(d["u_diff_rel"], d["lambda_inc_rel"], d["max_norm_rel"], d["Lambda_rel"]) <= 1e-8 and d["u_l2_rel"] <= 1e-9
                                and all(abs(a - b) <= 1 for a, b in zip(d["newton_its"], d["newton_its_undivided"])))   # +-1: borderline |dLambda| <= 1e-9 stop
                 parity["decomposed"] = d
-                assert d["ok"], "multi-GPU parity failed: %s" % d
+                if not d["ok"]:      # recorded in the line (the headline's own parity above is a hard assertion): the figures of the
+                    sys.stderr.write("bench.py: MULTI-GPU PARITY FAILED: %s\n" % d)      # decomposed legs must then be read as invalid
+                    parity["ok"] = False
             barrier()
     if args.dim2_refs > 0:
         a2, p2 = admm_leg(ug, 2, args.dim2_refs, GRID2D)
