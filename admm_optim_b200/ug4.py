@@ -716,6 +716,11 @@ class Backend:
                 I = dom._iface[level]
                 offb, slotb, bpos, brow, mult = P.match_blocks(rp, ci, I["neigh"], I["offsets"], I["idx"], self.rank, self._gather)
                 del rp, ci
+                # both sides of every pair must have found the same number of common blocks (they exchange exactly that many
+                # values at solver:init); every rank sees the whole table, so all ranks take the same decision
+                counts = self._gather({int(q): int(offb[n + 1] - offb[n]) for n, q in enumerate(I["neigh"])})
+                if any(c != counts[q].get(r) for r, tab in enumerate(counts) for q, c in tab.items()):
+                    raise AdmmB200Error("shared-block lists of level %d are not symmetric between the ranks" % level)
                 call("ab_domain_set_block_interface", dom.h, level, len(I["neigh"]), _ip(I["neigh"]) if len(I["neigh"]) else None, _ip(offb),
                      _ip(slotb) if len(slotb) else None, len(bpos), _ip(bpos) if len(bpos) else None, _ip(brow) if len(brow) else None,
                      _ip(mult) if len(mult) else None)
