@@ -33,25 +33,58 @@ static inline uint64_t ekey(int32_t a, int32_t b) {
     return ((uint64_t)lo << 32) | hi;
 }
 
+// Unique edges (lo, hi), sorted lexicographically.  Bucket sort by the lower vertex instead of one comparison sort over all
+// 6 ne element edges (239 M keys at level 5): count per lo, scatter the hi ends into the buckets (order inside a bucket is
+// irrelevant), then sort + unique every bucket (a few dozen entries) and compact.  The result does not depend on the scatter order.
 void ensure_edges(HostLevel& L) {
     if (L.have_edges) return;
     const int nen = L.dim + 1, nle = L.dim == 3 ? 6 : 3;
-    std::vector<uint64_t> keys((size_t)L.ne * nle);
+    const int nv = L.nv;
+    const int64_t ne = L.ne;
+    std::vector<int64_t> start((size_t)nv + 1, 0);
+    {
+        std::vector<int32_t> cnt((size_t)nv, 0);
 #pragma omp parallel for schedule(static)
-    for (int64_t e = 0; e < L.ne; ++e) {
-        const int32_t* v = &L.elems[(size_t)e * nen];
-        for (int k = 0; k < nle; ++k) {
-            const int* le = L.dim == 3 ? LE3[k] : LE2[k];
-            keys[(size_t)e * nle + k] = ekey(v[le[0]], v[le[1]]);
+        for (int64_t e = 0; e < ne; ++e) {
+            const int32_t* v = &L.elems[(size_t)e * nen];
+            for (int k = 0; k < nle; ++k) {
+                const int* le = L.dim == 3 ? LE3[k] : LE2[k];
+                const int32_t a = v[le[0]], b = v[le[1]];
+                __atomic_fetch_add(&cnt[a < b ? a : b], 1, __ATOMIC_RELAXED);
+            }
+        }
+        for (int v = 0; v < nv; ++v) start[v + 1] = start[v] + cnt[v];
+    }
+    std::vector<int32_t> his((size_t)start[nv]);
+    {
+        std::vector<int32_t> fill((size_t)nv, 0);
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < ne; ++e) {
+            const int32_t* v = &L.elems[(size_t)e * nen];
+            for (int k = 0; k < nle; ++k) {
+                const int* le = L.dim == 3 ? LE3[k] : LE2[k];
+                const int32_t a = v[le[0]], b = v[le[1]];
+                const int32_t lo = a < b ? a : b, hi = a < b ? b : a;
+                his[(size_t)(start[lo] + __atomic_fetch_add(&fill[lo], 1, __ATOMIC_RELAXED))] = hi;
+            }
         }
     }
-    AB_SORT(keys.begin(), keys.end());
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    L.edges.resize(keys.size() * 2);
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)keys.size(); ++i) {
-        L.edges[2 * i] = (int32_t)(keys[i] >> 32);
-        L.edges[2 * i + 1] = (int32_t)(keys[i] & 0xffffffffu);
+    std::vector<int64_t> ustart((size_t)nv + 1, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int v = 0; v < nv; ++v) {
+        int32_t* b = his.data() + start[v];
+        int32_t* e = his.data() + start[v + 1];
+        std::sort(b, e);
+        ustart[v + 1] = std::unique(b, e) - b;
+    }
+    for (int v = 0; v < nv; ++v) ustart[v + 1] += ustart[v];
+    L.edges.resize((size_t)ustart[nv] * 2);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int v = 0; v < nv; ++v) {
+        const int32_t* b = his.data() + start[v];
+        const int64_t n = ustart[v + 1] - ustart[v];
+        int32_t* out = L.edges.data() + 2 * ustart[v];
+        for (int64_t i = 0; i < n; ++i) { out[2 * i] = v; out[2 * i + 1] = b[i]; }
     }
     L.have_edges = true;
 }
