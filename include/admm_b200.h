@@ -82,7 +82,8 @@ int ab_domain_set_interface(ab_domain* dom, int level, int nneigh, const int32_t
  * as one global hierarchy.  Every rank states the level; rank 0 also passes `coarse` (the GLOBAL grid refined
  * gather_level times, same context) and, concatenated over the ranks 0..nranks-1: the number of level-`gather_level`
  * vertices / matrix blocks of each rank, the local -> global vertex ids and the local block -> global block positions
- * (BSR order of ab_domain_level_pattern).  Other ranks pass NULL for all of them.                                 */
+ * (BSR order of ab_domain_level_pattern).  Other ranks pass NULL for all of them.  `coarse` stays owned by the caller
+ * and must outlive `dom` (the hierarchies of `dom` keep pointers into its level structures).                       */
 int ab_domain_set_gather(ab_domain* dom, int gather_level, ab_domain* coarse, const int32_t* nv_per_rank, const int32_t* l2g_cat,
                          const int64_t* nblk_per_rank, const int32_t* gpos_cat);
 /* Matrix blocks shared with neighbour ranks on a decomposed level (both vertices on the interface, block present on both sides), in
