@@ -181,27 +181,27 @@ CPU_NOTE = ("UG4 cannot be built or run here (no UG4 / plugins / Lua in the imag
             "the ratio of the two arms is 'B200 path vs this CPU port', not 'vs UG4'")
 
 
-def oracle_problem(refs, threads=None):
+def oracle_problem(refs, threads=None, smoother="gs"):
     from admm_optim_b200.driver import ObstacleOptim
     from oracle import ug4_np
     # Gauss-Seidel is what the reference's descriptor asks for (u3:16): sequential lexicographic on one thread, block-Jacobi across
     # threads otherwise (UG4's behaviour under mpirun).  fast_assembly / c_solver: element loops and the whole
     # solver:init + solver:apply path run compiled (oracle_kernels.c, solver_c.c); what stays in NumPy is vector algebra and the norms
     threads = cpu_cores() if threads is None else threads
-    ug = ug4_np.Backend(smoother="gs", threads=threads, fast_assembly=True, c_solver=True)
+    ug = ug4_np.Backend(smoother=smoother, threads=threads, fast_assembly=True, c_solver=True)
     p = ObstacleOptim(ug, 3, numRefs=refs, grid=GRID3D).setup()
     p.set_sensitivity(p.synthetic_sensitivity(0.5))
     p.begin_step()
     return p
 
 
-def pick_threads(refs):
+def pick_threads(refs, smoother="gs"):
     """The thread count a CPU user would run with: one solver:init + solver:apply of the workload timed on all cores, half, a
     quarter ... one; the fastest wins (hyper-threads and neighbours on a shared host make 'all' not always the best)."""
     import numpy as np
     cores = cpu_cores()
     cands = sorted({max(1, cores >> k) for k in range(0, 5)} | {1}, reverse=True)
-    p = oracle_problem(refs, cores)
+    p = oracle_problem(refs, cores, smoother)
     DD = p.DeformationEquation_DomainDisc
     DD.assemble_jacobian(p.A_u_Hessian, p.u)
     p.Lu.from_numpy(np.random.default_rng(5).standard_normal(p.u.v.size), 2)
@@ -230,8 +230,8 @@ def run_reference(args):
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
     import numpy as np  # noqa: F401
     cores = cpu_cores()
-    threads, calib = (args.threads, {}) if args.threads > 0 else pick_threads(args.refs)
-    p = oracle_problem(args.refs, threads)
+    threads, calib = (args.threads, {}) if args.threads > 0 else pick_threads(args.refs, args.smoother)
+    p = oracle_problem(args.refs, threads, args.smoother)
     for _ in range(args.warmup):
         p.admm_iteration()
     t0 = time.perf_counter()
@@ -246,7 +246,7 @@ def run_reference(args):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": common_config(args.refs),
-            "arm": {"note": CPU_NOTE, "smoother": "Gauss-Seidel (block-Jacobi across %d threads)" % threads,
+            "arm": {"note": CPU_NOTE, "smoother": ("Gauss-Seidel (block-Jacobi across %d threads)" % threads) if args.smoother == "gs" else "Chebyshev(3)-Jacobi (the GPU arm's smoother)",
                     "host_cores_available": cores, "threads_used": threads,
                     "thread_calibration_s": {str(k): round(x, 4) for k, x in calib.items()}, "bicgstab_its_per_step": its / args.steps},
             "cpu_baseline": {"value": v, "unit": "iters/s", "cores": threads, "kind": "port", "host_cores_available": cores,
@@ -260,7 +260,7 @@ def cpu_baseline_sample(refs):
     """cpu_baseline of the B200 line: the reference arm in a child process (its OpenMP runtime needs its own wait policy; this
     process has torch's runtime loaded), two timed iterations on the calibrated thread count and one on a single thread."""
     out = {}
-    for label, extra in (("best", []), ("one", ["--threads", "1"])):
+    for label, extra in (("best", []), ("one", ["--threads", "1"]), ("cheb", ["--smoother", "cheb"])):
         env = dict(os.environ, OMP_WAIT_POLICY="active")
         for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS"):
             env.pop(k, None)
@@ -270,7 +270,9 @@ def cpu_baseline_sample(refs):
         out[label] = json.loads(r.stdout.strip().splitlines()[-1])
     b = out["best"]
     cb = dict(b["cpu_baseline"])
-    cb.update({"value_1_thread": out["one"]["value"], "note": CPU_NOTE, "thread_calibration_s": b["arm"]["thread_calibration_s"],
+    cb.update({"value_1_thread": out["one"]["value"], "value_chebyshev_smoother": out["cheb"]["value"], "threads_chebyshev_smoother": out["cheb"]["arm"]["threads_used"],
+               "bicgstab_its_per_step_chebyshev_smoother": out["cheb"]["arm"]["bicgstab_its_per_step"],
+               "note": CPU_NOTE, "thread_calibration_s": b["arm"]["thread_calibration_s"],
                "bicgstab_its_per_step": b["arm"]["bicgstab_its_per_step"], "bicgstab_its_per_step_1_thread": out["one"]["arm"]["bicgstab_its_per_step"]})
     return cb
 
@@ -635,6 +637,7 @@ def main():
     ap.add_argument("--roofline-refs", type=int, default=5, help="refinement level of the SpMV / V-cycle / solve roofline leg (0 = skip); 5 = 20.3 M DoFs, 7.6 GB matrix")
     ap.add_argument("--admm-refs", type=int, default=4, help="refinement of the larger 3D ADMM-iteration leg (BASELINE.json configs[2]: numRefs 4); 0 = skip")
     ap.add_argument("--dim2-refs", type=int, default=7, help="refinement of the 2D leg (BASELINE.json configs[3]: refined.ugx numRefs 7); 0 = skip")
+    ap.add_argument("--smoother", default="gs", choices=["gs", "cheb"], help="reference arm: GMG smoother (gs = what the reference asks for; cheb = the GPU arm's)")
     ap.add_argument("--threads", type=int, default=0, help="reference arm: host threads (0 = calibrate: all / half / ... / one, fastest wins)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
