@@ -278,6 +278,9 @@ def test_bench_algorithmic_byte_formulas_match_survey():
     assert bench.spmv_bytes(3, *lv[5]) == 7986164224
     assert bench.vcycle_bytes(3, lv[:5]) == 8183626352
     assert abs(bench.vcycle_bytes(3, lv) / 64.8e9 - 1) < 0.005
+    # bytes the V(3,3) kernels really stream (6 matrix passes per level): within 10 % of the ncu DRAM sum of one cycle at numRefs 5
+    # (62.03 GB read + 2.11 GB written, profiles/r02_vcycle_L5_dram_launches.csv) and below the 7-pass SURVEY figure
+    assert abs(bench.vcycle_dram_bytes(3, lv) / 64.13e9 - 1) < 0.10 and bench.vcycle_dram_bytes(3, lv) < bench.vcycle_bytes(3, lv)
     l2 = bench.global_counts(3, 2)
     assert l2[3] == (9008, 9008 + 2 * 26672)
     assert abs(bench.spmv_bytes(2, *l2[3]) / 2.57e6 - 1) < 0.01
