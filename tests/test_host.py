@@ -410,3 +410,20 @@ def test_ug4_plugin_shim_registers_the_names_the_scripts_call(tmp_path):
         src = open(os.path.join(ref, "3d_admm.lua")).read()
         for name in SHIM_ELEMDISC_CLASSES + SHIM_FREE_FUNCTIONS:
             assert re.search(r"\b%s\(" % name, src) or re.search(r"\b%s\(" % name, open(os.path.join(ref, "2d_admm.lua")).read()), name
+
+
+def test_bench_b200_arm_dry_run_produces_the_full_line():
+    """Control flow of bench.py's B200 arm without a GPU (tools/bench_dryrun.py: torch.cuda and the CUDA backend replaced by
+    stand-ins on top of the oracle): every leg runs and the JSON line carries every key of the contract and of DESIGN.md section 8.
+    Checks the Python of the arm only -- the numbers are meaningless here."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "e2e", "gpu_launches", "clocks", "roofline", "parity", "vcycle_frac_effective", "vcycle_frac_dram", "solve_ms",
+                "gmg_init_ms", "assemble_ms", "admm_refs1", "admm_2d_refs2", "elementwise_roofline", "bicgstab_its_per_step"):
+        assert key in line, key
+    assert line["parity"]["ok"] and "workload" in line["config"] and "error" not in line["elementwise_roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"]) and line["e2e"]["h2d_bytes_per_step"] > 0
