@@ -427,3 +427,24 @@ def test_bench_b200_arm_dry_run_produces_the_full_line():
     assert line["parity"]["ok"] and "workload" in line["config"] and "error" not in line["elementwise_roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"]) and line["e2e"]["h2d_bytes_per_step"] > 0
+
+
+def test_bench_b200_arm_multi_rank_dry_run_gloo_world_size_2():
+    """The multi-rank control flow of bench.py (rank bookkeeping, barriers, max-over-ranks timing, the decomposed legs' extra keys, the
+    decomposed-vs-undivided parity block on rank 0, the common exit) on 2 gloo ranks with the stand-ins of tools/bench_dryrun.py
+    (DRYRUN_DECOMPOSED=1 makes the larger legs claim to be decomposed).  Rank 0 alone prints the line; both ranks exit 0."""
+    import json
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29692", WORLD_SIZE="2", DRYRUN_DECOMPOSED="1")
+    args = ["--gpus", "2", "--refs", "0", "--roofline-refs", "1", "--admm-refs", "1", "--dim2-refs", "1", "--steps", "1", "--warmup", "1"]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py")] + args, env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=900)
+        assert p.returncode == 0, err[-3000:]
+        outs.append(out.strip())
+    assert outs[1] == ""
+    line = json.loads(outs[0].splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["parity"]["ok"] and line["parity"]["decomposed"]["ok"]
+    assert line["admm_refs1"]["decomposed"] and line["roofline_decomposed"] and "spmv_with_exchange_ms" in line
+    assert line["parity"]["decomposed"]["bicgstab_its"] == line["parity"]["decomposed"]["bicgstab_its_undivided"]

@@ -56,9 +56,16 @@ class _Solver(ug4_np.BiCGStabGMG):
         self.desc = _Desc(desc)
 
 
+DECOMPOSED = os.environ.get("DRYRUN_DECOMPOSED") == "1"      # pretend the larger legs are domain-decomposed (multi-rank control flow)
+
+
 class _Domain(ug4_np.Domain):
-    decomposed = False
-    _dist = None
+    @property
+    def decomposed(self):       # only the legs above the headline size pretend, and only on the "distributed" backend
+        return DECOMPOSED and getattr(self, "_backend_distributed", False) and self.top.nv > 1000
+    @property
+    def _dist(self):
+        return dict(gather_level=0) if self.decomposed else None
     def p2p_status(self): return dict(connected=False, error=0)
     def get_level(self, level, elems=True):
         l = self.levels[level]
@@ -69,10 +76,14 @@ class FakeBackend(ug4_np.Backend):
     name = "dryrun"
     def __init__(self, device=0, stream=None, distributed=False):
         super().__init__(smoother="cheb")
-        self.rank, self.nranks = 0, 1
+        self.rank, self.nranks = (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))) if distributed else (0, 1)
+        self._distributed = bool(distributed)
         self.util.solver.CreateSolver = lambda desc: _Solver(self, desc)
         self._launches = 0
-    def Domain(self): return _Domain()
+    def Domain(self):
+        d = _Domain()
+        d._backend_distributed = self._distributed
+        return d
     def launch_count(self):
         self._launches += 1
         return self._launches
@@ -87,6 +98,10 @@ FakeBackend.AssembledLinearOperator = lambda self, dd: _Op(dd)
 
 import admm_optim_b200.ug4 as ug4   # noqa: E402  (host-only import: the shared library is not touched)
 ug4.Backend = FakeBackend
+
+import torch.distributed as _dist   # noqa: E402
+_init = _dist.init_process_group
+_dist.init_process_group = lambda backend=None, **kw: _init("gloo")      # the multi-rank flow on CPU: gloo instead of nccl
 
 import bench   # noqa: E402
 
