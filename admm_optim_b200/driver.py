@@ -519,6 +519,16 @@ class ObstacleOptim:
         self.write_newton_traces()
         return self.admm_trace
 
+    def write_deformation(self, directory="."):
+        """`if bOutputMesh then ... vtkWriter:select_nodal("u1,u2,u3","u"); vtkWriter:print("u", u, step+1, step+1, false)` (3d:1400-1406):
+        the accepted deformation of the step as <directory>/u_t<step+1>.vtu on the current coordinates."""
+        import os
+        from .vtk import VTKOutput
+        w = self.ug.VTKOutput() if hasattr(self.ug, "VTKOutput") else VTKOutput(self.ug)
+        w.clear_selection()
+        w.select_nodal(self.ucmps, "u")
+        return w.print(os.path.join(directory, "u"), self.u, self.step + 1, self.step + 1, False)
+
     def write_newton_traces(self):
         """3d:1307-1311: gnuplot.write_data of the Newton tables of the last ADMM iteration (only with -bNewtonOutput true)."""
         if not (self.newton_output and self.trace_dir is not None and self.vNS):

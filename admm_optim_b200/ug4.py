@@ -812,6 +812,11 @@ class Backend:
             return lambda fcts, subsets: ElemDisc(self, name, fcts, subsets)
         raise AttributeError(name)
 
+    # -- output (VTKOutput on deformation-space functions, 3d_admm.lua:716,1400-1406) ---------------
+    def VTKOutput(self):
+        from .vtk import VTKOutput
+        return VTKOutput(self)
+
     # -- solvers --------------------------------------------------------------------------------
     def CG(self):
         return CG(self)

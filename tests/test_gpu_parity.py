@@ -580,3 +580,23 @@ def test_aliased_import_is_never_served_from_the_hessian_cache(gpu_backend):
         A2, B2 = g.A_u_Hessian.to_scipy().tocsr(), o.A_u_Hessian.to_scipy().tocsr()
         assert abs(A2 - B2).max() <= 1e-12 * abs(B2).max()
         assert abs(A2 - A1).max() > 1e-6 * abs(A1).max()     # and it really is a different operator
+
+
+def test_vtk_output_of_a_device_resident_grid_function(gpu_backend, tmp_path):
+    """VTKOutput on a grid function that lives in HBM (3d_admm.lua:1400-1406): current coordinates (after
+    TransformDomainByDisplacement), connectivity and nodal values come back exactly."""
+    from admm_optim_b200 import vtk
+    from admm_optim_b200.driver import ObstacleOptim
+    p = ObstacleOptim(gpu_backend, 3, numRefs=1, grid=GRID3D).setup()
+    n = p.DeformationSpace_ApproxSpace.num_dofs()
+    p.u.from_numpy(1e-3 * np.random.default_rng(6).standard_normal(n))
+    p.DeformationEquation_DomainDisc.adjust_solution(p.u)
+    gpu_backend.TransformDomainByDisplacement(p.u, p.ucmps)
+    w = gpu_backend.VTKOutput()
+    w.clear_selection()
+    w.select_nodal(p.ucmps, "u")
+    path = w.print(str(tmp_path / "u"), p.u, 1, 1, False)
+    back = vtk.read_vtu(path)
+    lv = p.dom.get_level(p.dom.num_levels() - 1)
+    assert np.array_equal(back["points"], lv["xyz"]) and np.array_equal(back["connectivity"], lv["elems"])
+    assert np.array_equal(back["point_data"]["u"], p.u.to_numpy().reshape(-1, 3))

@@ -448,3 +448,44 @@ def test_bench_b200_arm_multi_rank_dry_run_gloo_world_size_2():
     assert line["n_gpus"] == 2 and line["parity"]["ok"] and line["parity"]["decomposed"]["ok"]
     assert line["admm_refs1"]["decomposed"] and line["roofline_decomposed"] and "spmv_with_exchange_ms" in line
     assert line["parity"]["decomposed"]["bicgstab_its"] == line["parity"]["decomposed"]["bicgstab_its_undivided"]
+
+
+def test_vtu_writer_round_trip(tmp_path):
+    """admm_optim_b200/vtk.py (VTKOutput of deformation-space functions, 3d_admm.lua:1400-1406): an XML UnstructuredGrid with the
+    current coordinates, tetrahedra / triangles and nodal vectors padded to 3 components; read back exactly."""
+    from admm_optim_b200 import vtk
+    rng = np.random.default_rng(0)
+    for dim in (2, 3):
+        xyz = rng.standard_normal((7, dim))
+        elems = np.array([[0, 1, 2, 3][:dim + 1], [3, 4, 5, 6][:dim + 1]], np.int32)
+        u = rng.standard_normal((7, dim))
+        path = str(tmp_path / ("u%d.vtu" % dim))
+        vtk.write_vtu(path, xyz, elems, {"u": u, "s": u[:, 0]})
+        back = vtk.read_vtu(path)
+        assert np.array_equal(back["points"][:, :dim], xyz) and np.all(back["points"][:, dim:] == 0)
+        assert np.array_equal(back["connectivity"], elems) and list(back["offsets"]) == [dim + 1, 2 * (dim + 1)]
+        assert set(back["types"]) == {5 if dim == 2 else 10}
+        assert np.array_equal(back["point_data"]["u"][:, :dim], u) and back["point_data"]["u"].shape[1] == 3
+        assert np.array_equal(back["point_data"]["s"][:, 0], u[:, 0])
+
+
+def test_vtkoutput_selection_and_naming_on_the_oracle_backend(tmp_path):
+    """vtkWriter:clear_selection(); :select_nodal("u1,u2,u3","u"); :print("u", u, step, step, false) -- 3d_admm.lua:1400-1406."""
+    from admm_optim_b200 import vtk
+    from admm_optim_b200.driver import ObstacleOptim
+    from oracle import ug4_np
+    ug = ug4_np.Backend()
+    p = ObstacleOptim(ug, 3, numRefs=0, grid=GRID3D).setup()
+    p.u.from_numpy(np.random.default_rng(2).standard_normal(p.u.v.size))
+    w = vtk.VTKOutput(ug)
+    w.clear_selection()
+    w.select_nodal(p.ucmps, "u")
+    path = w.print(str(tmp_path / "u"), p.u, 3, 3, False)
+    assert os.path.basename(path) == "u_t0003.vtu"
+    back = vtk.read_vtu(path)
+    assert np.array_equal(back["points"], p.dom.top.xyz) and np.array_equal(back["connectivity"], p.dom.top.elems)
+    assert np.array_equal(back["point_data"]["u"], p.u.to_numpy().reshape(-1, 3))
+    w.clear_selection()
+    w.select_nodal("u2", "uy")
+    back = vtk.read_vtu(w.print(str(tmp_path / "uy"), p.u))
+    assert np.array_equal(back["point_data"]["uy"][:, 0], p.u.to_numpy().reshape(-1, 3)[:, 1])
