@@ -204,6 +204,27 @@ def block_positions(local_elems, nv_local: int, l2g, global_keys, nv_global: int
     return pos.astype(np.int32)
 
 
+def csr_keys(rowptr, colidx, nv: int):
+    """The keys of pattern_keys from a BSR pattern (ab_domain_level_pattern): already sorted, no np.unique needed."""
+    rowptr = np.asarray(rowptr, np.int64)
+    rows = np.repeat(np.arange(len(rowptr) - 1, dtype=np.int64), np.diff(rowptr))
+    return rows * nv + np.asarray(colidx, np.int64)
+
+
+def block_positions_csr(rowptr_l, colidx_l, l2g, rowptr_g, colidx_g):
+    """block_positions from the two BSR patterns the native side builds (same result, a fraction of the host time)."""
+    l2g = np.asarray(l2g, np.int64)
+    nvg = len(rowptr_g) - 1
+    rowptr_l = np.asarray(rowptr_l, np.int64)
+    rows = np.repeat(np.arange(len(rowptr_l) - 1, dtype=np.int64), np.diff(rowptr_l))
+    gk = l2g[rows] * nvg + l2g[np.asarray(colidx_l, np.int64)]
+    gkeys = csr_keys(rowptr_g, colidx_g, nvg)
+    pos = np.searchsorted(gkeys, gk)
+    if len(gk) and (pos.max(initial=0) >= len(gkeys) or not np.array_equal(gkeys[pos], gk)):
+        raise ValueError("a local matrix block has no global counterpart")
+    return pos.astype(np.int32)
+
+
 # ------------------------------------------------------------------------------------------------
 # shared matrix blocks of a decomposed level (exact Gershgorin bound of the additive operators)
 # ------------------------------------------------------------------------------------------------

@@ -93,6 +93,14 @@ class Domain(_Handle):
         call("ab_domain_level_info", self.h, level, *[C.byref(x) for x in v])
         return dict(dim=v[0].value, nv=v[1].value, ne=v[2].value, nedges=v[3].value, nv_coarse=v[4].value)
 
+    def level_pattern(self, level):
+        """(rowptr, colidx) of the P1 block pattern of a grid level, BSR order (rows and columns ascending)."""
+        info = self.level_info(level)
+        rp, ci = np.empty(info["nv"] + 1, np.int32), np.empty(info["nv"] + 2 * info["nedges"], np.int32)
+        nn = C.c_int64()
+        call("ab_domain_level_pattern", self.h, level, C.byref(nn), _ip(rp), _ip(ci))
+        return rp, ci[:nn.value]
+
     def get_level(self, level, elems=True):
         i = self.level_info(level)
         d, nv, ne, nvc = i["dim"], i["nv"], i["ne"], i["nv_coarse"]
@@ -709,10 +717,7 @@ class Backend:
         dom._biface = {}
         if os.environ.get("ADMM_B200_EXACT_GERSHGORIN", "1") != "0":
             for level in range(lg + 1, dom.num_levels()):
-                info = dom.level_info(level)
-                rp, ci = np.empty(info["nv"] + 1, np.int32), np.empty(info["nv"] + 2 * info["nedges"], np.int32)
-                nn = C.c_int64()
-                call("ab_domain_level_pattern", dom.h, level, C.byref(nn), _ip(rp), _ip(ci))
+                rp, ci = dom.level_pattern(level)
                 I = dom._iface[level]
                 offb, slotb, bpos, brow, mult = P.match_blocks(rp, ci, I["neigh"], I["offsets"], I["idx"], self.rank, self._gather)
                 del rp, ci
@@ -733,11 +738,11 @@ class Backend:
         for level in range(1, lg + 1):
             gl, ll = cdom.get_level(level, elems=False), dom.get_level(level, elems=False)
             l2g = P.propagate_l2g(l2g, gl["nv_coarse"], gl["parent_a"], gl["parent_b"], ll["parent_a"], ll["parent_b"])
-        glev, llev = cdom.get_level(lg), dom.get_level(lg)
+        glev, llev = cdom.get_level(lg, elems=False), dom.get_level(lg, elems=False)
         if not np.array_equal(glev["xyz"][l2g], llev["xyz"]):
             raise AdmmB200Error("vertical interface: local and global refinement disagree on level %d" % lg)
         nvg = len(glev["xyz"])
-        gpos = P.block_positions(llev["elems"], len(llev["xyz"]), l2g, P.pattern_keys(glev["elems"], nvg), nvg)
+        gpos = P.block_positions_csr(*dom.level_pattern(lg), l2g, *cdom.level_pattern(lg))
         mine = (np.ascontiguousarray(l2g, np.int32), gpos)
         everyone = self._gather(mine)
         dom._gather = dict(level=lg, l2g=mine[0], gpos=gpos, nv_global=nvg)

@@ -61,6 +61,8 @@ rp, ci = np.empty(nvl + 1, np.int32), np.empty(nn.value, np.int32)
 ug4.call("ab_domain_level_pattern", dom.h, lg, C.byref(nn), rp.ctypes.data_as(C.POINTER(C.c_int32)), ci.ctypes.data_as(C.POINTER(C.c_int32)))
 rows = np.repeat(np.arange(nvl, dtype=np.int64), np.diff(rp))
 assert np.array_equal(rows * nvl + ci, lk), "numpy pattern order differs from build_pattern"
+# the product derives gpos from the two native patterns; the element-based NumPy derivation must give the same positions
+assert np.array_equal(G["gpos"], P.block_positions(ll["elems"], nvl, G["l2g"], P.pattern_keys(gl["elems"], nvg), nvg))
 parts = gather((G["gpos"], lc, G["l2g"], ll["xyz"]))
 ok = True
 if rank == 0:
