@@ -529,6 +529,14 @@ class ObstacleOptim:
         w.select_nodal(self.ucmps, "u")
         return w.print(os.path.join(directory, "u"), self.u, self.step + 1, self.step + 1, False)
 
+    def write_debug_mesh(self, directory="."):
+        """`if bDebugOutput then SaveGridLevelToFile(dom:grid(), dom:subset_handler(), numRefs, "Mesh_lev"..numRefs.."_step"..step..".ugx")`
+        (3d:795, 2d:788): the top grid level with its current (transformed) coordinates."""
+        import os
+        top = self.dom.num_levels() - 1
+        return self.ug.SaveGridLevelToFile(self.dom.grid(), self.dom.subset_handler(), top,
+                                           os.path.join(directory, "Mesh_lev%d_step%d.ugx" % (top, self.step)))
+
     def write_newton_traces(self):
         """3d:1307-1311: gnuplot.write_data of the Newton tables of the last ADMM iteration (only with -bNewtonOutput true)."""
         if not (self.newton_output and self.trace_dir is not None and self.vNS):

@@ -131,6 +131,14 @@ class Domain(_Handle):
         return dict(dim=self.level_info(level)["dim"], xyz=lv["xyz"], elems=lv["elems"], vsub=lv["vsub"], esub=esub, sp_edges=se,
                     sp_edges_sub=ses, sp_faces=sf, sp_faces_sub=sfs, subset_names=names)
 
+    def grid(self):
+        """dom:grid() -- a handle SaveGridLevelToFile accepts (3d_admm.lua:795)."""
+        return _DomainPart(self, "grid")
+
+    def subset_handler(self):
+        """dom:subset_handler()  3d_admm.lua:795."""
+        return _DomainPart(self, "subset_handler")
+
     def p2p_status(self):
         """{connected, error}: error != 0 means a bounded spin of the peer-to-peer exchange expired (a peer was lost)."""
         c, e = C.c_int(), C.c_int()
@@ -356,6 +364,13 @@ class DirichletBoundary:
 
     def add(self, value, fct, subset):
         self.entries.append((float(value), fct, subset))
+
+
+class _DomainPart:
+    """What dom:grid() / dom:subset_handler() return: a reference back to the domain that owns both."""
+
+    def __init__(self, dom, what):
+        self.dom, self.what = dom, what
 
 
 class DomainDiscretization(_Handle):
@@ -821,6 +836,19 @@ class Backend:
     def VTKOutput(self):
         from .vtk import VTKOutput
         return VTKOutput(self)
+
+    def SaveGridLevelToFile(self, grid, sh, level, filename):
+        """SaveGridLevelToFile(dom:grid(), dom:subset_handler(), numRefs, "Mesh_lev..step...ugx")  3d_admm.lua:795: one grid
+        level with its CURRENT coordinates and subsets as .ugx.  A decomposed domain writes one file per rank
+        (<name>_p<rank>.ugx, the rank's sub-grid)."""
+        from .ugx import save_grid_level
+        dom = grid.dom if isinstance(grid, _DomainPart) else grid
+        if isinstance(sh, _DomainPart) and sh.dom is not dom:
+            raise AdmmB200Error("SaveGridLevelToFile: grid and subset handler belong to different domains")
+        if getattr(dom, "decomposed", False):
+            root, ext = os.path.splitext(filename)
+            filename = "%s_p%04d%s" % (root, self.rank, ext or ".ugx")
+        return save_grid_level(dom.get_grid_dict(int(level)), filename)
 
     # -- solvers --------------------------------------------------------------------------------
     def CG(self):

@@ -489,3 +489,39 @@ def test_vtkoutput_selection_and_naming_on_the_oracle_backend(tmp_path):
     w.select_nodal("u2", "uy")
     back = vtk.read_vtu(w.print(str(tmp_path / "uy"), p.u))
     assert np.array_equal(back["point_data"]["uy"][:, 0], p.u.to_numpy().reshape(-1, 3)[:, 1])
+
+
+def _special_set(g):
+    e = {(int(a), int(b), int(s)) for (a, b), s in zip(np.sort(g["sp_edges"], axis=1), g["sp_edges_sub"])}
+    f = {(int(a), int(b), int(c), int(s)) for (a, b, c), s in zip(np.sort(g["sp_faces"], axis=1), g["sp_faces_sub"])} if len(g["sp_faces"]) else set()
+    return e, f
+
+
+@pytest.mark.parametrize("grid,level", [(GRID3D, 0), (GRID3D, 1), (GRID2D, 2)])
+def test_save_grid_level_to_file_round_trip(grid, level, tmp_path):
+    """SaveGridLevelToFile (3d_admm.lua:795): the written .ugx read back by LoadDomain reproduces the level bit for bit
+    (coordinates, elements, subsets of vertices / boundary edges / boundary faces), by the oracle's reader too, and refining
+    the re-read grid gives the next level of the original hierarchy."""
+    from admm_optim_b200 import ug4
+    from oracle import mesh_np as M
+    dom = _host_domain(grid, level + 1)
+    ug = dom.ug
+    name = ug.SaveGridLevelToFile(dom.grid(), dom.subset_handler(), level, str(tmp_path / ("Mesh_lev%d_step1.ugx" % level)))
+    g = dom.get_grid_dict(level)
+    back = ug4.Domain(ug)
+    ug.LoadDomain(back, name)
+    h = back.get_grid_dict(0)
+    assert h["dim"] == g["dim"] and h["subset_names"] == g["subset_names"]
+    for k in ("xyz", "elems", "vsub", "esub"):
+        assert np.array_equal(h[k], g[k]), k
+    assert _special_set(h) == _special_set(g)
+    o = M.load_ugx(name)
+    assert np.array_equal(o.xyz, g["xyz"]) and np.array_equal(o.elems, g["elems"]) and np.array_equal(o.vsub, g["vsub"])
+    ug.util.refinement.CreateRegularHierarchy(back, 1, False, None)
+    a, b = back.get_level(1), dom.get_level(level + 1)
+    assert np.array_equal(a["xyz"], b["xyz"]) and np.array_equal(a["elems"], b["elems"]) and np.array_equal(a["vsub"], b["vsub"])
+    # every edge / face / volume sits in exactly one subset, as in the shipped grids
+    txt = open(name).read()
+    n_edges = len(re.search(r"<edges>(.*?)</edges>", txt, re.S).group(1).split()) // 2
+    listed = sum(len(m.split()) for m in re.findall(r"<subset name.*?</subset>", txt, re.S) for m in re.findall(r"<edges>(.*?)</edges>", m, re.S))
+    assert listed == n_edges == dom.level_info(level)["nedges"]
