@@ -228,6 +228,7 @@ def run_reference(args):
     # the OpenMP runtime must spin between the (many, short) parallel regions of the solve: with the default passive policy the
     # wake-ups cost more than the sweeps.  Set before the OpenMP runtime is loaded (this arm never imports torch).
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    os.environ.pop("OMP_NUM_THREADS", None)       # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm picks its own count
     import numpy as np  # noqa: F401
     cores = cpu_cores()
     threads, calib = (args.threads, {}) if args.threads > 0 else pick_threads(args.refs, args.smoother)
