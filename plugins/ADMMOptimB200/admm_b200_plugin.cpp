@@ -10,6 +10,9 @@
 // (Domain, ApproximationSpace, GridFunction, DomainDiscretization, GeometricMultiGrid, BiCGStab, VecProd ...) are registered
 // with the prefix "B200"; admm_b200_prelude.lua binds the ugcore names to them for the deformation objects before it runs the
 // UNCHANGED driver script, so that the Navier-Stokes / adjoint part keeps UG4's CPU objects (out of scope).
+#include <algorithm>
+#include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -353,6 +356,173 @@ static std::vector<number> BarycenterDefect(B200GridFunction& u, const char*, co
 static void SetZeroAwayFromSubset(B200GridFunction& gf, const char*, const char* subset) { check(ab_set_zero_away_from_subset(gf.h, subset)); }
 static void TransformDomainByDisplacement(B200GridFunction& u, const char*) { check(ab_transform_domain_by_displacement(u.space->dom->h, u.h)); }
 
+
+// ---- output of GPU-resident data ------------------------------------------------------------------------------------------
+// SaveGridLevelToFile(dom:grid(), dom:subset_handler(), numRefs, "Mesh_lev..step...ugx")  3d_admm.lua:795 (bDebugOutput) for the
+// GPU-side copy of the grid: one level with its CURRENT coordinates in the layout of the shipped grids -- all edges, all
+// triangles (3D: the faces of the tetrahedra), the tetrahedra, and a subset handler in which every entity has exactly one subset
+// (boundary edges / faces keep the subset handed down by the refinement, interior ones fall into the subset of the volumes).
+// Same statement as admm_optim_b200/ugx.py (the Python mirror); LoadDomain reads the file back bit for bit.
+void SaveGridLevelToFileB200(ab_domain* dom, int level, const char* filename) {
+    int dim = 0, nv = 0, ne = 0, nse = 0, nsf = 0, nsub = 0;
+    check(ab_domain_level_info(dom, level, &dim, &nv, &ne, nullptr, nullptr));
+    check(ab_domain_special_info(dom, level, &nse, &nsf, &nsub));
+    const int nen = dim + 1;
+    std::vector<double> xyz((size_t)nv * dim);
+    std::vector<int32_t> el((size_t)ne * nen), vsub((size_t)nv), esub((size_t)ne), se((size_t)nse * 2), ses((size_t)nse), sf((size_t)nsf * 3), sfs((size_t)nsf);
+    check(ab_domain_get_level(dom, level, xyz.data(), el.data(), vsub.data(), nullptr, nullptr));
+    check(ab_domain_get_special(dom, level, nse ? se.data() : nullptr, nse ? ses.data() : nullptr, nsf ? sf.data() : nullptr, nsf ? sfs.data() : nullptr, esub.data()));
+    if (ne == 0) UG_THROW("ADMMOptimB200: SaveGridLevelToFile on an empty level");
+    const int vol_sub = esub[0];
+    typedef std::array<int32_t, 2> E2;
+    typedef std::array<int32_t, 3> F3;
+    static const int LE[6][2] = {{0, 1}, {1, 2}, {0, 2}, {0, 3}, {1, 3}, {2, 3}};
+    static const int LF[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {0, 2, 3}};
+    std::vector<E2> edges;
+    std::vector<F3> faces;
+    edges.reserve((size_t)ne * (dim == 3 ? 6 : 3));
+    for (int e = 0; e < ne; ++e) {
+        const int32_t* v = &el[(size_t)e * nen];
+        for (int k = 0; k < (dim == 3 ? 6 : 3); ++k) {
+            const int32_t a = v[LE[k][0]], b = v[LE[k][1]];
+            edges.push_back({std::min(a, b), std::max(a, b)});
+        }
+        if (dim == 3)
+            for (int k = 0; k < 4; ++k) {
+                F3 f = {v[LF[k][0]], v[LF[k][1]], v[LF[k][2]]};
+                std::sort(f.begin(), f.end());
+                faces.push_back(f);
+            }
+    }
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    std::sort(faces.begin(), faces.end());
+    faces.erase(std::unique(faces.begin(), faces.end()), faces.end());
+    std::vector<int32_t> edge_sub(edges.size(), vol_sub), face_sub(faces.size(), vol_sub);
+    for (int i = 0; i < nse; ++i) {
+        const E2 k = {std::min(se[2 * i], se[2 * i + 1]), std::max(se[2 * i], se[2 * i + 1])};
+        auto it = std::lower_bound(edges.begin(), edges.end(), k);
+        if (it == edges.end() || *it != k) UG_THROW("ADMMOptimB200: a boundary edge is not a side of any element");
+        edge_sub[it - edges.begin()] = ses[i];
+    }
+    for (int i = 0; i < nsf; ++i) {
+        F3 k = {sf[3 * i], sf[3 * i + 1], sf[3 * i + 2]};
+        std::sort(k.begin(), k.end());
+        auto it = std::lower_bound(faces.begin(), faces.end(), k);
+        if (it == faces.end() || *it != k) UG_THROW("ADMMOptimB200: a boundary face is not a side of any element");
+        face_sub[it - faces.begin()] = sfs[i];
+    }
+    FILE* f = std::fopen(filename, "w");
+    if (!f) UG_THROW("ADMMOptimB200: cannot write " << filename);
+    std::fprintf(f, "<?xml version=\"1.0\" encoding=\"utf-8\"?>\n<grid name=\"defGrid\">\n\t<vertices coords=\"%d\">", dim);
+    for (size_t i = 0; i < xyz.size(); ++i) std::fprintf(f, "%s%.17g", i ? " " : "", xyz[i]);
+    std::fprintf(f, "</vertices>\n\t<edges>");
+    for (size_t i = 0; i < edges.size(); ++i) std::fprintf(f, "%s%d %d", i ? " " : "", edges[i][0], edges[i][1]);
+    std::fprintf(f, "</edges>\n\t<triangles>");
+    if (dim == 3) for (size_t i = 0; i < faces.size(); ++i) std::fprintf(f, "%s%d %d %d", i ? " " : "", faces[i][0], faces[i][1], faces[i][2]);
+    else for (int e = 0; e < ne; ++e) std::fprintf(f, "%s%d %d %d", e ? " " : "", el[3 * (size_t)e], el[3 * (size_t)e + 1], el[3 * (size_t)e + 2]);
+    std::fprintf(f, "</triangles>\n");
+    if (dim == 3) {
+        std::fprintf(f, "\t<tetrahedrons>");
+        for (size_t i = 0; i < el.size(); ++i) std::fprintf(f, "%s%d", i ? " " : "", el[i]);
+        std::fprintf(f, "</tetrahedrons>\n");
+    }
+    std::fprintf(f, "\t<subset_handler name=\"defSH\">\n");
+    for (int s = 0; s < nsub; ++s) {
+        char name[256];
+        check(ab_domain_subset_name(dom, s, name, (int)sizeof(name)));
+        std::fprintf(f, "\t\t<subset name=\"%s\" color=\"%.4f %.4f %.4f 1\" state=\"0\">\n", name, 0.15 + 0.7 * ((s * 37) % 10) / 10.0, 0.15 + 0.7 * ((s * 53 + 3) % 10) / 10.0, 0.15 + 0.7 * ((s * 71 + 6) % 10) / 10.0);
+        struct Item { const char* tag; const std::vector<int32_t>* sub; };
+        const Item items3[4] = {{"vertices", &vsub}, {"edges", &edge_sub}, {"faces", &face_sub}, {"volumes", &esub}};
+        const Item items2[3] = {{"vertices", &vsub}, {"edges", &edge_sub}, {"faces", &esub}};
+        const Item* items = dim == 3 ? items3 : items2;
+        for (int t = 0; t < (dim == 3 ? 4 : 3); ++t) {
+            bool any = false;
+            const std::vector<int32_t>& sub = *items[t].sub;
+            for (size_t i = 0; i < sub.size(); ++i) {
+                if (sub[i] != s) continue;
+                if (!any) { std::fprintf(f, "\t\t\t<%s>%zu", items[t].tag, i); any = true; }
+                else std::fprintf(f, " %zu", i);
+            }
+            if (any) std::fprintf(f, "</%s>\n", items[t].tag);
+        }
+        std::fprintf(f, "\t\t</subset>\n");
+    }
+    std::fprintf(f, "\t</subset_handler>\n</grid>\n");
+    std::fclose(f);
+}
+static void SaveGridLevelToFile(B200Domain& dom, int level, const char* filename) { SaveGridLevelToFileB200(dom.h, level, filename); }
+
+// XML UnstructuredGrid (.vtu, ASCII) of nodal data on a simplex grid: points padded to 3 coordinates, 2- and 3-vectors padded to 3
+// components (same layout as admm_optim_b200/vtk.py)
+void WriteVTUB200(const char* path, int dim, int nv, const double* xyz, int ne, const int32_t* elems,
+                  const std::vector<std::string>& names, const std::vector<std::vector<int>>& comps, int nfct, const double* values) {
+    FILE* f = std::fopen(path, "w");
+    if (!f) UG_THROW("ADMMOptimB200: cannot write " << path);
+    const int nen = dim + 1;
+    std::fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n <UnstructuredGrid>\n");
+    std::fprintf(f, "  <Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n   <Points>\n    <DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", nv, ne);
+    for (int v = 0; v < nv; ++v) {
+        for (int c = 0; c < 3; ++c) std::fprintf(f, "%s%.17g", c ? " " : "", c < dim ? xyz[(size_t)v * dim + c] : 0.0);
+        std::fprintf(f, "\n");
+    }
+    std::fprintf(f, "    </DataArray>\n   </Points>\n   <Cells>\n    <DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
+    for (int e = 0; e < ne; ++e) {
+        for (int k = 0; k < nen; ++k) std::fprintf(f, "%s%d", k ? " " : "", elems[(size_t)e * nen + k]);
+        std::fprintf(f, "\n");
+    }
+    std::fprintf(f, "    </DataArray>\n    <DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
+    for (int e = 0; e < ne; ++e) std::fprintf(f, "%s%d", e ? " " : "", nen * (e + 1));
+    std::fprintf(f, "\n    </DataArray>\n    <DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+    for (int e = 0; e < ne; ++e) std::fprintf(f, "%s%d", e ? " " : "", dim == 3 ? 10 : 5);     // VTK_TETRA / VTK_TRIANGLE
+    std::fprintf(f, "\n    </DataArray>\n   </Cells>\n   <PointData>\n");
+    for (size_t s = 0; s < names.size(); ++s) {
+        const int nc = (int)comps[s].size(), out = (nc == 2 || nc == 3) ? 3 : nc;
+        std::fprintf(f, "    <DataArray type=\"Float64\" Name=\"%s\" NumberOfComponents=\"%d\" format=\"ascii\">\n", names[s].c_str(), out);
+        for (int v = 0; v < nv; ++v) {
+            for (int c = 0; c < out; ++c) std::fprintf(f, "%s%.17g", c ? " " : "", c < nc ? values[(size_t)v * nfct + comps[s][c]] : 0.0);
+            std::fprintf(f, "\n");
+        }
+        std::fprintf(f, "    </DataArray>\n");
+    }
+    std::fprintf(f, "   </PointData>\n  </Piece>\n </UnstructuredGrid>\n</VTKFile>\n");
+    std::fclose(f);
+}
+// VTKOutput on deformation-space functions: vtkWriter:clear_selection(); vtkWriter:select_nodal("u1,u2,u3","u");
+// vtkWriter:print("u", u, step+1, step+1, false)   3d_admm.lua:716, 985-987, 1099-1101, 1400-1406
+class B200VTKOutput {
+ public:
+    std::vector<std::string> names;
+    std::vector<std::vector<std::string>> fcts;
+    void clear_selection() { names.clear(); fcts.clear(); }
+    void select_nodal(const char* functions, const char* name) { fcts.push_back(tokenize(functions)); names.push_back(name); }
+    void select_all(bool flag) { if (!flag) clear_selection(); }
+    void print(const char* filename, B200GridFunction& gf, int step, number /*time*/, bool make_consistent) {
+        B200ApproximationSpace& sp = *gf.space;
+        if (sp.kind != AB_SPACE_P1) UG_THROW("ADMMOptimB200: VTKOutput writes nodal (Lagrange-1) functions");
+        ab_domain* dom = sp.dom->h;
+        int nl = 0, dim = 0, nv = 0, ne = 0;
+        check(ab_domain_num_levels(dom, &nl));
+        check(ab_domain_level_info(dom, nl - 1, &dim, &nv, &ne, nullptr, nullptr));
+        std::vector<double> xyz((size_t)nv * dim), vals(gf.num_dofs());
+        std::vector<int32_t> el((size_t)ne * (dim + 1)), vsub((size_t)nv);
+        check(ab_domain_get_level(dom, nl - 1, xyz.data(), el.data(), vsub.data(), nullptr, nullptr));
+        if (make_consistent) gf.change_storage_type_to_consistent();
+        gf.copy_to_host(vals.data());
+        std::vector<std::string> nm = names;
+        std::vector<std::vector<std::string>> fc = fcts;
+        if (nm.empty()) { nm.push_back("u"); fc.push_back(sp.names); }
+        std::vector<std::vector<int>> comps;
+        for (auto& group : fc) {
+            comps.emplace_back();
+            for (auto& n : group) comps.back().push_back(sp.fct_index(n));
+        }
+        char path[1024];
+        std::snprintf(path, sizeof(path), "%s_t%04d.vtu", filename, step);
+        WriteVTUB200(path, dim, nv, xyz.data(), ne, el.data(), nm, comps, (int)sp.names.size(), vals.data());
+    }
+};
+
 template <typename T>
 static void register_elemdisc(bridge::Registry& reg, const std::string& name, const std::string& grp) {
     typedef B200ElemDisc B;
@@ -488,6 +658,12 @@ static void register_all(bridge::Registry& reg, const std::string& grp) {
     reg.add_function("BarycenterDefect", &BarycenterDefect, grp);
     reg.add_function("SetZeroAwayFromSubset", &SetZeroAwayFromSubset, grp);
     reg.add_function("TransformDomainByDisplacement", &TransformDomainByDisplacement, grp);
+    // output of GPU-resident data
+    reg.add_function("B200SaveGridLevelToFile", &SaveGridLevelToFile, grp, "", "Domain#Level#Filename");
+    reg.add_class_<B200VTKOutput>("B200VTKOutput", grp).add_constructor()
+        .add_method("clear_selection", &B200VTKOutput::clear_selection).add_method("select_nodal", &B200VTKOutput::select_nodal)
+        .add_method("select_all", &B200VTKOutput::select_all).add_method("print", &B200VTKOutput::print)
+        .set_construct_as_smart_pointer(true);
 }
 
 }  // namespace ADMMOptimB200

@@ -3,7 +3,7 @@
 -- The plugin ADMMOptimB200 registers the hot-path objects of the replaced plugins under their own names
 -- (DeformationEquation, Testing, VolumeDefect ...).  Objects whose names belong to ugcore are registered with the prefix
 -- "B200"; this file binds the ugcore names to them WHERE THE DEFORMATION / EXTENSION SUBPROBLEM USES THEM and leaves
--- everything else (Navier-Stokes, adjoint, VTK, Drag, Sensitivity) on UG4's CPU objects.  The dispatch is by argument
+-- everything else (Navier-Stokes, adjoint, Drag, Sensitivity, VTK of the flow fields) on UG4's CPU objects.  The dispatch is by argument
 -- type: an object made from a B200 domain stays on the GPU side.
 -- [UPSTREAM-UNVERIFIED]: no Lua interpreter / ugshell exists in the build image; written against the Lua API the scripts use.
 
@@ -32,6 +32,29 @@ local ug_CreateRegularHierarchy = util.refinement.CreateRegularHierarchy
 util.refinement.CreateRegularHierarchy = function(dom, numRefs, verbose, balancerDesc)
 	ug_CreateRegularHierarchy(dom, numRefs, verbose, balancerDesc)
 	B200CreateRegularHierarchy(b200_domains[dom], numRefs)
+end
+
+-- bDebugOutput (3d_admm.lua:795): the UG4 grid is written by UG4, the GPU-side copy next to it (same level, current coordinates)
+local ug_SaveGridLevelToFile = SaveGridLevelToFile
+function SaveGridLevelToFile(grid, sh, level, filename)
+	ug_SaveGridLevelToFile(grid, sh, level, filename)
+	for _, gdom in pairs(b200_domains) do
+		B200SaveGridLevelToFile(gdom, level, string.gsub(filename, "%.ugx$", "") .. "_b200.ugx")
+	end
+end
+
+-- VTKOutput (3d_admm.lua:716): one writer object serves both sides -- print() of a B200 grid function goes to the GPU-side writer
+local ug_VTKOutput = VTKOutput
+function VTKOutput()
+	local w = { cpu = ug_VTKOutput(), gpu = B200VTKOutput() }
+	function w:clear_selection() self.cpu:clear_selection(); self.gpu:clear_selection() end
+	function w:select_nodal(fcts, name) self.cpu:select_nodal(fcts, name); self.gpu:select_nodal(fcts, name) end
+	function w:select_all(flag) self.cpu:select_all(flag); self.gpu:select_all(flag) end
+	function w:print(filename, gf, step, time, makeConsistent)
+		if is_b200(gf) then return self.gpu:print(filename, gf, step or 0, time or 0, makeConsistent or false) end
+		return self.cpu:print(filename, gf, step, time, makeConsistent)
+	end
+	return setmetatable(w, { __index = function(t, key) return function(self, ...) return self.cpu[key](self.cpu, ...) end end })
 end
 
 -- approximation spaces: the Lagrange-1 deformation space and the piecewise-constant tensor space go to the GPU, the

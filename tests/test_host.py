@@ -525,3 +525,53 @@ def test_save_grid_level_to_file_round_trip(grid, level, tmp_path):
     n_edges = len(re.search(r"<edges>(.*?)</edges>", txt, re.S).group(1).split()) // 2
     listed = sum(len(m.split()) for m in re.findall(r"<subset name.*?</subset>", txt, re.S) for m in re.findall(r"<edges>(.*?)</edges>", m, re.S))
     assert listed == n_edges == dom.level_info(level)["nedges"]
+
+
+def _build_shim(tmp_path):
+    import shutil
+    lib_dir = os.path.join(ROOT, "admm_optim_b200")
+    if not shutil.which("g++") or not os.path.exists(os.path.join(lib_dir, "libadmm_b200.so")):
+        pytest.skip("no C++ compiler / library not built")
+    exe = str(tmp_path / "shim_test")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "ug4_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "plugins", "ADMMOptimB200", "admm_b200_plugin.cpp"), os.path.join(ROOT, "tests", "ug4_stub", "shim_main.cpp"),
+                        "-o", exe, "-L" + lib_dir, "-l:libadmm_b200.so", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+@pytest.mark.parametrize("grid,refs", [(GRID3D, 1), (GRID2D, 2)])
+def test_ug4_plugin_shim_writers(grid, refs, tmp_path):
+    """The output functions of the shim (B200SaveGridLevelToFile, the .vtu writer behind B200VTKOutput) run without a GPU on a
+    host-only domain / synthetic data: the .ugx of a refined level equals the Python mirror's file entity by entity after
+    re-reading both, and the .vtu parses with the reader of admm_optim_b200/vtk.py."""
+    from admm_optim_b200 import ug4
+    from admm_optim_b200.vtk import read_vtu
+    exe = _build_shim(tmp_path)
+    dom = _host_domain(grid, refs)
+    ug = dom.ug
+    base = ug.SaveGridLevelToFile(dom.grid(), dom.subset_handler(), 0, str(tmp_path / "level0.ugx"))
+    py = ug.SaveGridLevelToFile(dom.grid(), dom.subset_handler(), refs, str(tmp_path / "py.ugx"))
+    cc = str(tmp_path / "cc.ugx")
+    r = subprocess.run([exe, "ugx", base, str(refs), str(refs), cc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = ug4.Domain(ug), ug4.Domain(ug)
+    ug.LoadDomain(a, py)
+    ug.LoadDomain(b, cc)
+    ga, gb, g = a.get_grid_dict(0), b.get_grid_dict(0), dom.get_grid_dict(refs)
+    for k in ("xyz", "elems", "vsub", "esub", "sp_edges", "sp_edges_sub", "sp_faces", "sp_faces_sub"):
+        assert np.array_equal(ga[k], gb[k]), k
+    assert np.array_equal(gb["xyz"], g["xyz"]) and np.array_equal(gb["elems"], g["elems"]) and gb["subset_names"] == g["subset_names"]
+    assert _special_set(gb) == _special_set(g)
+    # the two files list the same edges / faces in the same order
+    import re as _re
+    for tag in ("edges", "triangles"):
+        ta = _re.search(r"<%s>(.*?)</%s>" % (tag, tag), open(py).read(), _re.S).group(1).split()
+        tb = _re.search(r"<%s>(.*?)</%s>" % (tag, tag), open(cc).read(), _re.S).group(1).split()
+        assert ta == tb, tag
+    out = str(tmp_path / "f.vtu")
+    assert subprocess.run([exe, "vtu", out]).returncode == 0
+    v = read_vtu(out)
+    assert v["points"].shape == (5, 3) and v["connectivity"].tolist() == [[0, 1, 2, 3], [1, 2, 3, 4]] and set(v["types"]) == {10}
+    vals = (0.1 * np.arange(15) - 0.3).reshape(5, 3)
+    assert np.array_equal(v["point_data"]["u"], vals) and np.array_equal(v["point_data"]["first"][:, 0], vals[:, 0])
