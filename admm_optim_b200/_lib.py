@@ -49,6 +49,7 @@ PROTOTYPES = {
     "ab_domain_set_interface": [_P, _I, _I, _I32P, _I32P, _I32P, C.POINTER(C.c_ubyte)],
     "ab_domain_set_gather": [_P, _I, _P, _I32P, _I32P, _I64P, _I32P],
     "ab_domain_level_pattern": [_P, _I, _I64P, _I32P, _I32P],
+    "ab_domain_level_incidence": [_P, _I, _I32P, _I32P],
     "ab_domain_set_block_interface": [_P, _I, _I, _I32P, _I32P, _I32P, _I, _I32P, _I32P, _I32P],
     "ab_domain_p2p_export": [_P, _P, _I64P, _I32P],
     "ab_domain_p2p_connect": [_P, _P, _I64P, _I64P],

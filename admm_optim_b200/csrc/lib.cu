@@ -183,12 +183,8 @@ void Domain::finalize() {
             {   // vertex -> element incidence, elements ascending (fixed summation order of the row-owner assembly)
                 const int N = H.dim + 1;
                 AB_REQUIRE((int64_t)H.ne * N < (int64_t)1 << 31, AB_ERR_UNSUPPORTED, "level exceeds int32 incidence entries");
-                std::vector<int> vp((size_t)H.nv + 1, 0), vi((size_t)H.ne * N);
-                for (size_t k = 0; k < (size_t)H.ne * N; ++k) vp[H.elems[k] + 1]++;
-                for (int v = 0; v < H.nv; ++v) vp[v + 1] += vp[v];
-                std::vector<int> fill(vp.begin(), vp.end() - 1);
-                for (int e = 0; e < H.ne; ++e)
-                    for (int a = 0; a < N; ++a) vi[fill[H.elems[(size_t)e * N + a]]++] = e;
+                std::vector<int32_t> vp, vi;
+                build_v2e(H, vp, vi);
                 L.v2e_ptr.upload(vp, ctx->stream);
                 L.v2e_idx.upload(vi, ctx->stream);
             }
@@ -1860,6 +1856,15 @@ int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* r
     if (nnzb) *nnzb = (int64_t)P.colidx.size();
     if (rowptr) memcpy(rowptr, P.rowptr.data(), P.rowptr.size() * sizeof(int32_t));
     if (colidx) memcpy(colidx, P.colidx.data(), P.colidx.size() * sizeof(int32_t));
+    AB_CATCH
+}
+int ab_domain_level_incidence(ab_domain* dom, int level, int32_t* ptr, int32_t* idx) {
+    AB_TRY
+    AB_REQUIRE(dom && ptr && idx && level >= 0 && level < (int)dom->mesh.levels.size(), AB_ERR_ARG, "level out of range");
+    std::vector<int32_t> vp, vi;
+    build_v2e(dom->mesh.levels[level], vp, vi);
+    memcpy(ptr, vp.data(), vp.size() * sizeof(int32_t));
+    memcpy(idx, vi.data(), vi.size() * sizeof(int32_t));
     AB_CATCH
 }
 int ab_domain_p2p_export(ab_domain* dom, void* handle64, int64_t* level_base /* nlevels */, int32_t* totals /* nlevels */) {

@@ -227,33 +227,75 @@ void refine_level(const HostLevel& C, HostLevel& F) {
     F.edges.clear();
 }
 
+// Rows of the P1 vertex graph: [lower neighbours ascending | diagonal | upper neighbours ascending].  The edges are sorted by
+// (lo, hi), so the upper part of row lo is a contiguous run of the edge list (copied in parallel); the lower part of row hi
+// collects the edges (lo, hi) from all over the list -- scattered with an atomic cursor and then sorted per row by the edge
+// index (= ascending lo), which makes the result independent of the scatter order.
 void build_pattern(HostLevel& L, HostPattern& P) {
     ensure_edges(L);
     const int nv = L.nv;
     const int64_t ned = L.nedges();
-    std::vector<int32_t> nlow((size_t)nv, 0), nup((size_t)nv, 0);
-    for (int64_t k = 0; k < ned; ++k) { nup[L.edges[2 * k]]++; nlow[L.edges[2 * k + 1]]++; }
+    const int32_t* E = L.edges.data();
+    std::vector<int32_t> nlow((size_t)nv, 0);
+    std::vector<int64_t> estart((size_t)nv + 1, 0);       // first edge with lo == v
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < ned; ++k) {
+        __atomic_fetch_add(&nlow[E[2 * k + 1]], 1, __ATOMIC_RELAXED);
+        if (k == 0 || E[2 * k] != E[2 * k - 2])
+            estart[E[2 * k]] = k + 1;                      // marker (+1 so that 0 means "no edge starts here")
+    }
+    {   // vertices without an upper edge inherit the next start
+        int64_t next = ned;
+        for (int v = nv - 1; v >= 0; --v) {
+            if (estart[v]) next = estart[v] - 1;
+            estart[v] = next;
+        }
+        estart[nv] = ned;
+    }
     P.rowptr.resize((size_t)nv + 1);
     P.rowptr[0] = 0;
-    for (int i = 0; i < nv; ++i) P.rowptr[i + 1] = P.rowptr[i] + nlow[i] + nup[i] + 1;
+    for (int i = 0; i < nv; ++i) P.rowptr[i + 1] = P.rowptr[i] + nlow[i] + (int32_t)(estart[i + 1] - estart[i]) + 1;
     const int64_t nnz = P.rowptr[nv];
     P.colidx.resize(nnz);
     P.mid.resize(nnz);
     P.diagpos.resize(nv);
-    std::vector<int32_t> clow((size_t)nv), cup((size_t)nv);
+    std::vector<int32_t> fill((size_t)nv, 0);
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < nv; ++i) {
-        clow[i] = P.rowptr[i];
-        P.diagpos[i] = P.rowptr[i] + nlow[i];
-        cup[i] = P.diagpos[i] + 1;
-        P.colidx[P.diagpos[i]] = i;
-        P.mid[P.diagpos[i]] = i;
+        const int32_t d = P.rowptr[i] + nlow[i];
+        P.diagpos[i] = d;
+        P.colidx[d] = i;
+        P.mid[d] = i;
+        int32_t o = d + 1;
+        for (int64_t k = estart[i]; k < estart[i + 1]; ++k, ++o) { P.colidx[o] = E[2 * k + 1]; P.mid[o] = (int32_t)(nv + k); }
     }
+    // lower parts: mid holds the edge index until the per-row sort
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < ned; ++k) {
-        int32_t lo = L.edges[2 * k], hi = L.edges[2 * k + 1];
-        int32_t m = (int32_t)(nv + k);
-        P.colidx[cup[lo]] = hi; P.mid[cup[lo]++] = m;
-        P.colidx[clow[hi]] = lo; P.mid[clow[hi]++] = m;
+        const int32_t hi = E[2 * k + 1];
+        P.mid[P.rowptr[hi] + __atomic_fetch_add(&fill[hi], 1, __ATOMIC_RELAXED)] = (int32_t)(nv + k);
     }
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int i = 0; i < nv; ++i) {
+        int32_t* m = P.mid.data() + P.rowptr[i];
+        std::sort(m, m + nlow[i]);
+        for (int j = 0; j < nlow[i]; ++j) P.colidx[P.rowptr[i] + j] = E[2 * (int64_t)(m[j] - nv)];
+    }
+}
+
+// vertex -> element incidence (CSR), elements ascending per vertex: the fixed summation order of the row-owner assembly.
+// Deliberately serial: the element loop visits the vertices with good locality, and a scatter with atomic cursors plus a per-vertex
+// sort was measured slower than this on 8 threads (level 5: 1.8 s serial, 2.2 s threaded).
+void build_v2e(const HostLevel& L, std::vector<int32_t>& ptr, std::vector<int32_t>& idx) {
+    const int N = L.dim + 1, nv = L.nv;
+    const int64_t n = (int64_t)L.ne * N;
+    ptr.assign((size_t)nv + 1, 0);
+    idx.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) ptr[L.elems[k] + 1]++;
+    for (int v = 0; v < nv; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < L.ne; ++e)
+        for (int a = 0; a < N; ++a) idx[fill[L.elems[(size_t)e * N + a]]++] = (int32_t)e;
 }
 
 // ---------------------------------------------------------------------------------------------

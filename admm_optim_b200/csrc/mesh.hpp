@@ -38,6 +38,7 @@ struct HostMesh {
 void ensure_edges(HostLevel& L);
 void refine_level(const HostLevel& coarse_with_edges, HostLevel& fine);
 void build_pattern(HostLevel& L, HostPattern& P);
+void build_v2e(const HostLevel& L, std::vector<int32_t>& ptr, std::vector<int32_t>& idx);
 bool load_ugx(const std::string& path, HostMesh& mesh, std::string& err);
 
 }  // namespace ab

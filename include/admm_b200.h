@@ -97,6 +97,9 @@ int ab_domain_set_block_interface(ab_domain* dom, int level, int nneigh, const i
 /* P1 block pattern of a level (host side, no GPU needed): block rows = vertices, columns ascending, diagonal included;
  * nnzb = V + 2E.  rowptr (nv+1) / colidx (nnzb) may be NULL to query the size only.                              */
 int ab_domain_level_pattern(ab_domain* dom, int level, int64_t* nnzb, int32_t* rowptr, int32_t* colidx);
+/* vertex -> element incidence of a level (host side): ptr (nv+1), idx (ne*(dim+1)), elements ascending per vertex -- the fixed
+ * summation order of the row-owner Hessian assembly (assemble_jacobian, 3d_admm.lua:972).                          */
+int ab_domain_level_incidence(ab_domain* dom, int level, int32_t* ptr, int32_t* idx);
 /* NVLink peer-to-peer interface sums (CUDA IPC; optional -- without it the exchanges use ncclSend/ncclRecv):
  * export this rank's receive window after the first ApproximationSpace exists, gather all handles / layouts on the
  * host, then connect.  remote_dst / remote_stride: one entry per (level, neighbour) in level-major, neighbour order. */

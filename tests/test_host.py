@@ -575,3 +575,22 @@ def test_ug4_plugin_shim_writers(grid, refs, tmp_path):
     assert v["points"].shape == (5, 3) and v["connectivity"].tolist() == [[0, 1, 2, 3], [1, 2, 3, 4]] and set(v["types"]) == {10}
     vals = (0.1 * np.arange(15) - 0.3).reshape(5, 3)
     assert np.array_equal(v["point_data"]["u"], vals) and np.array_equal(v["point_data"]["first"][:, 0], vals[:, 0])
+
+
+@pytest.mark.parametrize("grid,refs", [(GRID3D, 2), (GRID2D, 4)])
+def test_native_pattern_and_incidence_match_numpy(grid, refs):
+    """The (multi-threaded) host builders of the P1 block pattern and of the vertex -> element incidence give exactly the NumPy
+    statement: rows = sorted unique vertex pairs sharing an element; incidence = elements ascending per vertex."""
+    import ctypes as C
+    from admm_optim_b200 import partition as P, ug4
+    dom = _host_domain(grid, refs)
+    for level in range(refs + 1):
+        lv = dom.get_level(level)
+        nv, el = len(lv["xyz"]), lv["elems"]
+        rp, ci = dom.level_pattern(level)
+        assert np.array_equal(P.csr_keys(rp, ci, nv), P.pattern_keys(el, nv))
+        ptr, idx = np.empty(nv + 1, np.int32), np.empty(el.size, np.int32)
+        ug4.call("ab_domain_level_incidence", dom.h, level, ptr.ctypes.data_as(C.POINTER(C.c_int32)), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+        order = np.argsort(el.ravel(), kind="stable")                   # by vertex, then by position in the element list = element ascending
+        assert np.array_equal(idx, (order // el.shape[1]).astype(np.int32))
+        assert np.array_equal(np.diff(ptr), np.bincount(el.ravel(), minlength=nv))
