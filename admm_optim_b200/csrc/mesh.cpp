@@ -33,41 +33,30 @@ static inline uint64_t ekey(int32_t a, int32_t b) {
     return ((uint64_t)lo << 32) | hi;
 }
 
-// Unique edges (lo, hi), sorted lexicographically.  Bucket sort by the lower vertex instead of one comparison sort over all
-// 6 ne element edges (239 M keys at level 5): count per lo, scatter the hi ends into the buckets (order inside a bucket is
-// irrelevant), then sort + unique every bucket (a few dozen entries) and compact.  The result does not depend on the scatter order.
-void ensure_edges(HostLevel& L) {
-    if (L.have_edges) return;
-    const int nen = L.dim + 1, nle = L.dim == 3 ? 6 : 3;
-    const int nv = L.nv;
-    const int64_t ne = L.ne;
+// Unique edges (lo, hi), sorted lexicographically, from a generator of candidate pairs (duplicates allowed).  Bucket sort by the
+// lower vertex instead of one comparison sort over all candidates (239 M element edges at level 5): count per lo, scatter the hi
+// ends into the buckets (order inside a bucket is irrelevant), then sort + unique every bucket (a few dozen entries) and compact.
+// The result does not depend on the scatter order.  gen(i, emit) calls emit(a, b) for every candidate of outer index i.
+namespace {
+template <class Gen>
+void unique_edges(int nv, int64_t n_outer, const Gen& gen, std::vector<int32_t>& edges) {
     std::vector<int64_t> start((size_t)nv + 1, 0);
     {
         std::vector<int32_t> cnt((size_t)nv, 0);
-#pragma omp parallel for schedule(static)
-        for (int64_t e = 0; e < ne; ++e) {
-            const int32_t* v = &L.elems[(size_t)e * nen];
-            for (int k = 0; k < nle; ++k) {
-                const int* le = L.dim == 3 ? LE3[k] : LE2[k];
-                const int32_t a = v[le[0]], b = v[le[1]];
-                __atomic_fetch_add(&cnt[a < b ? a : b], 1, __ATOMIC_RELAXED);
-            }
-        }
+#pragma omp parallel for schedule(dynamic, 16384)
+        for (int64_t i = 0; i < n_outer; ++i)
+            gen(i, [&](int32_t a, int32_t b) { __atomic_fetch_add(&cnt[a < b ? a : b], 1, __ATOMIC_RELAXED); });
         for (int v = 0; v < nv; ++v) start[v + 1] = start[v] + cnt[v];
     }
     std::vector<int32_t> his((size_t)start[nv]);
     {
         std::vector<int32_t> fill((size_t)nv, 0);
-#pragma omp parallel for schedule(static)
-        for (int64_t e = 0; e < ne; ++e) {
-            const int32_t* v = &L.elems[(size_t)e * nen];
-            for (int k = 0; k < nle; ++k) {
-                const int* le = L.dim == 3 ? LE3[k] : LE2[k];
-                const int32_t a = v[le[0]], b = v[le[1]];
+#pragma omp parallel for schedule(dynamic, 16384)
+        for (int64_t i = 0; i < n_outer; ++i)
+            gen(i, [&](int32_t a, int32_t b) {
                 const int32_t lo = a < b ? a : b, hi = a < b ? b : a;
                 his[(size_t)(start[lo] + __atomic_fetch_add(&fill[lo], 1, __ATOMIC_RELAXED))] = hi;
-            }
-        }
+            });
     }
     std::vector<int64_t> ustart((size_t)nv + 1, 0);
 #pragma omp parallel for schedule(dynamic, 4096)
@@ -78,15 +67,61 @@ void ensure_edges(HostLevel& L) {
         ustart[v + 1] = std::unique(b, e) - b;
     }
     for (int v = 0; v < nv; ++v) ustart[v + 1] += ustart[v];
-    L.edges.resize((size_t)ustart[nv] * 2);
+    edges.resize((size_t)ustart[nv] * 2);
 #pragma omp parallel for schedule(dynamic, 4096)
     for (int v = 0; v < nv; ++v) {
         const int32_t* b = his.data() + start[v];
         const int64_t n = ustart[v + 1] - ustart[v];
-        int32_t* out = L.edges.data() + 2 * ustart[v];
+        int32_t* out = edges.data() + 2 * ustart[v];
         for (int64_t i = 0; i < n; ++i) { out[2 * i] = v; out[2 * i + 1] = b[i]; }
     }
+}
+}  // namespace
+
+void ensure_edges(HostLevel& L) {
+    if (L.have_edges) return;
+    const int nen = L.dim + 1, nle = L.dim == 3 ? 6 : 3, dim = L.dim;
+    const int32_t* el = L.elems.data();
+    unique_edges(L.nv, L.ne, [=](int64_t e, auto emit) {
+        const int32_t* v = el + (size_t)e * nen;
+        for (int k = 0; k < nle; ++k) {
+            const int* le = dim == 3 ? LE3[k] : LE2[k];
+            emit(v[le[0]], v[le[1]]);
+        }
+    }, L.edges);
     L.have_edges = true;
+}
+
+// Edges of a regularly refined level from its parent instead of from its own 6 ne element edges: every fine edge is
+//   (a) one half of a coarse edge k = (a, b):  (a, m_k), (b, m_k)                                 -- 2 per coarse edge, no duplicates
+//   (b) an edge between two midpoints inside a coarse element: 2D the 3 sides of the inner triangle (child 3); 3D the 12 sides
+//       of the inner octahedron + its diagonal = the edges of children 4..7 = {p, q, c_j, c_j+1} (refine_level): (p, q), (p, c_j),
+//       (q, c_j), (c_j, c_j+1) -- 13 per tetrahedron, the octahedron sides on a coarse face are seen from both neighbours.
+// 3.7x (3D) fewer candidates than the generic path, same sorted unique result (checked against it in the tests).
+void edges_from_parent(const HostLevel& C, HostLevel& F) {
+    const int dim = C.dim, nvc = C.nv;
+    const int64_t nec = C.ne, nedc = C.nedges();
+    const int32_t* ce = C.edges.data();
+    const int32_t* fe = F.elems.data();
+    unique_edges(F.nv, nec + nedc, [=](int64_t i, auto emit) {
+        if (i >= nec) {
+            const int64_t k = i - nec;
+            const int32_t m = (int32_t)(nvc + k);
+            emit(ce[2 * k], m);
+            emit(ce[2 * k + 1], m);
+        } else if (dim == 2) {
+            const int32_t* c = fe + ((size_t)i * 4 + 3) * 3;          // child 3 = (mab, mbc, mca)
+            emit(c[0], c[1]); emit(c[1], c[2]); emit(c[2], c[0]);
+        } else {
+            const int32_t* c4 = fe + ((size_t)i * 8 + 4) * 4;          // children 4..7 = (p, q, x, y), x/y possibly swapped
+            const int32_t p = c4[0], q = c4[1];
+            emit(p, q);
+            for (int j = 0; j < 4; ++j) emit(c4[4 * j + 2], c4[4 * j + 3]);
+            for (int j = 0; j < 4; j += 2)                             // c0, c1 from child 4; c2, c3 from child 6
+                for (int t = 2; t < 4; ++t) { emit(p, c4[4 * j + t]); emit(q, c4[4 * j + t]); }
+        }
+    }, F.edges);
+    F.have_edges = true;
 }
 
 namespace {
@@ -225,6 +260,7 @@ void refine_level(const HostLevel& C, HostLevel& F) {
     }
     F.have_edges = false;
     F.edges.clear();
+    if (!getenv("ADMM_B200_GENERIC_EDGES")) edges_from_parent(C, F);
 }
 
 // Rows of the P1 vertex graph: [lower neighbours ascending | diagonal | upper neighbours ascending].  The edges are sorted by

@@ -36,6 +36,7 @@ struct HostMesh {
 };
 
 void ensure_edges(HostLevel& L);
+void edges_from_parent(const HostLevel& coarse_with_edges, HostLevel& fine);
 void refine_level(const HostLevel& coarse_with_edges, HostLevel& fine);
 void build_pattern(HostLevel& L, HostPattern& P);
 void build_v2e(const HostLevel& L, std::vector<int32_t>& ptr, std::vector<int32_t>& idx);

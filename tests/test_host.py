@@ -594,3 +594,20 @@ def test_native_pattern_and_incidence_match_numpy(grid, refs):
         order = np.argsort(el.ravel(), kind="stable")                   # by vertex, then by position in the element list = element ascending
         assert np.array_equal(idx, (order // el.shape[1]).astype(np.int32))
         assert np.array_equal(np.diff(ptr), np.bincount(el.ravel(), minlength=nv))
+
+
+@pytest.mark.parametrize("grid,refs", [(GRID3D, 3), (GRID2D, 4)])
+def test_edges_from_parent_equal_generic_edges(grid, refs, monkeypatch):
+    """Refined levels take their edge list from the parent level (halves of coarse edges + midpoint-midpoint edges of the inner
+    children) instead of from all element edges: same hierarchy (vertex numbering of the next level = edge order) and same
+    patterns as the generic path."""
+    a = _host_domain(grid, refs)
+    monkeypatch.setenv("ADMM_B200_GENERIC_EDGES", "1")
+    b = _host_domain(grid, refs)
+    for level in range(refs + 1):
+        la, lb = a.get_level(level), b.get_level(level)
+        for k in ("xyz", "elems", "vsub", "parent_a", "parent_b"):
+            assert np.array_equal(la[k], lb[k]), (level, k)
+        assert a.level_info(level)["nedges"] == b.level_info(level)["nedges"]
+        for x, y in zip(a.level_pattern(level), b.level_pattern(level)):
+            assert np.array_equal(x, y)
