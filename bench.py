@@ -407,6 +407,69 @@ def run_b200(args):
     headline_decomposed = bool(prob.dom.decomposed)
     del prob
 
+    # ---- the line as far as it is known; the legs below add to `extra` / `roof` -----------------------------
+    # The headline is complete here.  The secondary legs (larger configurations, decomposed at N > 1) must never cost the line: an
+    # exception in one of them is recorded in the line, and a watchdog prints the line with what has been measured if they exceed
+    # --legs-timeout (a lost peer makes a collective wait forever; the device-side spins are bounded, the host-side waits are not).
+    import threading
+    state = {"leg": "none", "printed": False, "roof": None}
+    emit_lock = threading.Lock()
+
+    def emit_line(with_cpu_baseline):
+        with emit_lock:
+            if state["printed"] or rank != 0:
+                return
+            state["printed"] = True
+        value = args.steps / (ms_dev * 1e-3)
+        e2e_v = args.steps / (ms_e2e * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": common_config(args.refs),
+                "arm": {"parallelism": ("%d GPUs, headline undivided" % world if not headline_decomposed else "domain decomposition x%d" % world) if world > 1 else "1 GPU",
+                        "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
+                "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clk, "parity": parity,
+                "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps}
+        if state["roof"]:
+            line["roofline"] = state["roof"]
+        line.update(extra)
+        if with_cpu_baseline and not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(args.refs)
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+    def watchdog_fired():
+        extra["secondary_legs_error"] = "leg '%s' exceeded --legs-timeout %d s; the line carries what was measured before" % (state["leg"], args.legs_timeout)
+        sys.stderr.write("bench.py: %s\n" % extra["secondary_legs_error"])
+        emit_line(False)
+        sys.stderr.flush()
+        os._exit(0)
+
+    extra = {}
+    watchdog = threading.Timer(args.legs_timeout, watchdog_fired)
+    watchdog.daemon = True
+    if args.legs_timeout > 0:
+        watchdog.start()
+    try:
+        secondary_legs(args, ug, ug4, torch, np, stream, rank, world, local, peak, peak_src, barrier, maxtime, timeit, parity, extra, state)
+    except Exception as exc:
+        import traceback
+        traceback.print_exc()
+        extra["secondary_legs_error"] = "leg '%s' failed: %s" % (state["leg"], repr(exc)[:400])
+        watchdog.cancel()
+        emit_line(world == 1)   # one GPU: nothing can be left hanging, the CPU baseline still runs
+        sys.stderr.flush()
+        os._exit(0)             # the other ranks may be inside a collective this rank will never join: their watchdogs end them
+    watchdog.cancel()
+    emit_line(True)
+
+
+def secondary_legs(args, ug, ug4, torch, np, stream, rank, world, local, peak, peak_src, barrier, maxtime, timeit, parity, extra, state):
+    """Everything of the B200 arm after the headline: roofline leg (numRefs 5), configs[2] / configs[3] ADMM iterations, elementwise
+    kernel figures, decomposed-vs-undivided parity.  Fills `extra` and state['roof']; state['leg'] names the running leg."""
+    from admm_optim_b200.driver import ObstacleOptim
+
     # ---- one ADMM iteration of a larger configuration (BASELINE.json configs[2] / configs[3]) -------------------
     def admm_leg(ug, dim, refs, grid, steps=2, collective=True, abs_tol=None):
         bar = barrier if collective else torch.cuda.synchronize
@@ -440,10 +503,10 @@ def run_b200(args):
             assert p.dom.p2p_status()["error"] == 0, "peer-to-peer interface exchange timed out"
         return out, p
 
-    extra = {}
     # ---- roofline leg: SpMV / V-cycle / solve on a level larger than L2 ---------------------------------
     roof = None
     if args.roofline_refs > 0:
+        state["leg"] = "roofline (numRefs %d)" % args.roofline_refs
         from admm_optim_b200.driver import linear_solver
         # lean problem: deformation space + Hessian + solver only (no P0 tensors)
         ug.InitUG(3, None)
@@ -480,7 +543,7 @@ def run_b200(args):
             t_spmv_x = timeit(spmv_consistent, 20)
         bytes_spmv = spmv_bytes(3, nb, nnzb)
         ach = bytes_spmv / t_spmv / 1e9
-        roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak,
+        state["roof"] = roof = {"bound": "hbm", "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / world / peak,
                 "traffic": NCU_TRAFFIC_BYTES.get(args.roofline_refs) if world == 1 else None,
                 "kernel": "k_bsr_spmv_tma<3,0,0,3> (y = A x, BSR 3x3 fp64, TMA-staged tiles)", "peak_source": peak_src,
                 "bytes_per_launch": bytes_spmv // world, "us_per_launch": t_spmv * 1e6,
@@ -526,6 +589,7 @@ def run_b200(args):
         del s, A, DD, xv, bvec, yv, uv, DS, dom
 
     if args.admm_refs > 0:
+        state["leg"] = "admm_refs%d" % args.admm_refs
         a4, p4 = admm_leg(ug, 3, args.admm_refs, GRID3D)
         # roofline figures of the BLAS-1 and P0 (ADMM prox / dual / norm) kernels on this problem's LOCAL vectors: algorithmic bytes
         # (8 B x vectors read + written; element kernels: + 4 (d+1) connectivity per element and the coordinate / u gathers counted
@@ -566,6 +630,7 @@ def run_b200(args):
         del p4
         extra["admm_refs%d" % args.admm_refs] = a4
         if world > 1 and a4["decomposed"]:
+            state["leg"] = "parity.decomposed (numRefs %d)" % args.admm_refs
             # multi-GPU parity inside the driver-run line: the same problem and iteration sequence at a matched, tight solver
             # tolerance (1e-13, as the golden traces) -- decomposed over the N ranks, and UNDIVIDED on rank 0's own GPU while the
             # other ranks wait at the barrier
@@ -590,6 +655,7 @@ def run_b200(args):
                     parity["ok"] = False
             barrier()
     if args.dim2_refs > 0:
+        state["leg"] = "admm_2d_refs%d" % args.dim2_refs
         a2, p2 = admm_leg(ug, 2, args.dim2_refs, GRID2D)
         # SpMV / V-cycle of the 2D top level (2x2 blocks)
         DD2 = p2.DeformationEquation_DomainDisc
@@ -607,25 +673,7 @@ def run_b200(args):
         del p2
         extra["admm_2d_refs%d" % args.dim2_refs] = a2
 
-    if rank != 0:
-        return
-    value = args.steps / (ms_dev * 1e-3)
-    e2e_v = args.steps / (ms_e2e * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": common_config(args.refs),
-            "arm": {"parallelism": ("%d GPUs, headline undivided" % world if not headline_decomposed else "domain decomposition x%d" % world) if world > 1 else "1 GPU",
-                    "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps},
-            "e2e": {"value": e2e_v, "unit": "iters/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk, "parity": parity,
-            "newton_its_per_step": newton / args.steps, "bicgstab_its_per_step": its / args.steps}
-    if roof:
-        line["roofline"] = roof
-    line.update(extra)
-    if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_sample(args.refs)
-    print(json.dumps(line))
+    state["leg"] = "done"
 
 
 def main():
@@ -641,6 +689,7 @@ def main():
     ap.add_argument("--smoother", default="gs", choices=["gs", "cheb"], help="reference arm: GMG smoother (gs = what the reference asks for; cheb = the GPU arm's)")
     ap.add_argument("--threads", type=int, default=0, help="reference arm: host threads (0 = calibrate: all / half / ... / one, fastest wins)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--legs-timeout", type=int, default=900, help="B200 arm: seconds the legs after the headline may take before the line is printed without them (0 = no limit)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -611,3 +611,23 @@ def test_edges_from_parent_equal_generic_edges(grid, refs, monkeypatch):
         assert a.level_info(level)["nedges"] == b.level_info(level)["nedges"]
         for x, y in zip(a.level_pattern(level), b.level_pattern(level)):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("mode", ["raise", "hang"])
+def test_bench_line_survives_a_failing_or_hanging_secondary_leg(mode):
+    """The headline of bench.py's B200 arm is never lost to a secondary leg: an exception in a leg, or a leg that exceeds
+    --legs-timeout (a collective waiting for a lost peer), still ends with exit code 0 and the JSON line carrying the headline,
+    the legs measured before, and `secondary_legs_error` naming the leg."""
+    import json
+    env = dict(os.environ, DRYRUN_FAIL_IN_2D_LEG=mode)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py"), "--refs", "1", "--roofline-refs", "1", "--admm-refs", "0", "--dim2-refs", "2",
+                        "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--legs-timeout", "25" if mode == "hang" else "600"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["parity"]["ok"]
+    assert "roofline" in line and "vcycle_ms" in line                      # the leg that ran before the failing one is kept
+    assert "admm_2d_refs2" not in line and "admm_2d_refs2" in line["secondary_legs_error"]
+    assert ("injected failure" if mode == "raise" else "legs-timeout") in line["secondary_legs_error"]

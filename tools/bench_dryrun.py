@@ -105,6 +105,18 @@ _dist.init_process_group = lambda backend=None, **kw: _init("gloo")      # the m
 
 import bench   # noqa: E402
 
+FAIL_LEG = os.environ.get("DRYRUN_FAIL_IN_2D_LEG")      # "raise": an exception inside the last leg; "hang": it never returns
+if FAIL_LEG:
+    _L2 = FakeBackend.L2Norm
+
+    def _l2(self, gf, cmp, *a):
+        if gf.space.dom.dim == 2 and gf.space.dom.top.nv > 1000:
+            if FAIL_LEG == "hang":
+                time.sleep(3600)
+            raise RuntimeError("injected failure in the 2D leg")
+        return _L2(self, gf, cmp, *a)
+    FakeBackend.L2Norm = _l2
+
 bench.golden_parity.__defaults__ = ("3d_refs1",)      # the smaller golden trace: the oracle stands in for the GPU here
 
 if __name__ == "__main__":
