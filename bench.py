@@ -308,6 +308,11 @@ def golden_parity(ug, name="3d_refs2"):
 
 
 def run_b200(args):
+    # torchrun exports OMP_NUM_THREADS=1 to its workers unless the user set it: the host side of the setup (refinement, edge lists,
+    # patterns: OpenMP in csrc/mesh.cpp) would run on one core per rank.  Give every rank its share of the host cores instead --
+    # before torch (and with it the OpenMP runtime) is loaded.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, cpu_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ["WORLD_SIZE"])))))
     import numpy as np
     import torch
     import torch.distributed as dist
