@@ -203,25 +203,11 @@ void Domain::finalize() {
             AB_REQUIRE((int)H.owned.size() == nv, AB_ERR_ARG, "interface: owned mask size mismatch");
             I.neigh = H.neigh; I.offset = H.offset;
             I.total = H.offset.empty() ? 0 : H.offset.back();
-            I.my_pos = 0;
-            for (size_t n = 0; n < H.neigh.size(); ++n) {
+            for (size_t n = 0; n < H.neigh.size(); ++n)
                 AB_REQUIRE(H.neigh[n] != me && (n == 0 || H.neigh[n] > H.neigh[n - 1]), AB_ERR_ARG, "interface: neighbour ranks must be ascending and exclude this rank");
-                if (H.neigh[n] < me) I.my_pos++;
-            }
-            // unique interface vertices ordered by (first neighbour, slot); CSR vertex -> (slot, neighbour index), neighbours ascending
-            std::vector<int> pos((size_t)nv, -1), iv;
-            for (size_t n = 0; n < H.neigh.size(); ++n)
-                for (int k = H.offset[n]; k < H.offset[n + 1]; ++k)
-                    if (pos[H.idx[k]] < 0) { pos[H.idx[k]] = (int)iv.size(); iv.push_back(H.idx[k]); }
-            std::vector<int> ptr(iv.size() + 1, 0);
-            for (int v : H.idx) ptr[pos[v] + 1]++;
-            for (size_t k = 0; k < iv.size(); ++k) ptr[k + 1] += ptr[k];
-            std::vector<int> fill(ptr.begin(), ptr.end() - 1), slot((size_t)I.total), nb((size_t)I.total);
-            for (size_t n = 0; n < H.neigh.size(); ++n)
-                for (int k = H.offset[n]; k < H.offset[n + 1]; ++k) {
-                    const int e = fill[pos[H.idx[k]]]++;
-                    slot[e] = k; nb[e] = (int)n;
-                }
+            const IfaceCsr csr = build_iface_csr(nv, me, H.neigh, H.offset, H.idx);      // iface_xchg.cuh
+            I.my_pos = csr.my_pos;
+            const std::vector<int>&iv = csr.iv, &ptr = csr.ptr, &slot = csr.slot, &nb = csr.nb;
             I.niv = (int)iv.size();
             I.idx.upload(H.idx, ctx->stream);
             I.iv.upload(iv, ctx->stream);

@@ -631,3 +631,41 @@ def test_bench_line_survives_a_failing_or_hanging_secondary_leg(mode):
     assert "roofline" in line and "vcycle_ms" in line                      # the leg that ran before the failing one is kept
     assert "admm_2d_refs2" not in line and "admm_2d_refs2" in line["secondary_legs_error"]
     assert ("injected failure" if mode == "raise" else "legs-timeout") in line["secondary_legs_error"]
+
+
+def test_interface_exchange_protocol_on_the_host(tmp_path):
+    """The source of the NVLink peer-memory interface exchange (csrc/iface_xchg.cuh: slot tables + k_iface_xchg) compiled for the
+    CPU -- one std::thread per CUDA thread, C++ atomics for the flag traffic (tests/cuda_host_shim/xchg_emulation.cpp): 4-5 ranks
+    drifting up to one exchange apart over many launches, capped grids with grid-stride phases, vertices on up to 3 ranks.
+    Consistent copies must be bitwise equal to the rank-ordered sum; under ThreadSanitizer no window access may race; and a mutant
+    with single-buffered windows must be caught (the harness can fail)."""
+    import shutil
+    if not shutil.which("g++"):
+        pytest.skip("no C++ compiler")
+    src = os.path.join(ROOT, "tests", "cuda_host_shim", "xchg_emulation.cpp")
+    inc = os.path.join(ROOT, "admm_optim_b200", "csrc")
+    base = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-ffp-contract=off", "-w"]
+
+    def build(out, include, tsan):
+        r = subprocess.run(base + (["-fsanitize=thread"] if tsan else []) + ["-I" + include, src, "-o", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        return out
+
+    plain = build(str(tmp_path / "xchg"), inc, False)
+    for cfg in (["4", "3", "60", "8", "3", "8"], ["5", "2", "300", "12", "2", "4"], ["2", "3", "40", "6", "1", "4"], ["3", "1", "50", "9", "4", "2"]):
+        r = subprocess.run([plain] + cfg, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout[-2000:]
+    probe = subprocess.run(base + ["-fsanitize=thread", "-x", "c++", "-", "-o", str(tmp_path / "probe")], input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
+        return                                              # no ThreadSanitizer runtime on this machine: the functional part stands
+    tsan = build(str(tmp_path / "xchg_tsan"), inc, True)
+    r = subprocess.run([tsan, "4", "3", "60", "12", "3", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "data race" not in r.stderr and r.stdout.startswith("OK"), (r.stdout + r.stderr)[-3000:]
+    mut = tmp_path / "mut"
+    mut.mkdir()
+    text = open(os.path.join(inc, "iface_xchg.cuh")).read()
+    assert "const int parity = (int)(epoch & 1ull);" in text
+    (mut / "iface_xchg.cuh").write_text(text.replace("const int parity = (int)(epoch & 1ull);", "const int parity = 0;"))
+    bad = build(str(tmp_path / "xchg_mut"), str(mut), True)
+    r = subprocess.run([bad, "4", "3", "60", "30", "3", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 or "data race" in r.stderr, "single-buffered windows went unnoticed"
