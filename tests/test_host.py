@@ -623,7 +623,7 @@ def test_bench_line_survives_a_failing_or_hanging_secondary_leg(mode):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py"), "--refs", "1", "--roofline-refs", "1", "--admm-refs", "0", "--dim2-refs", "2",
-                        "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--legs-timeout", "25" if mode == "hang" else "600"],
+                        "--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--legs-timeout", "10" if mode == "hang" else "600"],
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])

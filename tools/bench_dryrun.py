@@ -75,7 +75,7 @@ class _Domain(ug4_np.Domain):
 class FakeBackend(ug4_np.Backend):
     name = "dryrun"
     def __init__(self, device=0, stream=None, distributed=False):
-        super().__init__(smoother="cheb")
+        super().__init__(smoother="cheb", threads=1, fast_assembly=True, c_solver=True)   # compiled oracle paths: the dry runs stay short
         self.rank, self.nranks = (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))) if distributed else (0, 1)
         self._distributed = bool(distributed)
         self.util.solver.CreateSolver = lambda desc: _Solver(self, desc)
