@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "iface_xchg.cuh"
+#include "gershgorin_dist.cuh"
 
 namespace ab {
 
@@ -81,18 +82,6 @@ struct Interface {
 };
 
 
-__global__ void k_iface_pack(int total, int D, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total * D; t += gridDim.x * blockDim.x) {
-        const int k = t / D, c = t - k * D;
-        buf[t] = v[(int64_t)idx[k] * D + c];
-    }
-}
-__global__ void k_iface_unpack_add(int total, int D, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ v) {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total * D; t += gridDim.x * blockDim.x) {
-        const int k = t / D, c = t - k * D;
-        atomicAdd(v + (int64_t)idx[k] * D + c, buf[t]);
-    }
-}
 // zero the copies this rank does not own (consistent -> unique, a valid additive representation)
 __global__ void k_zero_not_owned(int64_t n, int D, const unsigned char* __restrict__ owned, double* __restrict__ v) {
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)

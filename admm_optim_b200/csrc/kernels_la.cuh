@@ -5,6 +5,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "gershgorin_dist.cuh"
 
 namespace ab {
 namespace cg = cooperative_groups;
@@ -206,23 +207,6 @@ __global__ void k_bicg_roll(double* sc, const double* out2) {
     sc[SC_RR] = out2[0];
     sc[SC_RHO] = out2[1];
 }
-// point-Jacobi data, distributed: additive diagonal and additive absolute row sums (made consistent by an interface sum)
-template <int D>
-__global__ void k_diag_rowabs(int nb, const int* __restrict__ rowptr, const int* __restrict__ diagpos, const double* __restrict__ vals,
-                              double* __restrict__ diag, double* __restrict__ rowabs) {
-    constexpr int DD = D * D;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nb * D; t += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(t / D), r = (int)(t - (int64_t)row * D);
-        const int s = rowptr[row], e = rowptr[row + 1];
-        double sum = 0.0;
-        for (int k = s; k < e; ++k) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) sum += fabs(vals[(int64_t)k * DD + r * D + c]);
-        }
-        diag[t] = vals[(int64_t)diagpos[row] * DD + r * D + r];
-        rowabs[t] = sum;
-    }
-}
 // point-Jacobi data from consistent diagonal / row sums with two row-sum variants: red[0] = max rows_a / a_ii, red[1] = max rows_b / a_ii
 __global__ void __launch_bounds__(256) k_dinv_lmax2(int64_t n, double* __restrict__ diag_to_dinv, const double* __restrict__ rows_a,
                                                     const double* __restrict__ rows_b, double* partials, unsigned int* ticket, double* red) {
@@ -234,28 +218,6 @@ __global__ void __launch_bounds__(256) k_dinv_lmax2(int64_t n, double* __restric
         mx[1] = fmax(mx[1], rows_b[t] / aii);
     }
     grid_reduce<2, 1>(mx, partials, ticket, red);
-}
-// exact row sums of an additive operator (multi-GPU): compact copy of the blocks shared with neighbour ranks ...
-__global__ void k_pack_blocks(int64_t n, int DD, const int* __restrict__ bpos, const double* __restrict__ vals, double* __restrict__ cv) {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = t / DD;
-        cv[t] = vals[(int64_t)bpos[k] * DD + (t - k * DD)];
-    }
-}
-// ... and, once the neighbours' parts were added to cv, the correction of the local row sums: every rank holding a shared block
-// contributes |sum| / mult instead of |its own part|, so that the interface sum of the rows counts |sum| exactly once
-template <int D>
-__global__ void k_rowabs_fix(int nsb, const int* __restrict__ bpos, const int* __restrict__ brow, const int* __restrict__ mult,
-                             const double* __restrict__ vals, const double* __restrict__ cv, double* rowabs) {
-    constexpr int DD = D * D;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < (int64_t)nsb * D; t += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(t / D), r = (int)(t - (int64_t)k * D);
-        const double inv = 1.0 / (double)mult[k];
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < D; ++c) s += fabs(cv[(int64_t)k * DD + r * D + c]) * inv - fabs(vals[(int64_t)bpos[k] * DD + r * D + c]);
-        atomicAdd(rowabs + (int64_t)brow[k] * D + r, s);
-    }
 }
 // ---------------------------------------------------------------------------------------------
 // BSR SpMV family (k_bsr_spmv_tma: default; k_bsr_spmv_warp: fallback when a row exceeds a tile).

@@ -124,7 +124,47 @@ for n, q in enumerate(It["neigh"]):
     np.add.at(tot, Bt["slot_block"][Bt["offsets"][n]:Bt["offsets"][n + 1]], ev[int(q)][rank])
 np.add.at(rowabs, Bt["brow"], np.abs(tot) / Bt["mult"] - np.abs(vals[Bt["bpos"]]))
 exact = vertex_sum(rowabs)
-rows = gather((lt["xyz"], exact, loose))
+# the same steps through the kernel SOURCE of the library compiled for the host (tests/cuda_host_shim/gershgorin_emulation.cpp,
+# path in ADMM_B200_GERSH_EMU): d x d blocks a_ij * M with a sign-mixed M, every kernel of lib.cu gmg_setup_kernels' exact-bound
+# branch in its order; the result must be the global scalar row sums times the absolute row sums of M
+emu_path = os.environ.get("ADMM_B200_GERSH_EMU")
+emu_worst = None
+if emu_path:
+    emu = C.CDLL(emu_path)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    d = lt["xyz"].shape[1]
+    DD = d * d
+    M = np.array([[1.0, -0.3, 0.2], [0.25, 1.0, -0.5], [-0.125, 0.4, 1.0]])[:d, :d]
+    bvals = np.ascontiguousarray((vals[:, None, None] * M[None]).reshape(-1))
+    diagpos = np.ascontiguousarray(np.array([rp[i] + np.searchsorted(ci[rp[i]:rp[i + 1]], i) for i in range(nvt)], np.int32))
+    diag, rab = np.zeros(nvt * d), np.zeros(nvt * d)
+    emu.emu_diag_rowabs(d, nvt, ip(rp), ip(diagpos), dp(bvals), dp(diag), dp(rab))
+    assert np.array_equal(diag.reshape(nvt, d), vals[diagpos][:, None] * np.diag(M)[None])
+    nsb = len(Bt["bpos"])
+    bpos, brow, mult, slotb = (np.ascontiguousarray(Bt[k], np.int32) for k in ("bpos", "brow", "mult", "slot_block"))
+    cvb = np.zeros(max(nsb, 1) * DD)
+    emu.emu_pack_blocks(C.c_int64(nsb * DD), DD, ip(bpos), dp(bvals), dp(cvb))
+    totalb = int(Bt["offsets"][-1])
+    send, recv = np.zeros(max(totalb, 1) * DD), np.zeros(max(totalb, 1) * DD)
+    emu.emu_iface_pack(totalb, DD, ip(slotb), dp(cvb), dp(send))
+    evb = gather({int(q): send[Bt["offsets"][n] * DD:Bt["offsets"][n + 1] * DD] for n, q in enumerate(It["neigh"])})     # ncclSend / ncclRecv
+    for n, q in enumerate(It["neigh"]):
+        recv[Bt["offsets"][n] * DD:Bt["offsets"][n + 1] * DD] = evb[int(q)][rank]
+    emu.emu_iface_unpack_add(totalb, DD, ip(slotb), dp(recv), dp(cvb))
+    emu.emu_rowabs_fix(d, nsb, ip(bpos), ip(brow), ip(mult), dp(bvals), dp(cvb), dp(rab))
+    # interface sum of the rows (exchange_sum; its own kernel is covered by tests/cuda_host_shim/xchg_emulation.cpp): the NCCL form
+    total_v = int(It["offsets"][-1])
+    idx_v = np.ascontiguousarray(It["idx"], np.int32)
+    sendv, recvv = np.zeros(max(total_v, 1) * d), np.zeros(max(total_v, 1) * d)
+    emu.emu_iface_pack(total_v, d, ip(idx_v), dp(rab), dp(sendv))
+    evv = gather({int(q): sendv[It["offsets"][n] * d:It["offsets"][n + 1] * d] for n, q in enumerate(It["neigh"])})
+    for n, q in enumerate(It["neigh"]):
+        recvv[It["offsets"][n] * d:It["offsets"][n + 1] * d] = evv[int(q)][rank]
+    emu.emu_iface_unpack_add(total_v, d, ip(idx_v), dp(recvv), dp(rab))
+    want = exact[:, None] * np.abs(M).sum(axis=1)[None]          # `exact` was checked against the global operator below
+    emu_worst = float(np.abs(rab.reshape(nvt, d) - want).max() / want.max())
+rows = gather((lt["xyz"], exact, loose, emu_worst))
 gersh = dict(ok=True)
 if rank == 0:
     gdom = ug4.Domain(ug)
@@ -134,11 +174,13 @@ if rank == 0:
     Ag = stiffness(gl2["xyz"], gl2["elems"])
     lut = {tuple(x): v for x, v in zip(gl2["xyz"].tolist(), np.abs(Ag).sum(axis=1).A1)}
     worst, differing = 0.0, 0
-    for Xr, ex, lo in rows:
+    for Xr, ex, lo, _ in rows:
         ref = np.array([lut[tuple(x)] for x in Xr.tolist()])
         worst = max(worst, float(np.abs(ex - ref).max() / ref.max()))
         differing += int((np.abs(lo - ref) > 1e-9 * ref.max()).sum())
-    gersh = dict(ok=bool(worst < 1e-12), worst=worst, rows_where_loose_differs=differing, shared_blocks=int(len(Bt["bpos"])))
+    emu_all = [r[3] for r in rows]
+    gersh = dict(ok=bool(worst < 1e-12) and all(e is None or e < 1e-12 for e in emu_all), worst=worst, rows_where_loose_differs=differing,
+                 shared_blocks=int(len(Bt["bpos"])), kernel_source_emulation_worst=emu_all)
 allres = gather(dict(decomposed=True, gather_level=lg, levels=res, blocks_ok=ok, gershgorin=gersh))
 if rank == 0:
     print(json.dumps(allres))

@@ -151,9 +151,30 @@ def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
     assert outs[1] == ""
 
 
+_GERSH_EMU = {}
+
+
+def _gershgorin_emulation_library():
+    """tests/cuda_host_shim/gershgorin_emulation.cpp (the library's exact-Gershgorin / pack / unpack kernel SOURCE compiled for the
+    host) as a shared library, built once per session; None without a C++ compiler."""
+    import shutil
+    import tempfile
+    if "path" not in _GERSH_EMU:
+        _GERSH_EMU["path"] = None
+        if shutil.which("g++"):
+            out = os.path.join(tempfile.mkdtemp(prefix="ab_emu_"), "libgersh_emu.so")
+            r = subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-w", "-I" + os.path.join(ROOT, "admm_optim_b200", "csrc"),
+                                os.path.join(ROOT, "tests", "cuda_host_shim", "gershgorin_emulation.cpp"), "-o", out], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-3000:]
+            _GERSH_EMU["path"] = out
+    return _GERSH_EMU["path"]
+
+
 def _run_dist_host_workers(grid, refs, gather_dofs, port, world=2):
     import json
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), ADMM_B200_GATHER_DOFS=str(gather_dofs))
+    if _gershgorin_emulation_library():
+        env["ADMM_B200_GERSH_EMU"] = _gershgorin_emulation_library()
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_host_worker.py"), grid, str(refs)],
                               env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
     outs = []
@@ -175,6 +196,9 @@ def test_partition_and_interfaces_gloo_world_size_2(grid, refs, counts, gather_d
     assert res[0]["blocks_ok"]
     # exact Gershgorin rows through the shared-block lists (NumPy twin of the device steps) = rows of the global operator
     assert res[0]["gershgorin"]["ok"] and res[0]["gershgorin"]["shared_blocks"] > 0, res[0]["gershgorin"]
+    if _gershgorin_emulation_library():      # the kernel source of the library, compiled for the host, gave the global row sums on every rank
+        emu = res[0]["gershgorin"]["kernel_source_emulation_worst"]
+        assert len(emu) == 2 and all(e is not None and e < 1e-12 for e in emu), emu
     lv = [r["levels"] for r in res]
     for level in range(refs + 1):
         assert sum(r[level]["owned"] for r in lv) == counts[level]
@@ -191,6 +215,8 @@ def test_partition_with_vertices_shared_by_four_ranks_gloo_world_size_4():
     assert all(r["decomposed"] and r["gather_level"] == 1 for r in res) and res[0]["blocks_ok"]
     g = res[0]["gershgorin"]
     assert g["ok"] and g["rows_where_loose_differs"] > 0 and g["shared_blocks"] > 0, g
+    if _gershgorin_emulation_library():
+        assert len(g["kernel_source_emulation_worst"]) == 4 and all(e is not None and e < 1e-12 for e in g["kernel_source_emulation_worst"]), g
     lv = [r["levels"] for r in res]
     for level, count in enumerate([338, 2124, 14910]):
         assert sum(r[level]["owned"] for r in lv) == count
