@@ -149,6 +149,9 @@ def test_bench_reference_arm_runs_under_gloo_world_size_2(tmp_path):
     line = json.loads(outs[0])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert outs[1] == ""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.common_config(0)          # the driver compares the two arms' `config`: one object for both
 
 
 _GERSH_EMU = {}
@@ -451,6 +454,9 @@ def test_bench_b200_arm_dry_run_produces_the_full_line():
                 "gmg_init_ms", "assemble_ms", "admm_refs1", "admm_2d_refs2", "elementwise_roofline", "bicgstab_its_per_step"):
         assert key in line, key
     assert line["parity"]["ok"] and "workload" in line["config"] and "error" not in line["elementwise_roofline"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.common_config(1)           # identical to the reference arm's for the same --refs
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"]) and line["e2e"]["h2d_bytes_per_step"] > 0
 
