@@ -78,7 +78,8 @@ AB_XCHG_KERNEL k_iface_xchg(int niv, int D, int nneigh, int my_pos, const int* _
                                                     const unsigned long long* __restrict__ peer_stride, const unsigned long long* __restrict__ peer_flag,
                                                     int total, const double* my_recv, unsigned long long* my_flags, unsigned long long* state,
                                                     int* err, double* v, const double* cf, const double* din, const double* xin, double* xout) {
-    // The grid is capped by the host (kXchgCtasPerSm CTAs per SM, far below the residency limit of this 32-register kernel): every
+    // The grid is capped by the host (lib.cu launch_xchg: three quarters of the residency limit of this 32-register kernel, at least
+    // kXchgCtasPerSm CTAs per SM): every
     // CTA of the grid is resident while it waits for the neighbours, so the CTAs that still have to store can always run -- a grid
     // larger than the device could hold would dead-lock against the neighbour's equally oversized grid.  The entries are therefore
     // walked with a grid-stride loop, in the put phase and again in the sum phase.

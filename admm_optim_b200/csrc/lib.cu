@@ -70,6 +70,7 @@ struct Domain {
     // without interfaces on a multi-rank context is a plain local (replicated) domain.  Shared-vertex interfaces per level
     // (host staging until finalize):
     bool dist_enabled = false;
+    int xchg_ctas_per_sm = 0;          // grid cap of the interface-exchange kernel (launch_xchg), set at finalize
     struct HostIface { std::vector<int> neigh, offset, idx; std::vector<unsigned char> owned; };
     std::vector<HostIface> host_iface;
     std::vector<Interface> iface;
@@ -195,6 +196,11 @@ void Domain::finalize() {
         AB_REQUIRE((int)host_iface.size() == nl, AB_ERR_STATE, "multi-GPU: ab_domain_set_interface must be called for every level before the first ApproximationSpace");
         AB_REQUIRE(gather_level >= 0 && gather_level < nl - 1, AB_ERR_STATE, "multi-GPU: ab_domain_set_gather missing (the gather level must lie below the top level)");
         iface.resize(nl);
+        {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_iface_xchg<true>, 256, 0) != cudaSuccess) { occ = 0; (void)cudaGetLastError(); }
+            xchg_ctas_per_sm = occ * 3 / 4;
+        }
         const int me = ctx->comm->rank;
         for (int l = 0; l < nl; ++l) {
             HostIface& H = host_iface[l];
@@ -241,8 +247,11 @@ void Domain::finalize() {
 // interface sum: additive -> consistent for a P1 vector with D components on `level`
 static void launch_xchg(Domain* dom, Interface& I, int D, bool smooth, double* v, const double* cf, const double* din, const double* xin, double* xout) {
     Context* ctx = dom->ctx;
-    // capped grid: all CTAs are resident while they wait for the neighbours (see k_iface_xchg); larger interfaces are strided
-    const int g = std::max(1, std::min((I.niv * D + 255) / 256, kXchgCtasPerSm * ctx->num_sms));
+    // capped grid: all CTAs are resident while they wait for the neighbours (see k_iface_xchg); larger interfaces are strided.
+    // Cap = three quarters of what the device can hold of this kernel (occupancy query at finalize; 8 CTAs per SM -> 6), never below
+    // kXchgCtasPerSm: interfaces up to ~ 227 k entries (numRefs 5 on 8 GPUs: 868 CTAs) still get one thread per entry.
+    const int per_sm = std::max(kXchgCtasPerSm, dom->xchg_ctas_per_sm);      // Domain::finalize
+    const int g = std::max(1, std::min((I.niv * D + 255) / 256, per_sm * ctx->num_sms));
     if (smooth)
         AB_LAUNCH(ctx, (k_iface_xchg<true>), g, 256, 0, I.niv, D, (int)I.neigh.size(), I.my_pos, I.iv.p, I.iv_ptr.p, I.iv_slot.p, I.iv_nb.p, I.d_offset.p, I.d_neigh.p,
                   I.d_peer_dst.p, I.d_peer_stride.p, I.d_peer_flag.p, I.total, I.win_recv, I.win_flags, I.state.p, dom->p2p_err.p, v, cf, din, xin, xout);
